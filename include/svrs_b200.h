@@ -1,0 +1,201 @@
+/*
+ * svrs_b200.h - C ABI of the B200-native (sm_100a) kernels behind the Simple-VAE-RS training step.
+ *
+ * The reference (Etienne-bdt/Simple-VAE-RS) has no FFI layer: its hot path is Python calling
+ * torch.nn / torch.nn.functional.  Each entry point below therefore cites the reference CALL SITE
+ * whose arithmetic it replaces (file:line into the reference tree).  The Python host code in
+ * simple-vae-rs_b200/ binds these with ctypes and keeps the reference's
+ * Python API (models.VAE / models.Cond_SRVAE / loss.base_loss / loss.cond_loss / fit()).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; the library never allocates, frees,
+ *     or synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - activations are NHWC ("pixel-major"): [N][H][W][C], dtype SVRS_F32 or SVRS_BF16.
+ *   - weights are consumed in packed per-tap form produced by svrs_pack_weights():
+ *         KN pack: [tap][K][N]   (tap = ky*ksize + kx, K = reduction channels, N = output channels)
+ *   - return value: 0 = enqueued, <0 = error (SVRS_E_*); svrs_last_error() gives the message.
+ *   - thread-safety: calls are re-entrant; the error string is thread-local.
+ */
+#ifndef SVRS_B200_H
+#define SVRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVRS_F32 0
+#define SVRS_BF16 1
+
+#define SVRS_ACT_NONE 0
+#define SVRS_ACT_SIGMOID 1  /* nn.Sigmoid   - cond_vae.py:80,143 ; vae.py:84 */
+#define SVRS_ACT_HARDTANH7 2 /* nn.Hardtanh(-7,7) - cond_vae.py:230 */
+
+#define SVRS_E_ARG (-1)
+#define SVRS_E_CUDA (-2)
+#define SVRS_E_UNSUPPORTED (-3)
+
+const char* svrs_last_error(void);
+int svrs_abi_version(void);
+/* compute capability major*10+minor of device `dev`, or <0 */
+int svrs_device_cc(int dev);
+
+/* ---- layout glue: nn.Flatten / nn.Unflatten / torch.chunk / torch.cat views
+ *      (cond_vae.py:47,52,106,111,163,168,188,192,209,212,229,240-244,254,259,272).
+ *      NCHW is the reference's (API-facing) order, NHWC the internal one.  `src_ld`/`dst_ld` are the
+ *      per-sample strides (elements) of the NCHW side so that a [B, C*H*W] slice of a wider flat
+ *      latent row (torch.cat / torch.chunk) can be addressed in place. */
+int svrs_nchw_to_nhwc(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype,
+                      int N, int C, int H, int W, void* stream);
+int svrs_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t dst_ld,
+                      int N, int C, int H, int W, int accumulate, void* stream);
+
+/* ---- weight packing: torch layout w[d0][d1][kk] (fp32 master) -> p01[kk][d0][d1], p10[kk][d1][d0]
+ *      in `dtype`.  nn.Conv2d weight is [Cout][Cin][k][k] (layers.py:231-236), nn.ConvTranspose2d
+ *      weight is [Cin][Cout][k][k] (layers.py:275-277).  Either output may be NULL. */
+int svrs_pack_weights(const float* w, int d0, int d1, int kk, void* p01, void* p10, int dtype,
+                      void* stream);
+
+/* ---- nn.Conv2d k3 s1 p1 / k4 s2 p1 (layers.py:231-236; every bare nn.Conv2d of cond_vae.py / vae.py)
+ *      x [N,H,W,Cin] -> y [N,H/s,W/s,Cout];  w_kn = p10 pack [tap][Cin][Cout]; bias fp32 [Cout] or NULL.
+ *      ksize 3 => stride 1, ksize 4 => stride 2 (pad 1 both). */
+int svrs_conv2d_fprop(const void* x, const void* w_kn, const float* bias, void* y, int dtype,
+                      int N, int H, int W, int Cin, int Cout, int ksize, int act, void* stream);
+/* dgrad: dy [N,H/s,W/s,Cout] -> dx [N,H,W,Cin]; w_kn = p01 pack [tap][Cout][Cin].
+ * (autograd of the same call sites, reached through loss.backward() models/base.py:105) */
+int svrs_conv2d_dgrad(const void* dy, const void* w_kn, void* dx, int dtype,
+                      int N, int H, int W, int Cin, int Cout, int ksize, void* stream);
+/* wgrad: dw[Cout][Cin][k][k] += sum x (*) dy  (fp32, torch layout, ATOMIC accumulate - zero it first);
+ * db[Cout] += column sums of dy when db != NULL.  `ksplit` <= 0 picks a split automatically. */
+int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float* db, int dtype,
+                      int N, int H, int W, int Cin, int Cout, int ksize, int ksplit, void* stream);
+
+/* ---- nn.ConvTranspose2d k4 s2 p1 (layers.py:275-277): x [N,H,W,Cin] -> y [N,2H,2W,Cout].
+ *      four output-parity sub-convolutions of 2x2 taps.  w_kn = p01 pack [tap][Cin][Cout]. */
+int svrs_convT2d_fprop(const void* x, const void* w_kn, const float* bias, void* y, int dtype,
+                       int N, int H, int W, int Cin, int Cout, int act, void* stream);
+/* dgrad: dy [N,2H,2W,Cout] -> dx [N,H,W,Cin]; w_kn = p10 pack [tap][Cout][Cin]. */
+int svrs_convT2d_dgrad(const void* dy, const void* w_kn, void* dx, int dtype,
+                       int N, int H, int W, int Cin, int Cout, void* stream);
+/* wgrad: dw[Cin][Cout][4][4] += ... ; db[Cout] += column sums of dy. */
+int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, float* db, int dtype,
+                       int N, int H, int W, int Cin, int Cout, int ksplit, void* stream);
+
+/* ---- nn.BatchNorm2d (+ nn.ReLU) of down_block / up_block (layers.py:237-238,252-255,278-279,293-296)
+ *      x viewed as [M = N*H*W][C].  `sums` is a zeroed double[2*C] scratch (sum, sum of squares). */
+int svrs_bn_stats(const void* x, int dtype, int64_t M, int C, double* sums, void* stream);
+/* train: batch stats -> scale/shift (+ saved mean/invstd), running stats updated `n_updates` times
+ * (y_to_z runs twice per forward) and *num_batches_tracked += n_updates (may be NULL). */
+int svrs_bn_finalize_train(const double* sums, int64_t M, int C, const float* gamma, const float* beta,
+                           float eps, float momentum, float* running_mean, float* running_var,
+                           int64_t* num_batches_tracked, int n_updates,
+                           float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* eval: scale/shift from the running statistics */
+int svrs_bn_finalize_eval(int C, const float* gamma, const float* beta, float eps,
+                          const float* running_mean, const float* running_var,
+                          float* scale, float* shift, void* stream);
+/* y = relu?(x*scale[c] + shift[c]) ; in-place (y == x) allowed */
+int svrs_bn_apply(const void* x, void* y, int dtype, int64_t M, int C, const float* scale,
+                  const float* shift, int relu, void* stream);
+/* backward of BN(train)+ReLU.  x = pre-BN conv output, dy = grad wrt the block output.
+ * pass 1: sums[0:C] = sum dy*mask, sums[C:2C] = sum dy*mask*xhat (double, zeroed by caller) */
+int svrs_bn_bwd_reduce(const void* x, const void* dy, int dtype, int64_t M, int C, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu,
+                       double* sums, void* stream);
+/* pass 2: dx = gamma*invstd*(dym - mean(dym) - xhat*mean(dym*xhat)); dgamma += sums[C:], dbeta += sums[:C] */
+int svrs_bn_bwd_apply(const void* x, const void* dy, void* dx, int dtype, int64_t M, int C,
+                      const float* scale, const float* shift, const float* mean, const float* invstd,
+                      const float* gamma, int relu, const double* sums, float* dgamma, float* dbeta,
+                      void* stream);
+
+/* ---- reparameterize (cond_vae.py:261-265, vae.py:94-98) on the NCHW-flat encoder output
+ *      enc [B][2*Wd] fp32 (mu = enc[:, :Wd], logvar = enc[:, Wd:], torch.chunk cond_vae.py:254,259).
+ *      z[b][j] = mu + eps*exp(0.5*logvar).  eps: injected tensor [B][Wd] (eps != NULL) or on-device
+ *      Philox4x32-10 keyed by (seed, stream_id, sample_offset+b, j).  eps_out (may be NULL) receives the
+ *      draws.  Backward: denc[:, :Wd] += dz ; denc[:, Wd:] += dz*eps*0.5*std  (eps regenerated). */
+int svrs_reparam_fwd(const float* enc, const float* eps, float* z, int64_t z_ld, float* eps_out, int B, int Wd,
+                     uint64_t seed, uint32_t stream_id, uint64_t sample_offset, const int64_t* step_ptr,
+                     void* stream);
+int svrs_reparam_bwd(const float* enc, const float* eps, const float* dz, int64_t dz_ld, float* denc, int B, int Wd,
+                     uint64_t seed, uint32_t stream_id, uint64_t sample_offset, const int64_t* step_ptr,
+                     void* stream);
+/* test hook: n standard normals from the same generator convention (row b = i / Wd, col = i % Wd).
+ * step_ptr (device, may be NULL => 0) supplies Philox counter word 3 so a captured CUDA graph draws fresh
+ * noise every replay; z_ld / dz_ld are row strides (elements) so z can live inside a torch.cat buffer. */
+int svrs_philox_normal(float* out, int B, int Wd, uint64_t seed, uint32_t stream_id,
+                       uint64_t sample_offset, const int64_t* step_ptr, void* stream);
+
+/* ---- Gaussian ELBO terms: loss/cond_vae_loss.py:39-58 and loss/vae_loss.py:8-13.
+ * A term set is described by up to two NLL pairs, one KL-to-N(0,I) and one KL(q2||p3):
+ *   nll k:  ssq_k = sum (recon_k - target_k)^2 over n_k elements (any common layout, dtype given)
+ *   kl1  :  sum_b sum_j (mu1^2 + exp(lv1) - 1 - lv1)              rows of width W1, row stride ld1
+ *   kl23 :  sum (lv3 - lv2 - 1) + exp(lv2 - lv3) + (mu2-mu3)^2 exp(-lv3)   width W2, strides ld2/ld3
+ * fwd accumulates the four raw sums in double acc[4] = {ssq_x, ssq_y, kl1, kl23} (zeroed by caller);
+ * finalize turns them into the reference's terms out[5] = {mse_x, kld_u, mse_y, kld_z, their sum} (fp32):
+ *   mse = ssq/(2 g^2) + n log g ;  kld = 0.5 * sum / B.   Unused pieces: pass NULL / n = 0. */
+int svrs_elbo_fwd(const void* recon_x, const void* x, int dt_x, int64_t n_x,
+                  const void* recon_y, const void* y, int dt_y, int64_t n_y,
+                  const float* mu1, const float* lv1, int64_t ld1, int W1,
+                  const float* mu2, const float* lv2, int64_t ld2,
+                  const float* mu3, const float* lv3, int64_t ld3, int W2,
+                  int B, double* acc, void* stream);
+int svrs_elbo_finalize(const double* acc, int64_t n_x, int64_t n_y, int B, const float* gammas /*[2] x,y*/,
+                       float* out5, void* stream);
+/* backward.  gout[4] = upstream grads of {mse_x, kld_u, mse_y, kld_z} (device).  Any output may be NULL.
+ * d_recon = g*(r - t)/gamma^2 ; d_gamma[k] = g*(-ssq/gamma^3 + n/gamma)
+ * d_mu1 = g*mu1/B ; d_lv1 = g*0.5*(exp(lv1)-1)/B
+ * d_mu2 = g*(mu2-mu3)exp(-lv3)/B = -d_mu3 ; d_lv2 = g*0.5*(exp(lv2-lv3)-1)/B
+ * d_lv3 = g*0.5*(1 - exp(lv2-lv3) - (mu2-mu3)^2 exp(-lv3))/B
+ * latent grads are written with the same row strides as their inputs (dst strides dld1/dld2/dld3). */
+int svrs_elbo_bwd(const void* recon_x, const void* x, int dt_x, int64_t n_x, void* d_recon_x,
+                  const void* recon_y, const void* y, int dt_y, int64_t n_y, void* d_recon_y,
+                  const float* mu1, const float* lv1, int64_t ld1, int W1, float* d_mu1, float* d_lv1, int64_t dld1,
+                  const float* mu2, const float* lv2, int64_t ld2, float* d_mu2, float* d_lv2, int64_t dld2,
+                  const float* mu3, const float* lv3, int64_t ld3, int W2, float* d_mu3, float* d_lv3, int64_t dld3,
+                  int B, const double* acc, const float* gammas, const float* gout, float* d_gammas,
+                  void* stream);
+
+/* ---- clip_grad_norm_(params, 1.0) + torch.optim.Adam (models/base.py:106-107, train.py:65) on flat buffers */
+int svrs_sumsq(const float* g, int64_t n, double* acc /* += */, void* stream);
+/* step_ptr: device int64 holding the 1-based step number t (bias corrections 1-b^t computed on device).
+ * sumsq == NULL => no clipping (the gamma param group).
+ * coef = min(1, max_norm/(sqrt(*sumsq)+1e-6)); g is NOT modified; p,m,v updated in place.
+ * grad_scale multiplies g first (1/world_size after a SUM all-reduce). */
+int svrs_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const double* sumsq,
+                   float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
+                   const int64_t* step_ptr, void* stream);
+int svrs_step_increment(int64_t* step_ptr, void* stream);
+
+/* ---- grid patching + per-patch per-channel min-max normalisation
+ *      (dataset.py:220-247,265-274 ; utils.py:4-23).  tiles [T][C][S][S] (fp32, or int16 when
+ *      src_is_i16) -> patches [(T*(S/P)^2)][...], patch index = tile*(S/P)^2 + row*(S/P) + col.
+ *      dst layout NCHW (nhwc=0) or NHWC (nhwc=1), dtype dst_dtype.  fp32 output is bit-exact with
+ *      the reference: (x - min) / ((max - min) + 1e-5f). */
+int svrs_grid_patch_normalize(const void* tiles, int src_is_i16, void* dst, int dst_dtype, int nhwc,
+                              int T, int C, int S, int P, void* stream);
+
+/* ---- backward of the fused epilogue activations from their OUTPUT y:
+ *      sigmoid: dx = dy*y*(1-y) ; hardtanh(-7,7): dx = dy if -7 < y < 7 else 0.  In-place (dx == dy) allowed. */
+int svrs_act_bwd(const void* y, const void* dy, void* dx, int dtype, int act, int64_t n, void* stream);
+
+/* ---- strided row copy (torch.cat / torch.chunk along channels, cond_vae.py:244,272):
+ *      dst[r*dst_ld + c] (+)= src[r*src_ld + c], r < rows, c < cols, with dtype conversion */
+int svrs_copy2d(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
+                int64_t rows, int cols, int accumulate, void* stream);
+
+/* ---- misc elementwise helpers used by the host runtime */
+int svrs_fill_zero(void* p, int64_t bytes, void* stream);
+int svrs_axpy_f32(float* y, const float* x, float a, int64_t n, void* stream); /* y += a*x */
+int svrs_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+/* ---- host-only test hook: dump the multi-tap GEMM geometry of a conv form (no device work).
+ *      form 0 conv3 fprop, 1 conv3 dgrad, 2 conv4s2 fprop (= convT dgrad), 3 convT4s2 fprop (= conv4s2 dgrad);
+ *      H, W, Cr describe the tensor being READ, Cw the channels written.  See csrc/conv_simt.cu for the layout
+ *      of `out`; returns the number of int64 written (<0 on error). */
+int svrs_debug_tap_geometry(int form, int N, int H, int W, int Cr, int Cw, int64_t* out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVRS_B200_H */

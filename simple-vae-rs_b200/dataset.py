@@ -1,0 +1,109 @@
+"""Data side of the hot path: grid-mode patching + per-patch normalisation on the device.
+
+Reference: dataset.py `select_crop` (:220-228), `grid_crop` (:230-247), `grid_collate` (:265-274),
+`prepare_patches` (:249-262) and utils.normalize_image (utils.py:4-23) - a 256x256 HR tile (and its 128x128 LR
+twin) becomes 16 patches of 64x64 (32x32), patch index = row*4 + col, each patch min-max normalised per channel,
+batches ordered tile-major.  Here that is ONE kernel launch per tensor (svrs_grid_patch_normalize, one CTA per
+patch, bit-exact fp32) instead of CPU slicing in DataLoader workers.
+
+The GeoTIFF / CSV reading of the reference's Sen2VenDataset (:49-218, tifffile + polars) is disk IO outside the
+hot-path scope; `TileDataset` wraps tiles that are already in memory (decoded by any reader) and
+`synthetic_tiles` produces the multispectral test tiles used by the benchmark.
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Tuple
+
+import torch
+
+
+def grid_patch_normalize(tiles: torch.Tensor, patch_size: int, out_dtype=torch.float32, nhwc: bool = False) -> torch.Tensor:
+    """tiles [T,C,S,S] (fp32 or int16, CUDA) -> patches [T*(S/P)^2, C, P, P] (or [.., P, P, C] if nhwc)."""
+    from svrs_native.lib import BF16, F32, lib
+
+    if not tiles.is_cuda:
+        raise RuntimeError("grid_patch_normalize: tiles must be on a CUDA device (no CPU fallback)")
+    if tiles.dtype not in (torch.float32, torch.int16):
+        tiles = tiles.float()
+    tiles = tiles.contiguous()
+    T, C, S, S2 = tiles.shape
+    assert S == S2 and S % patch_size == 0
+    n = T * (S // patch_size) ** 2
+    shape = (n, patch_size, patch_size, C) if nhwc else (n, C, patch_size, patch_size)
+    out = torch.empty(shape, device=tiles.device, dtype=out_dtype)
+    lib.grid_patch_normalize(tiles.data_ptr(), int(tiles.dtype == torch.int16), out.data_ptr(),
+                             F32 if out_dtype == torch.float32 else BF16, int(nhwc), T, C, S, patch_size,
+                             torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+def grid_batch(lr_tiles: torch.Tensor, hr_tiles: torch.Tensor, patch_size: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(LR tiles [T,4,S/2,S/2], HR tiles [T,4,S,S]) -> (y, x) patch batch in the (y, x) order of
+    Cond_SRVAE.train_step (cond_vae.py:327)."""
+    return grid_patch_normalize(lr_tiles, patch_size // 2), grid_patch_normalize(hr_tiles, patch_size)
+
+
+def synthetic_tiles(n_tiles: int, size: int = 256, seed: int = 1, device="cpu", as_int16: bool = False):
+    """Synthetic multispectral tile pairs of the Sen2Venus shape: HR [T,4,S,S] reflectance-like values and the
+    2x box-downsampled LR twin [T,4,S/2,S/2] (keeps the SR pairing meaningful).  Deterministic in `seed`."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(n_tiles, 4, size // 8, size // 8, generator=g)
+    hr = torch.nn.functional.interpolate(base, size=(size, size), mode="bilinear", align_corners=False)
+    hr = (hr + 0.15 * torch.rand(n_tiles, 4, size, size, generator=g)) * 3000.0
+    lr = torch.nn.functional.avg_pool2d(hr, 2)
+    if as_int16:
+        hr, lr = hr.round().to(torch.int16), lr.round().to(torch.int16)
+    return lr.to(device), hr.to(device)
+
+
+class TileDataset(torch.utils.data.Dataset):
+    """In-memory (LR tile, HR tile) pairs; item i -> (lr [4,S/2,S/2], hr [4,S,S])."""
+
+    def __init__(self, lr_tiles: torch.Tensor, hr_tiles: torch.Tensor):
+        assert lr_tiles.shape[0] == hr_tiles.shape[0]
+        self.lr, self.hr = lr_tiles, hr_tiles
+
+    def __len__(self):
+        return self.lr.shape[0]
+
+    def __getitem__(self, i):
+        return self.lr[i], self.hr[i]
+
+
+class GridPatchLoader:
+    """Iterates tile batches and emits (y, x) patch batches produced on the device - the on-device equivalent
+    of DataLoader(Sen2VenDataset(crop="grid"), collate_fn=grid_collate)."""
+
+    def __init__(self, tiles: TileDataset, tiles_per_batch: int, patch_size: int, device="cuda", shuffle: bool = False,
+                 seed: int = 0):
+        self.ds, self.tpb, self.P, self.device, self.shuffle = tiles, tiles_per_batch, patch_size, torch.device(device), shuffle
+        self._gen = torch.Generator().manual_seed(seed)
+
+    def __len__(self):
+        return (len(self.ds) + self.tpb - 1) // self.tpb
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        n = len(self.ds)
+        order = torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
+        for i in range(0, n, self.tpb):
+            idx = order[i:i + self.tpb]
+            lr = self.ds.lr[idx].to(self.device, non_blocking=True)
+            hr = self.ds.hr[idx].to(self.device, non_blocking=True)
+            yield grid_batch(lr, hr, self.P)
+
+
+def init_dataloader(dataset: str, batch_size: int = 16, patch_size: int = 64, device="cuda", n_tiles: int = 64):
+    """Same entry point as the reference (dataset.py:13-47).  `synthetic` builds in-memory tiles and grid-patches
+    them on the device (batch_size counts PATCHES, as in the reference's grid mode); the Sen2Venus / flood
+    datasets need the reference's GeoTIFF readers, which are outside this build's scope."""
+    if dataset != "synthetic":
+        raise NotImplementedError(
+            f"dataset '{dataset}': GeoTIFF decoding (tifffile/polars) is outside the hot-path scope of svrs_b200; "
+            "decode tiles with the reference's reader and wrap them in TileDataset, or use --dataset synthetic")
+    per_tile = (256 // patch_size) ** 2
+    tpb = max(1, batch_size // per_tile)
+    lr, hr = synthetic_tiles(n_tiles)
+    split = max(1, int(0.8 * n_tiles))
+    train = GridPatchLoader(TileDataset(lr[:split], hr[:split]), tpb, patch_size, device, shuffle=True)
+    val = GridPatchLoader(TileDataset(lr[split:], hr[split:]), tpb, patch_size, device)
+    return train, val

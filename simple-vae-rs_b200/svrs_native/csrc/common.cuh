@@ -1,0 +1,88 @@
+// common.cuh - shared helpers for the svrs_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../../include/svrs_b200.h"
+
+namespace svrs {
+
+void set_error(const char* fmt, ...);
+
+#define SVRS_CHECK_ARG(cond, ...)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            svrs::set_error(__VA_ARGS__);         \
+            return SVRS_E_ARG;                    \
+        }                                         \
+    } while (0)
+
+static inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return SVRS_E_CUDA;
+    }
+    return 0;
+}
+
+static inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+    __device__ __forceinline__ static float to_f(float v) { return v; }
+    __device__ __forceinline__ static float from_f(float v) { return v; }
+};
+template <> struct Cvt<__nv_bfloat16> {
+    __device__ __forceinline__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ __forceinline__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// 4-element vector load/store with dtype conversion to fp32.  `p` must be 4-element aligned.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == SVRS_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    if (act == SVRS_ACT_HARDTANH7) return fminf(fmaxf(v, -7.0f), 7.0f);
+    return v;
+}
+
+}  // namespace svrs

@@ -1,0 +1,457 @@
+// conv_simt.cu - CUDA-core (fp32 FMA) multi-tap GEMM convolution: fprop/dgrad for every conv form,
+// and the matching wgrad.  This is the exact-fp32 path (parity mode, 1e-5) and the path for layers
+// whose channel counts are too small / odd for the tcgen05 kernel (Cin or Cout in {4, 16}, cr != 2).
+// Accumulation is always fp32; T is the storage type of activations and packed weights.
+#include "common.cuh"
+#include "taps.cuh"
+
+namespace svrs {
+
+struct ConvArgs {
+    const void* in;
+    void* out;
+    const void* w;      // KN pack [tap][K][Nc]
+    const float* bias;  // [Nc] or null
+    int act;
+    TapGeom g;
+};
+
+constexpr int BK = 16;
+
+template <typename T, int BM, int BN>
+__global__ void __launch_bounds__(256) conv_taps_kernel(const __grid_constant__ ConvArgs a) {
+    constexpr int TM = 4, TN = 4;
+    constexpr int TX = BN / TN;            // threads along channels
+    static_assert((BM / TM) * TX == 256, "256 threads");
+    constexpr int A_VECS = BM * BK / 4 / 256;  // float4 loads of A per thread
+    constexpr int B_VECS_TOTAL = BK * BN / 4;
+    constexpr int PADM = 4;
+
+    __shared__ float As[BK][BM + PADM];
+    __shared__ float Bs[BK][BN];
+
+    const TapGeom& g = a.g;
+    const Prob& pb = g.prob[blockIdx.z];
+    const T* __restrict__ in = reinterpret_cast<const T*>(a.in);
+    const T* __restrict__ w = reinterpret_cast<const T*>(a.w);
+    T* __restrict__ out = reinterpret_cast<T*>(a.out) + pb.out_off;
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const long long M = (long long)g.N * g.OH * g.OW;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int K = g.K, Nc = g.Nc;
+    const bool vecA = (K % 4 == 0);
+    const bool vecB = (Nc % 4 == 0);
+
+    // per-thread A-load coordinates
+    int a_pix[A_VECS], a_kq[A_VECS], a_oy[A_VECS], a_ox[A_VECS];
+    long long a_nbase[A_VECS];
+    bool a_ok[A_VECS];
+#pragma unroll
+    for (int i = 0; i < A_VECS; ++i) {
+        int v = tid + i * 256;
+        a_pix[i] = v / (BK / 4);
+        a_kq[i] = v % (BK / 4);
+        long long m = m0 + a_pix[i];
+        a_ok[i] = m < M;
+        long long mm = a_ok[i] ? m : 0;
+        int n = (int)(mm / ((long long)g.OH * g.OW));
+        int r = (int)(mm % ((long long)g.OH * g.OW));
+        a_oy[i] = r / g.OW;
+        a_ox[i] = r % g.OW;
+        a_nbase[i] = (long long)n * g.i_sn;
+    }
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int kchunks = (K + BK - 1) / BK;
+    for (int t = 0; t < pb.ntaps; ++t) {
+        const Tap tp = pb.taps[t];
+        const T* __restrict__ wt = w + tp.w_off;
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const int k0 = kc * BK;
+            // ---- A tile: [BM pixels][BK channels], shifted by the tap, zero outside the view
+#pragma unroll
+            for (int i = 0; i < A_VECS; ++i) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                int iy = a_oy[i] + tp.dy, ix = a_ox[i] + tp.dx;
+                int kk = k0 + a_kq[i] * 4;
+                if (a_ok[i] && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW && kk < K) {
+                    const T* p = in + tp.in_off + a_nbase[i] + (long long)iy * g.i_sy + (long long)ix * g.i_sx + kk;
+                    if (vecA) {
+                        v = ld4(p);
+                    } else {
+                        v.x = Cvt<T>::to_f(p[0]);
+                        if (kk + 1 < K) v.y = Cvt<T>::to_f(p[1]);
+                        if (kk + 2 < K) v.z = Cvt<T>::to_f(p[2]);
+                        if (kk + 3 < K) v.w = Cvt<T>::to_f(p[3]);
+                    }
+                }
+                int kb = a_kq[i] * 4;
+                As[kb + 0][a_pix[i]] = v.x;
+                As[kb + 1][a_pix[i]] = v.y;
+                As[kb + 2][a_pix[i]] = v.z;
+                As[kb + 3][a_pix[i]] = v.w;
+            }
+            // ---- B tile: [BK][BN] of W_t (row k, contiguous along output channels)
+            for (int v = tid; v < B_VECS_TOTAL; v += 256) {
+                int kr = v / (BN / 4), nq = v % (BN / 4);
+                int kk = k0 + kr, nn = n0 + nq * 4;
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kk < K && nn < Nc) {
+                    const T* p = wt + (long long)kk * Nc + nn;
+                    if (vecB) {
+                        b = ld4(p);
+                    } else {
+                        b.x = Cvt<T>::to_f(p[0]);
+                        if (nn + 1 < Nc) b.y = Cvt<T>::to_f(p[1]);
+                        if (nn + 2 < Nc) b.z = Cvt<T>::to_f(p[2]);
+                        if (nn + 3 < Nc) b.w = Cvt<T>::to_f(p[3]);
+                    }
+                }
+                *reinterpret_cast<float4*>(&Bs[kr][nq * 4]) = b;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                float4 av = *reinterpret_cast<const float4*>(&As[k][ty * TM]);
+                float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * TN]);
+                float ar[4] = {av.x, av.y, av.z, av.w};
+                float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue: bias, activation, store (4 consecutive channels per row)
+    const int nn = n0 + tx * TN;
+    if (nn >= Nc) return;
+    float bz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (nn + j < Nc) bz[j] = a.bias[nn + j];
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        long long m = m0 + ty * TM + i;
+        if (m >= M) continue;
+        int n = (int)(m / ((long long)g.OH * g.OW));
+        int r = (int)(m % ((long long)g.OH * g.OW));
+        int oy = r / g.OW, ox = r % g.OW;
+        T* p = out + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx + nn;
+        float4 v;
+        v.x = apply_act(acc[i][0] + bz[0], a.act);
+        v.y = apply_act(acc[i][1] + bz[1], a.act);
+        v.z = apply_act(acc[i][2] + bz[2], a.act);
+        v.w = apply_act(acc[i][3] + bz[3], a.act);
+        if (vecB) {
+            st4(p, v);
+        } else {
+            p[0] = Cvt<T>::from_f(v.x);
+            if (nn + 1 < Nc) p[1] = Cvt<T>::from_f(v.y);
+            if (nn + 2 < Nc) p[2] = Cvt<T>::from_f(v.z);
+            if (nn + 3 < Nc) p[3] = Cvt<T>::from_f(v.w);
+        }
+    }
+}
+
+static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
+    const TapGeom& g = a.g;
+    long long M = (long long)g.N * g.OH * g.OW;
+    if (M == 0) return 0;
+    if (g.Nc <= 16) {
+        dim3 grid((unsigned)((M + 255) / 256), (g.Nc + 15) / 16, g.nprob);
+        if (dtype == SVRS_F32) conv_taps_kernel<float, 256, 16><<<grid, 256, 0, st>>>(a);
+        else conv_taps_kernel<__nv_bfloat16, 256, 16><<<grid, 256, 0, st>>>(a);
+    } else {
+        dim3 grid((unsigned)((M + 63) / 64), (g.Nc + 63) / 64, g.nprob);
+        if (dtype == SVRS_F32) conv_taps_kernel<float, 64, 64><<<grid, 256, 0, st>>>(a);
+        else conv_taps_kernel<__nv_bfloat16, 64, 64><<<grid, 256, 0, st>>>(a);
+    }
+    return check_launch("conv_taps_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad:  dW_t[a][b] += sum_m G[m][a] * X_t[m (+shift)][b]      (m over the output grid of `g`)
+// G lives on the output grid (channels Ca = g.Nc), X on the input view (channels Cb = g.K).
+// Destination is the torch layout dw[(a*Cb + b)*KK + tap], fp32 atomics; K (pixels) is split over grid.z.
+// ------------------------------------------------------------------------------------------------
+struct WgradArgs {
+    const void* gmat;  // operand on the output grid
+    const void* x;     // operand on the input view
+    float* dw;
+    int KK;
+    int ksplit;
+    TapGeom g;         // prob[0].taps[t].w_off unused; tap id = t
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_taps_kernel(const __grid_constant__ WgradArgs a) {
+    constexpr int BA = 64, BB = 64, BP = 16;
+    __shared__ float Gs[BP][BA];
+    __shared__ float Xs[BP][BB];
+    const TapGeom& g = a.g;
+    const Prob& pb = g.prob[0];
+    const T* __restrict__ G = reinterpret_cast<const T*>(a.gmat) + pb.out_off;
+    const T* __restrict__ X = reinterpret_cast<const T*>(a.x);
+    const int Ca = g.Nc, Cb = g.K;
+    const int b_tiles = (Cb + BB - 1) / BB;
+    const int a0 = (blockIdx.x / b_tiles) * BA;
+    const int b0 = (blockIdx.x % b_tiles) * BB;
+    const int t = blockIdx.y;
+    const Tap tp = pb.taps[t];
+    const long long M = (long long)g.N * g.OH * g.OW;
+    long long chunk = (M + a.ksplit - 1) / a.ksplit;
+    chunk = (chunk + BP - 1) / BP * BP;
+    const long long mbeg = (long long)blockIdx.z * chunk;
+    const long long mend = mbeg + chunk < M ? mbeg + chunk : M;
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const bool vecG = (Ca % 4 == 0), vecX = (Cb % 4 == 0);
+    const int lp = tid / 16;       // pixel within the BP chunk
+    const int lq = (tid % 16) * 4; // channel quad
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (long long mb = mbeg; mb < mend; mb += BP) {
+        long long m = mb + lp;
+        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), xv = gv;
+        if (m < mend) {
+            int n = (int)(m / ((long long)g.OH * g.OW));
+            int r = (int)(m % ((long long)g.OH * g.OW));
+            int oy = r / g.OW, ox = r % g.OW;
+            int ca = a0 + lq;
+            if (ca < Ca) {
+                const T* p = G + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx + ca;
+                if (vecG) gv = ld4(p);
+                else {
+                    gv.x = Cvt<T>::to_f(p[0]);
+                    if (ca + 1 < Ca) gv.y = Cvt<T>::to_f(p[1]);
+                    if (ca + 2 < Ca) gv.z = Cvt<T>::to_f(p[2]);
+                    if (ca + 3 < Ca) gv.w = Cvt<T>::to_f(p[3]);
+                }
+            }
+            int iy = oy + tp.dy, ix = ox + tp.dx;
+            int cb = b0 + lq;
+            if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW && cb < Cb) {
+                const T* p = X + tp.in_off + (long long)n * g.i_sn + (long long)iy * g.i_sy + (long long)ix * g.i_sx + cb;
+                if (vecX) xv = ld4(p);
+                else {
+                    xv.x = Cvt<T>::to_f(p[0]);
+                    if (cb + 1 < Cb) xv.y = Cvt<T>::to_f(p[1]);
+                    if (cb + 2 < Cb) xv.z = Cvt<T>::to_f(p[2]);
+                    if (cb + 3 < Cb) xv.w = Cvt<T>::to_f(p[3]);
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(&Gs[lp][lq]) = gv;
+        *reinterpret_cast<float4*>(&Xs[lp][lq]) = xv;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BP; ++k) {
+            float4 av = *reinterpret_cast<const float4*>(&Gs[k][ty * 4]);
+            float4 bv = *reinterpret_cast<const float4*>(&Xs[k][tx * 4]);
+            float ar[4] = {av.x, av.y, av.z, av.w};
+            float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int ca = a0 + ty * 4 + i;
+        if (ca >= Ca) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int cb = b0 + tx * 4 + j;
+            if (cb >= Cb) continue;
+            atomicAdd(&a.dw[((long long)ca * Cb + cb) * a.KK + t], acc[i][j]);
+        }
+    }
+}
+
+// column sums of a contiguous [M][C] matrix, atomically added to out[C] (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long M, int C,
+                                                      float* __restrict__ out, long long rows_per_block) {
+    __shared__ float red[8][33];
+    const int lx = threadIdx.x % 32, ly = threadIdx.x / 32;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        int c = c0 + lx;
+        float s = 0.f;
+        if (c < C)
+            for (long long r = r0 + ly; r < r1; r += 8) s += Cvt<T>::to_f(x[r * C + c]);
+        red[ly][lx] = s;
+        __syncthreads();
+        if (ly == 0 && c < C) {
+            float tot = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tot += red[k][lx];
+            atomicAdd(&out[c], tot);
+        }
+        __syncthreads();
+    }
+}
+
+static int launch_wgrad(WgradArgs& a, int dtype, int ksplit, cudaStream_t st) {
+    const TapGeom& g = a.g;
+    long long M = (long long)g.N * g.OH * g.OW;
+    if (M == 0) return 0;
+    int tiles = ((g.Nc + 63) / 64) * ((g.K + 63) / 64);
+    int ntaps = g.prob[0].ntaps;
+    if (ksplit <= 0) {
+        long long want = 4LL * num_sms();
+        long long base = (long long)tiles * ntaps;
+        ksplit = (int)((want + base - 1) / base);
+        long long maxsplit = (M + 255) / 256;  // at least 256 pixels per CTA
+        if (ksplit > maxsplit) ksplit = (int)maxsplit;
+        if (ksplit < 1) ksplit = 1;
+    }
+    a.ksplit = ksplit;
+    dim3 grid(tiles, ntaps, ksplit);
+    if (dtype == SVRS_F32) wgrad_taps_kernel<float><<<grid, 256, 0, st>>>(a);
+    else wgrad_taps_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+    return check_launch("wgrad_taps_kernel");
+}
+
+static int launch_colsum(const void* x, int dtype, long long M, int C, float* out, cudaStream_t st) {
+    if (M == 0 || C == 0) return 0;
+    long long blocks = (M + 511) / 512;
+    long long cap = 8LL * num_sms();
+    if (blocks > cap) blocks = cap;
+    long long rpb = (M + blocks - 1) / blocks;
+    blocks = (M + rpb - 1) / rpb;
+    if (dtype == SVRS_F32) colsum_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, M, C, out, rpb);
+    else colsum_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, M, C, out, rpb);
+    return check_launch("colsum_kernel");
+}
+
+}  // namespace svrs
+
+using namespace svrs;
+
+static bool dtype_ok(int d) { return d == SVRS_F32 || d == SVRS_BF16; }
+
+extern "C" int svrs_conv2d_fprop(const void* x, const void* w_kn, const float* bias, void* y, int dtype,
+                                 int N, int H, int W, int Cin, int Cout, int ksize, int act, void* stream) {
+    SVRS_CHECK_ARG(x && w_kn && y && dtype_ok(dtype), "conv2d_fprop: null pointer or bad dtype");
+    SVRS_CHECK_ARG(ksize == 3 || (ksize == 4 && H % 2 == 0 && W % 2 == 0), "conv2d_fprop: ksize must be 3, or 4 with even H,W");
+    SVRS_CHECK_ARG(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv2d_fprop: bad dims");
+    ConvArgs a;
+    a.in = x; a.out = y; a.w = w_kn; a.bias = bias; a.act = act;
+    if (ksize == 3) geom_conv3(a.g, N, H, W, Cin, Cout, false);
+    else geom_conv4s2(a.g, N, H, W, Cin, Cout);
+    return launch_conv(a, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int svrs_conv2d_dgrad(const void* dy, const void* w_kn, void* dx, int dtype,
+                                 int N, int H, int W, int Cin, int Cout, int ksize, void* stream) {
+    SVRS_CHECK_ARG(dy && w_kn && dx && dtype_ok(dtype), "conv2d_dgrad: null pointer or bad dtype");
+    SVRS_CHECK_ARG(ksize == 3 || (ksize == 4 && H % 2 == 0 && W % 2 == 0), "conv2d_dgrad: ksize must be 3, or 4 with even H,W");
+    ConvArgs a;
+    a.in = dy; a.out = dx; a.w = w_kn; a.bias = nullptr; a.act = SVRS_ACT_NONE;
+    if (ksize == 3) geom_conv3(a.g, N, H, W, Cout, Cin, true);
+    else geom_convT4s2(a.g, N, H / 2, W / 2, Cout, Cin);
+    return launch_conv(a, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int svrs_convT2d_fprop(const void* x, const void* w_kn, const float* bias, void* y, int dtype,
+                                  int N, int H, int W, int Cin, int Cout, int act, void* stream) {
+    SVRS_CHECK_ARG(x && w_kn && y && dtype_ok(dtype), "convT2d_fprop: null pointer or bad dtype");
+    ConvArgs a;
+    a.in = x; a.out = y; a.w = w_kn; a.bias = bias; a.act = act;
+    geom_convT4s2(a.g, N, H, W, Cin, Cout);
+    return launch_conv(a, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int svrs_convT2d_dgrad(const void* dy, const void* w_kn, void* dx, int dtype,
+                                  int N, int H, int W, int Cin, int Cout, void* stream) {
+    SVRS_CHECK_ARG(dy && w_kn && dx && dtype_ok(dtype), "convT2d_dgrad: null pointer or bad dtype");
+    ConvArgs a;
+    a.in = dy; a.out = dx; a.w = w_kn; a.bias = nullptr; a.act = SVRS_ACT_NONE;
+    geom_conv4s2(a.g, N, 2 * H, 2 * W, Cout, Cin);
+    return launch_conv(a, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float* db, int dtype,
+                                 int N, int H, int W, int Cin, int Cout, int ksize, int ksplit, void* stream) {
+    SVRS_CHECK_ARG(x && dy && dtype_ok(dtype), "conv2d_wgrad: null pointer or bad dtype");
+    SVRS_CHECK_ARG(ksize == 3 || (ksize == 4 && H % 2 == 0 && W % 2 == 0), "conv2d_wgrad: bad ksize");
+    int rc = 0;
+    if (dw) {
+        WgradArgs a;
+        a.gmat = dy; a.x = x; a.dw = dw; a.KK = ksize * ksize;
+        if (ksize == 3) geom_conv3(a.g, N, H, W, Cin, Cout, false);
+        else geom_conv4s2(a.g, N, H, W, Cin, Cout);
+        rc = launch_wgrad(a, dtype, ksplit, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    if (db) {
+        int s = ksize == 3 ? 1 : 2;
+        rc = launch_colsum(dy, dtype, (long long)N * (H / s) * (W / s), Cout, db, (cudaStream_t)stream);
+    }
+    return rc;
+}
+
+extern "C" int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, float* db, int dtype,
+                                  int N, int H, int W, int Cin, int Cout, int ksplit, void* stream) {
+    SVRS_CHECK_ARG(x && dy && dtype_ok(dtype), "convT2d_wgrad: null pointer or bad dtype");
+    int rc = 0;
+    if (dw) {
+        // adjoint view: the coarse input x sits on the output grid of a k4s2 conv that reads the fine dy.
+        WgradArgs a;
+        a.gmat = x; a.x = dy; a.dw = dw; a.KK = 16;
+        geom_conv4s2(a.g, N, 2 * H, 2 * W, Cout, Cin);
+        rc = launch_wgrad(a, dtype, ksplit, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    if (db) rc = launch_colsum(dy, dtype, (long long)N * 4 * H * W, Cout, db, (cudaStream_t)stream);
+    return rc;
+}
+
+// Host-only: dump the tap geometry of a conv form so the host logic can be verified without a GPU.
+// form: 0 conv3 fprop, 1 conv3 dgrad, 2 conv4s2 (fprop / convT dgrad), 3 convT4s2 (fprop / conv4s2 dgrad).
+// H, W are the dims of the tensor being READ.  Layout of `out` (int64):
+//   [0..10] = N, OH, OW, IH, IW, K, Nc, nprob, o_sn, o_sy, o_sx ; [11..13] = i_sn, i_sy, i_sx ;
+//   then per problem: out_off, ntaps, then per tap: in_off, w_off, dy, dx.   Returns #int64 written, <0 on error.
+extern "C" int svrs_debug_tap_geometry(int form, int N, int H, int W, int Cr, int Cw, int64_t* out, int cap) {
+    SVRS_CHECK_ARG(out && form >= 0 && form <= 3, "debug_tap_geometry: bad args");
+    TapGeom g;
+    if (form == 0) geom_conv3(g, N, H, W, Cr, Cw, false);
+    else if (form == 1) geom_conv3(g, N, H, W, Cr, Cw, true);
+    else if (form == 2) geom_conv4s2(g, N, H, W, Cr, Cw);
+    else geom_convT4s2(g, N, H, W, Cr, Cw);
+    int n = 0;
+    auto put = [&](long long v) { if (n < cap) out[n] = v; ++n; };
+    put(g.N); put(g.OH); put(g.OW); put(g.IH); put(g.IW); put(g.K); put(g.Nc); put(g.nprob);
+    put(g.o_sn); put(g.o_sy); put(g.o_sx); put(g.i_sn); put(g.i_sy); put(g.i_sx);
+    for (int p = 0; p < g.nprob; ++p) {
+        put(g.prob[p].out_off); put(g.prob[p].ntaps);
+        for (int t = 0; t < g.prob[p].ntaps; ++t) {
+            put(g.prob[p].taps[t].in_off); put(g.prob[p].taps[t].w_off); put(g.prob[p].taps[t].dy); put(g.prob[p].taps[t].dx);
+        }
+    }
+    SVRS_CHECK_ARG(n <= cap, "debug_tap_geometry: buffer too small (%d needed)", n);
+    return n;
+}

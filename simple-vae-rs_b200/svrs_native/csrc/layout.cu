@@ -1,0 +1,228 @@
+// layout.cu - layout glue (NCHW-flat <-> NHWC), weight packing, casts, error plumbing.
+#include "common.cuh"
+#include <string.h>
+
+namespace svrs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// One image: src is [C][HW] (row stride HW), dst is [HW][C].  32x32 smem tile transpose.
+template <typename TS, typename TD>
+__global__ void nchw_to_nhwc_kernel(const TS* __restrict__ src, long long src_ld, TD* __restrict__ dst,
+                                    int C, int HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const TS* s = src + (long long)n * src_ld;
+    TD* d = dst + (long long)n * C * HW;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? Cvt<TS>::to_f(s[(long long)c * HW + p]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C) d[(long long)p * C + c] = Cvt<TD>::from_f(tile[threadIdx.x][i]);
+    }
+}
+
+template <typename TS, typename TD>
+__global__ void nhwc_to_nchw_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long dst_ld,
+                                    int C, int HW, int accumulate) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const TS* s = src + (long long)n * C * HW;
+    TD* d = dst + (long long)n * dst_ld;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int p = p0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (p < HW && c < C) ? Cvt<TS>::to_f(s[(long long)p * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < HW) {
+            long long o = (long long)c * HW + p;
+            float v = tile[threadIdx.x][i];
+            if (accumulate) v += Cvt<TD>::to_f(d[o]);
+            d[o] = Cvt<TD>::from_f(v);
+        }
+    }
+}
+
+template <typename TD>
+__global__ void pack_weights_kernel(const float* __restrict__ w, int d0, int d1, int kk, TD* __restrict__ p01,
+                                    TD* __restrict__ p10) {
+    long long total = (long long)d0 * d1 * kk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int t = (int)(i % kk);
+        long long r = i / kk;
+        int b = (int)(r % d1);
+        int a = (int)(r / d1);
+        float v = w[i];
+        if (p01) p01[((long long)t * d0 + a) * d1 + b] = Cvt<TD>::from_f(v);
+        if (p10) p10[((long long)t * d1 + b) * d0 + a] = Cvt<TD>::from_f(v);
+    }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        d[i] = Cvt<TD>::from_f(Cvt<TS>::to_f(s[i]));
+}
+
+template <typename TS, typename TD>
+__global__ void copy2d_kernel(const TS* __restrict__ s, long long sld, TD* __restrict__ d, long long dld,
+                              long long rows, int cols, int accumulate) {
+    long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / cols;
+        int c = (int)(i % cols);
+        float v = Cvt<TS>::to_f(s[r * sld + c]);
+        if (accumulate) v += Cvt<TD>::to_f(d[r * dld + c]);
+        d[r * dld + c] = Cvt<TD>::from_f(v);
+    }
+}
+
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, int act, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float yv = Cvt<T>::to_f(y[i]), g = Cvt<T>::to_f(dy[i]);
+        float o = g;
+        if (act == SVRS_ACT_SIGMOID) o = g * yv * (1.f - yv);
+        else if (act == SVRS_ACT_HARDTANH7) o = (yv > -7.f && yv < 7.f) ? g : 0.f;
+        dx[i] = Cvt<T>::from_f(o);
+    }
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = fmaf(a, x[i], y[i]);
+}
+
+static inline unsigned grid_for(long long n, int block = 256) {
+    long long b = (n + block - 1) / block;
+    long long cap = 16LL * num_sms();
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace svrs
+
+using namespace svrs;
+
+extern "C" const char* svrs_last_error(void) { return svrs::g_err; }
+extern "C" int svrs_abi_version(void) { return 1; }
+extern "C" int svrs_device_cc(int dev) {
+    int ma = 0, mi = 0;
+    if (cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return SVRS_E_CUDA;
+    if (cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) return SVRS_E_CUDA;
+    return ma * 10 + mi;
+}
+
+#define DISPATCH2(sd, dd, CALL)                                                            \
+    do {                                                                                   \
+        if (sd == SVRS_F32 && dd == SVRS_F32) { CALL(float, float); }                      \
+        else if (sd == SVRS_F32 && dd == SVRS_BF16) { CALL(float, __nv_bfloat16); }        \
+        else if (sd == SVRS_BF16 && dd == SVRS_F32) { CALL(__nv_bfloat16, float); }        \
+        else if (sd == SVRS_BF16 && dd == SVRS_BF16) { CALL(__nv_bfloat16, __nv_bfloat16); } \
+        else { set_error("bad dtype pair %d,%d", sd, dd); return SVRS_E_ARG; }             \
+    } while (0)
+
+extern "C" int svrs_nchw_to_nhwc(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype,
+                                 int N, int C, int H, int W, void* stream) {
+    SVRS_CHECK_ARG(src && dst && N >= 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad args");
+    if (N == 0) return 0;
+    SVRS_CHECK_ARG(N <= 65535, "nchw_to_nhwc: N > 65535");
+    int HW = H * W;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(TS, TD) nchw_to_nhwc_kernel<TS, TD><<<grid, block, 0, st>>>((const TS*)src, src_ld, (TD*)dst, C, HW)
+    DISPATCH2(src_dtype, dst_dtype, CALL);
+#undef CALL
+    return check_launch("nchw_to_nhwc");
+}
+
+extern "C" int svrs_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t dst_ld,
+                                 int N, int C, int H, int W, int accumulate, void* stream) {
+    SVRS_CHECK_ARG(src && dst && N >= 0 && C > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad args");
+    if (N == 0) return 0;
+    SVRS_CHECK_ARG(N <= 65535, "nhwc_to_nchw: N > 65535");
+    int HW = H * W;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(TS, TD) nhwc_to_nchw_kernel<TS, TD><<<grid, block, 0, st>>>((const TS*)src, (TD*)dst, dst_ld, C, HW, accumulate)
+    DISPATCH2(src_dtype, dst_dtype, CALL);
+#undef CALL
+    return check_launch("nhwc_to_nchw");
+}
+
+extern "C" int svrs_pack_weights(const float* w, int d0, int d1, int kk, void* p01, void* p10, int dtype,
+                                 void* stream) {
+    SVRS_CHECK_ARG(w && d0 > 0 && d1 > 0 && kk > 0, "pack_weights: bad args");
+    long long total = (long long)d0 * d1 * kk;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SVRS_F32)
+        pack_weights_kernel<float><<<grid_for(total), 256, 0, st>>>(w, d0, d1, kk, (float*)p01, (float*)p10);
+    else if (dtype == SVRS_BF16)
+        pack_weights_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>(w, d0, d1, kk, (__nv_bfloat16*)p01,
+                                                                             (__nv_bfloat16*)p10);
+    else { set_error("pack_weights: bad dtype"); return SVRS_E_ARG; }
+    return check_launch("pack_weights");
+}
+
+extern "C" int svrs_fill_zero(void* p, int64_t bytes, void* stream) {
+    if (bytes <= 0) return 0;
+    SVRS_CHECK_ARG(p, "fill_zero: null");
+    cudaError_t e = cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("fill_zero: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
+    return 0;
+}
+
+extern "C" int svrs_axpy_f32(float* y, const float* x, float a, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    SVRS_CHECK_ARG(x && y, "axpy: null");
+    axpy_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(y, x, a, n);
+    return check_launch("axpy");
+}
+
+extern "C" int svrs_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    SVRS_CHECK_ARG(src && dst, "cast: null");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(TS, TD) cast_kernel<TS, TD><<<grid_for(n), 256, 0, st>>>((const TS*)src, (TD*)dst, n)
+    DISPATCH2(src_dtype, dst_dtype, CALL);
+#undef CALL
+    return check_launch("cast");
+}
+
+extern "C" int svrs_copy2d(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
+                           int64_t rows, int cols, int accumulate, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    SVRS_CHECK_ARG(src && dst && (src_ld >= cols || src_ld == 0) && dst_ld >= cols, "copy2d: bad args (src_ld 0 = broadcast)");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long n = rows * cols;
+#define CALL(TS, TD) copy2d_kernel<TS, TD><<<grid_for(n), 256, 0, st>>>((const TS*)src, src_ld, (TD*)dst, dst_ld, rows, cols, accumulate)
+    DISPATCH2(src_dtype, dst_dtype, CALL);
+#undef CALL
+    return check_launch("copy2d");
+}
+
+extern "C" int svrs_act_bwd(const void* y, const void* dy, void* dx, int dtype, int act, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    SVRS_CHECK_ARG(y && dy && dx, "act_bwd: null");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SVRS_F32) act_bwd_kernel<float><<<grid_for(n), 256, 0, st>>>((const float*)y, (const float*)dy, (float*)dx, act, n);
+    else if (dtype == SVRS_BF16) act_bwd_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, act, n);
+    else { set_error("act_bwd: bad dtype"); return SVRS_E_ARG; }
+    return check_launch("act_bwd");
+}

@@ -1,0 +1,737 @@
+"""Host-side runtime for the (Cond_)SRVAE training step on B200.
+
+Everything arithmetic happens in libsvrs_b200.so (hand-written sm_100a CUDA, bound through the C ABI in
+include/svrs_b200.h).  PyTorch is used for device memory (tensors as buffers), streams and - in
+`parallel.py` - torch.distributed.  There is no eager / CPU fallback: a model that is not on a CUDA device
+cannot run.
+
+Layout: activations are NHWC in the compute dtype (fp32 or bf16); latents cross sub-network boundaries in
+the reference's NCHW-flat fp32 order, which is also what the Python API returns.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .lib import ACT_HARDTANH7, ACT_NONE, ACT_SIGMOID, BF16, F32, SvrsError, lib
+
+BN_EPS_DEFAULT = 1e-5
+
+
+def _dt(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise SvrsError(f"unsupported compute dtype {dtype}")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise SvrsError(
+            f"{what} is on {t.device}: the svrs_b200 path runs hand-written sm_100a kernels only and has no "
+            f"CPU fallback - move the model and its inputs to a CUDA device.")
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter storage: one flat fp32 buffer for parameters, one for gradients (clip / Adam / all-reduce
+# then run over a single contiguous range).  nn.Parameter objects are kept (state_dict keys, optimizer
+# references) and re-pointed at views of the flat buffer.
+# ------------------------------------------------------------------------------------------------
+class ParamStore:
+    ALIGN = 4  # floats -> 16-byte aligned views
+
+    def __init__(self, module: nn.Module):
+        self.module = module
+        self.params: List[nn.Parameter] = []
+        self.names: List[str] = []
+        for n, p in module.named_parameters():
+            self.names.append(n)
+            self.params.append(p)
+        self.offsets: List[int] = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.total = off
+        self.flat: Optional[torch.Tensor] = None
+        self.grad: Optional[torch.Tensor] = None
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+
+    def valid(self) -> bool:
+        if self.flat is None or not self.params:
+            return self.flat is not None
+        base = self.flat.data_ptr()
+        for i in (0, len(self.params) // 2, len(self.params) - 1):
+            if self.params[i].data.data_ptr() != base + 4 * self.offsets[i]:
+                return False
+        return True
+
+    def ensure(self) -> bool:
+        """(Re)flatten if the module's parameters moved (model.to(), fresh construction). True if rebuilt."""
+        if self.valid():
+            return False
+        dev = self.params[0].device
+        _require_cuda(self.params[0], "model")
+        flat = torch.zeros(self.total, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                v = flat[off:off + p.numel()].view(p.shape)
+                v.copy_(p.data.to(torch.float32))
+                p.data = v
+        self.flat = flat
+        self.grad = torch.zeros_like(flat)
+        return True
+
+    def grad_view(self, p: nn.Parameter) -> torch.Tensor:
+        i = self._index[id(p)]
+        off = self.offsets[i]
+        return self.grad[off:off + p.numel()].view(p.shape)
+
+    def grad_ptr(self, p: nn.Parameter) -> int:
+        return self.grad.data_ptr() + 4 * self.offsets[self._index[id(p)]]
+
+
+# ------------------------------------------------------------------------------------------------
+# network plans
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ConvOp:
+    kind: str                  # "c3" (k3 s1 p1), "c4" (k4 s2 p1), "ct" (transposed k4 s2 p1)
+    mod: nn.Module
+    cin: int
+    cout: int
+    act: int = ACT_NONE
+    pack_f: Optional[torch.Tensor] = None   # KN pack for fprop
+    pack_b: Optional[torch.Tensor] = None   # KN pack for dgrad
+
+    @property
+    def kk(self) -> int:
+        return 9 if self.kind == "c3" else 16
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        if self.kind == "c3":
+            return h, w
+        if self.kind == "c4":
+            return h // 2, w // 2
+        return 2 * h, 2 * w
+
+
+@dataclass
+class BNOp:
+    mod: nn.BatchNorm2d
+    relu: bool = True
+    sums_f: Optional[torch.Tensor] = None   # double[2C] scratch, forward stats
+    sums_b: Optional[torch.Tensor] = None   # double[2C] scratch, backward sums
+
+
+@dataclass
+class Net:
+    name: str
+    ops: list = field(default_factory=list)
+
+    @property
+    def cin(self) -> int:
+        return self.ops[0].cin
+
+    @property
+    def cout(self) -> int:
+        for op in reversed(self.ops):
+            if isinstance(op, ConvOp):
+                return op.cout
+        raise RuntimeError("empty net")
+
+
+def plan_sequential(name: str, seq: nn.Sequential) -> Net:
+    """Translate one of the reference's nn.Sequential sub-networks (cond_vae.py:27-231, vae.py:36-85)
+    into a list of kernel ops.  Flatten/Unflatten are geometry handled by the caller."""
+    net = Net(name)
+    for m in seq:
+        cls = m.__class__.__name__
+        if cls == "down_block":          # layers.py:217-256
+            net.ops.append(ConvOp("c3", m.conv, m.conv.in_channels, m.conv.out_channels))
+            net.ops.append(ConvOp("c4", m.downsample, m.downsample.in_channels, m.downsample.out_channels))
+            if m.with_bn:
+                net.ops.append(BNOp(m.bn, relu=m.with_relu))
+            elif m.with_relu:
+                raise SvrsError("down_block(with_bn=False, with_relu=True) is not used by any model")
+        elif cls == "up_block":          # layers.py:259-297
+            net.ops.append(ConvOp("c3", m.conv, m.conv.in_channels, m.conv.out_channels))
+            net.ops.append(ConvOp("ct", m.upsample, m.upsample.in_channels, m.upsample.out_channels))
+            if m.with_bn:
+                net.ops.append(BNOp(m.bn, relu=m.with_relu))
+            elif m.with_relu:
+                raise SvrsError("up_block(with_bn=False, with_relu=True) is not used by any model")
+        elif isinstance(m, nn.Conv2d):
+            assert m.kernel_size == (3, 3) and m.stride == (1, 1) and m.padding == (1, 1)
+            net.ops.append(ConvOp("c3", m, m.in_channels, m.out_channels))
+        elif isinstance(m, nn.Sigmoid):
+            net.ops[-1].act = ACT_SIGMOID
+        elif isinstance(m, nn.Hardtanh):
+            assert m.min_val == -7 and m.max_val == 7
+            net.ops[-1].act = ACT_HARDTANH7
+        elif isinstance(m, (nn.Flatten, nn.Unflatten)):
+            continue
+        else:
+            raise SvrsError(f"unsupported layer {cls} in {name}")
+    return net
+
+
+class Runtime:
+    """Kernel-level forward/backward over Net plans; owns weight packs and scratch."""
+
+    def __init__(self, module: nn.Module, nets: Sequence[Net], compute_dtype: torch.dtype = torch.float32):
+        lib.load()
+        self.module = module
+        self.nets = list(nets)
+        self.dtype = compute_dtype
+        self.dt = _dt(compute_dtype)
+        self.store = ParamStore(module)
+        self._scratch: Optional[torch.Tensor] = None
+        self.packs_dirty = True
+        self.launches = 0          # kernels enqueued (our own), for bench.py's gpu_launches
+
+    # -------------------------------------------------------------------------------------- setup
+    @property
+    def device(self) -> torch.device:
+        return self.store.params[0].device
+
+    def set_dtype(self, compute_dtype: torch.dtype):
+        if compute_dtype != self.dtype:
+            self.dtype = compute_dtype
+            self.dt = _dt(compute_dtype)
+            for net in self.nets:
+                for op in net.ops:
+                    if isinstance(op, ConvOp):
+                        op.pack_f = op.pack_b = None
+            self.packs_dirty = True
+
+    def ensure(self):
+        rebuilt = self.store.ensure()
+        dev = self.device
+        if rebuilt or self._scratch is None or self._scratch.device != dev:
+            n = 0
+            for net in self.nets:
+                for op in net.ops:
+                    if isinstance(op, BNOp):
+                        n += 4 * op.mod.num_features
+            self._scratch = torch.zeros(max(n, 1), device=dev, dtype=torch.float64)
+            off = 0
+            for net in self.nets:
+                for op in net.ops:
+                    if isinstance(op, BNOp):
+                        c = op.mod.num_features
+                        op.sums_f = self._scratch[off:off + 2 * c]
+                        op.sums_b = self._scratch[off + 2 * c:off + 4 * c]
+                        off += 4 * c
+            self.packs_dirty = True
+            for net in self.nets:
+                for op in net.ops:
+                    if isinstance(op, ConvOp):
+                        op.pack_f = op.pack_b = None
+
+    def zero_scratch(self):
+        lib.fill_zero(_p(self._scratch), self._scratch.numel() * 8, _st())
+        self.launches += 1
+
+    def zero_grads(self):
+        lib.fill_zero(_p(self.store.grad), self.store.grad.numel() * 4, _st())
+        self.launches += 1
+
+    def pack_weights(self, force: bool = False):
+        """fp32 master weights (torch layout) -> per-tap KN packs in the compute dtype."""
+        if not (self.packs_dirty or force):
+            return
+        dev, st = self.device, _st()
+        for net in self.nets:
+            for op in net.ops:
+                if not isinstance(op, ConvOp):
+                    continue
+                w = op.mod.weight
+                n = w.numel()
+                if op.pack_f is None or op.pack_f.device != dev:
+                    op.pack_f = torch.empty(n, device=dev, dtype=self.dtype)
+                    op.pack_b = torch.empty(n, device=dev, dtype=self.dtype)
+                d0, d1 = w.shape[0], w.shape[1]
+                if op.kind == "ct":
+                    # weight [Cin][Cout][16]: fprop wants [t][Cin][Cout] = p01, dgrad wants [t][Cout][Cin] = p10
+                    lib.pack_weights(_p(w.data), d0, d1, op.kk, _p(op.pack_f), _p(op.pack_b), self.dt, st)
+                else:
+                    # weight [Cout][Cin][kk]: fprop wants [t][Cin][Cout] = p10, dgrad wants [t][Cout][Cin] = p01
+                    lib.pack_weights(_p(w.data), d0, d1, op.kk, _p(op.pack_b), _p(op.pack_f), self.dt, st)
+                self.launches += 1
+        self.packs_dirty = False
+
+    # -------------------------------------------------------------------------------------- layout glue
+    def to_nhwc(self, src: torch.Tensor, src_ld: int, n: int, c: int, h: int, w: int) -> torch.Tensor:
+        """NCHW-flat rows (fp32, row stride src_ld) -> NHWC compute-dtype tensor [n,h,w,c]."""
+        out = torch.empty((n, h, w, c), device=src.device, dtype=self.dtype)
+        lib.nchw_to_nhwc(_p(src), _dt(src.dtype), src_ld, _p(out), self.dt, n, c, h, w, _st())
+        self.launches += 1
+        return out
+
+    def to_nchw(self, src: torch.Tensor, dst: torch.Tensor, dst_ld: int, accumulate: bool = False):
+        """NHWC tensor [n,h,w,c] -> NCHW-flat rows of dst (row stride dst_ld)."""
+        n, h, w, c = src.shape
+        lib.nhwc_to_nchw(_p(src), _dt(src.dtype), _p(dst), _dt(dst.dtype), dst_ld, n, c, h, w, int(accumulate), _st())
+        self.launches += 1
+
+    def copy2d(self, src, src_ld, dst, dst_ld, rows, cols, accumulate=False):
+        lib.copy2d(_p(src) if isinstance(src, torch.Tensor) else src, _dt(self._dtype_of(src)), src_ld,
+                   _p(dst) if isinstance(dst, torch.Tensor) else dst, _dt(self._dtype_of(dst)), dst_ld,
+                   rows, cols, int(accumulate), _st())
+        self.launches += 1
+
+    @staticmethod
+    def _dtype_of(t):
+        return t.dtype
+
+    # -------------------------------------------------------------------------------------- forward
+    def net_forward(self, net: Net, x: torch.Tensor, training: bool, save: bool, bn_updates: int = 1):
+        """x: NHWC [N,H,W,Cin] in the compute dtype.  Returns (out NHWC, tape)."""
+        st = _st()
+        n, h, w, c = x.shape
+        assert c == net.cin, f"{net.name}: expected {net.cin} channels, got {c}"
+        tape = []
+        for op in net.ops:
+            if isinstance(op, ConvOp):
+                oh, ow = op.out_hw(h, w)
+                y = torch.empty((n, oh, ow, op.cout), device=x.device, dtype=self.dtype)
+                bias = op.mod.bias
+                if op.kind == "ct":
+                    lib.convT2d_fprop(_p(x), _p(op.pack_f), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout, op.act, st)
+                else:
+                    lib.conv2d_fprop(_p(x), _p(op.pack_f), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout,
+                                     3 if op.kind == "c3" else 4, op.act, st)
+                self.launches += 1
+                if save:
+                    tape.append((op, x, y if op.act != ACT_NONE else None))
+                x, h, w = y, oh, ow
+            else:
+                bn = op.mod
+                cch = bn.num_features
+                m = n * h * w
+                dev = x.device
+                scale = torch.empty(cch, device=dev, dtype=torch.float32)
+                shift = torch.empty(cch, device=dev, dtype=torch.float32)
+                if training:
+                    mean = torch.empty(cch, device=dev, dtype=torch.float32)
+                    invstd = torch.empty(cch, device=dev, dtype=torch.float32)
+                    lib.fill_zero(_p(op.sums_f), 16 * cch, st)
+                    lib.bn_stats(_p(x), self.dt, m, cch, _p(op.sums_f), st)
+                    mom = 0.1 if bn.momentum is None else bn.momentum
+                    track = bn.track_running_stats and bn.running_mean is not None
+                    lib.bn_finalize_train(_p(op.sums_f), m, cch, _p(bn.weight), _p(bn.bias), bn.eps, mom,
+                                          _p(bn.running_mean) if track else None,
+                                          _p(bn.running_var) if track else None,
+                                          _p(bn.num_batches_tracked) if track else None, bn_updates,
+                                          _p(scale), _p(shift), _p(mean), _p(invstd), st)
+                    self.launches += 3
+                else:
+                    mean = invstd = None
+                    lib.bn_finalize_eval(cch, _p(bn.weight), _p(bn.bias), bn.eps, _p(bn.running_mean),
+                                         _p(bn.running_var), _p(scale), _p(shift), st)
+                    self.launches += 1
+                y = torch.empty_like(x) if save else x
+                lib.bn_apply(_p(x), _p(y), self.dt, m, cch, _p(scale), _p(shift), int(op.relu), st)
+                self.launches += 1
+                if save:
+                    tape.append((op, x, scale, shift, mean, invstd))
+                x = y
+        return x, tape
+
+    # -------------------------------------------------------------------------------------- backward
+    def net_backward(self, net: Net, tape: list, dy: torch.Tensor, need_dx: bool) -> Optional[torch.Tensor]:
+        """dy: NHWC grad wrt the net output (compute dtype; MAY be modified in place).  Accumulates parameter
+        gradients into the flat fp32 gradient buffer; returns dx (NHWC) if need_dx."""
+        st = _st()
+        store = self.store
+        for idx in range(len(tape) - 1, -1, -1):
+            entry = tape[idx]
+            op = entry[0]
+            if isinstance(op, ConvOp):
+                _, x, yact = entry
+                n, h, w, _c = x.shape
+                if op.act != ACT_NONE:
+                    lib.act_bwd(_p(yact), _p(dy), _p(dy), self.dt, op.act, dy.numel(), st)
+                    self.launches += 1
+                dw = store.grad_ptr(op.mod.weight)
+                db = store.grad_ptr(op.mod.bias) if op.mod.bias is not None else None
+                if op.kind == "ct":
+                    lib.convT2d_wgrad(_p(x), _p(dy), dw, db, self.dt, n, h, w, op.cin, op.cout, 0, st)
+                else:
+                    lib.conv2d_wgrad(_p(x), _p(dy), dw, db, self.dt, n, h, w, op.cin, op.cout,
+                                     3 if op.kind == "c3" else 4, 0, st)
+                self.launches += 2
+                if idx > 0 or need_dx:
+                    dx = torch.empty_like(x)
+                    if op.kind == "ct":
+                        lib.convT2d_dgrad(_p(dy), _p(op.pack_b), _p(dx), self.dt, n, h, w, op.cin, op.cout, st)
+                    else:
+                        lib.conv2d_dgrad(_p(dy), _p(op.pack_b), _p(dx), self.dt, n, h, w, op.cin, op.cout,
+                                         3 if op.kind == "c3" else 4, st)
+                    self.launches += 1
+                    dy = dx
+                else:
+                    dy = None
+            else:
+                _, x, scale, shift, mean, invstd = entry
+                if mean is None:
+                    raise SvrsError("backward through eval-mode BatchNorm is not part of the training path")
+                n, h, w, cch = x.shape
+                m = n * h * w
+                bn = op.mod
+                lib.fill_zero(_p(op.sums_b), 16 * cch, st)
+                lib.bn_bwd_reduce(_p(x), _p(dy), self.dt, m, cch, _p(scale), _p(shift), _p(mean), _p(invstd),
+                                  int(op.relu), _p(op.sums_b), st)
+                lib.bn_bwd_apply(_p(x), _p(dy), _p(dy), self.dt, m, cch, _p(scale), _p(shift), _p(mean), _p(invstd),
+                                 _p(bn.weight), int(op.relu), _p(op.sums_b),
+                                 store.grad_ptr(bn.weight), store.grad_ptr(bn.bias), st)
+                self.launches += 3
+        return dy if need_dx else None
+
+
+# ------------------------------------------------------------------------------------------------
+# reparameterisation config
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class RngState:
+    seed: int = 0
+    sample_offset: int = 0          # global index of this rank's first sample (partition-invariant eps)
+    step_ptr: Optional[torch.Tensor] = None   # device int64 step counter (Philox counter word 3)
+
+
+def reparam_fwd(rt: Runtime, enc, eps, z, z_ld, b, wd, rng: RngState, stream_id: int, eps_out=None):
+    lib.reparam_fwd(_p(enc), _p(eps), z if isinstance(z, int) else _p(z), z_ld, _p(eps_out), b, wd,
+                    rng.seed, stream_id, rng.sample_offset, _p(rng.step_ptr), _st())
+    rt.launches += 1
+
+
+def reparam_bwd(rt: Runtime, enc, eps, dz, dz_ld, denc, b, wd, rng: RngState, stream_id: int):
+    lib.reparam_bwd(_p(enc), _p(eps), dz if isinstance(dz, int) else _p(dz), dz_ld, _p(denc), b, wd,
+                    rng.seed, stream_id, rng.sample_offset, _p(rng.step_ptr), _st())
+    rt.launches += 1
+
+
+# ------------------------------------------------------------------------------------------------
+# Cond_SRVAE engine
+# ------------------------------------------------------------------------------------------------
+class CondEngine:
+    """Forward/backward of Cond_SRVAE.forward (cond_vae.py:275-286) over the kernel library.
+
+    y_to_z is evaluated ONCE and consumed twice (z_cond :239 and decode_x :271); its BatchNorm running
+    statistics are advanced twice and num_batches_tracked by 2 to keep state_dict parity."""
+
+    def __init__(self, model: nn.Module, compute_dtype=torch.float32):
+        self.model = model
+        self.P = model.patch_size
+        self.L = model.latent_size
+        self.Lu = model.latent_size_y
+        names = ["encoder_y", "decoder_y", "encoder_x", "decoder_x", "y_to_z", "u_to_z", "mu_u_y_to_z", "logvar_u_y_to_z"]
+        self.nets = {n: plan_sequential(n, getattr(model, n)) for n in names}
+        self.rt = Runtime(model, list(self.nets.values()), compute_dtype)
+        P = self.P
+        assert P % 16 == 0, "patch_size must be a multiple of 16"
+        self.cz = self.L // 64                   # channels of mu_z at (P/8)^2
+        self.cu = self.Lu // 64
+        self.Wz = self.cz * (P // 8) ** 2        # true latent widths (SURVEY 3.2 caveat)
+        self.Wu = self.cu * (P // 8) ** 2
+        self.c16 = self.L // 16                  # y_to_z / u_to_z / prior-head channels at (P/16)^2
+        self.cu16 = self.Lu // 16
+        if self.c16 * (P // 16) ** 2 != self.Wz or self.cu16 * (P // 16) ** 2 != self.Wu:
+            raise SvrsError("inconsistent latent geometry (reference would fail in torch.cat/Unflatten)")
+        if self.Wz % 4 or self.Wu % 4:
+            raise SvrsError("latent widths must be multiples of 4")
+        self.rng = RngState()
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, y: torch.Tensor, eps_u: Optional[torch.Tensor], eps_z: Optional[torch.Tensor],
+                training: bool, save: bool, repack: bool = True):
+        """x [B,4,P,P], y [B,4,P/2,P/2] (NCHW, fp32, CUDA).  Returns (outs, ctx) where
+        outs = dict(x_hat, y_hat, enc_z [B,2Wz], enc_u [B,2Wu], mu3, lv3) all fp32 NCHW(-flat)."""
+        rt = self.rt
+        _require_cuda(x, "x")
+        _require_cuda(y, "y")
+        rt.ensure()
+        if repack:
+            rt.packs_dirty = True
+        rt.pack_weights()
+        P, B = self.P, x.shape[0]
+        assert x.shape[1:] == (4, P, P) and y.shape[1:] == (4, P // 2, P // 2) and y.shape[0] == B
+        x = x.contiguous().float()
+        y = y.contiguous().float()
+        dev = x.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        h8, h16 = P // 8, P // 16
+        Wz, Wu = self.Wz, self.Wu
+        N = self.nets
+        ctx = {}
+
+        y_nhwc = rt.to_nhwc(y, 4 * (P // 2) ** 2, B, 4, P // 2, P // 2)
+        x_nhwc = rt.to_nhwc(x, 4 * P * P, B, 4, P, P)
+
+        # q(u|y): encoder_y -> chunk -> reparameterize (RNG draw #1)
+        ey, ctx["t_ey"] = rt.net_forward(N["encoder_y"], y_nhwc, training, save)
+        enc_u = torch.empty((B, 2 * Wu), **f32)
+        rt.to_nchw(ey, enc_u, 2 * Wu)
+        u = torch.empty((B, Wu), **f32)
+        reparam_fwd(rt, enc_u, eps_u, u, Wu, B, Wu, self.rng, 0)
+
+        # q(z|x): encoder_x -> chunk -> reparameterize (draw #2); z lands in the right half of `stack`
+        ex, ctx["t_ex"] = rt.net_forward(N["encoder_x"], x_nhwc, training, save)
+        enc_z = torch.empty((B, 2 * Wz), **f32)
+        rt.to_nchw(ex, enc_z, 2 * Wz)
+        stack = torch.empty((B, 2 * Wz), **f32)          # torch.cat((y_enc, z), dim=1)  cond_vae.py:272
+        reparam_fwd(rt, enc_z, eps_z, stack.data_ptr() + 4 * Wz, 2 * Wz, B, Wz, self.rng, 1)
+
+        # y_to_z once (two BN running-stat updates)
+        yz, ctx["t_yz"] = rt.net_forward(N["y_to_z"], y_nhwc, training, save, bn_updates=2)
+        rt.to_nchw(yz, stack, 2 * Wz)                    # left half of stack = y_enc flat
+
+        # u_to_z on u re-viewed as (Lu/16, P/16, P/16)   cond_vae.py:168-175
+        u16 = rt.to_nhwc(u, Wu, B, self.cu16, h16, h16)
+        uz, ctx["t_uz"] = rt.net_forward(N["u_to_z"], u16, training, save)
+
+        # jointure = cat(y_enc, u_enc) viewed (2L/16, P/16, P/16) == channel concat in NHWC
+        c16 = self.c16
+        joint = torch.empty((B, h16, h16, 2 * c16), device=dev, dtype=rt.dtype)
+        rows = B * h16 * h16
+        es = joint.element_size()
+        rt.copy2d(yz, c16, joint, 2 * c16, rows, c16)
+        lib.copy2d(_p(uz), rt.dt, c16, joint.data_ptr() + es * c16, rt.dt, 2 * c16, rows, c16, 0, _st())
+        rt.launches += 1
+        m3, ctx["t_mu"] = rt.net_forward(N["mu_u_y_to_z"], joint, training, save)
+        l3, ctx["t_lv"] = rt.net_forward(N["logvar_u_y_to_z"], joint, training, save)
+        mu3 = torch.empty((B, Wz), **f32)
+        lv3 = torch.empty((B, Wz), **f32)
+        rt.to_nchw(m3, mu3, Wz)
+        rt.to_nchw(l3, lv3, Wz)
+
+        # decode_x(z, y): stack viewed (2L/64, P/8, P/8)
+        s8 = rt.to_nhwc(stack, 2 * Wz, B, 2 * self.cz, h8, h8)
+        xh, ctx["t_dx"] = rt.net_forward(N["decoder_x"], s8, training, save)
+        x_hat = torch.empty((B, 4, P, P), **f32)
+        rt.to_nchw(xh, x_hat, 4 * P * P)
+
+        # decode_y(u): u viewed (Lu/64, P/8, P/8)
+        u8 = rt.to_nhwc(u, Wu, B, self.cu, h8, h8)
+        yh, ctx["t_dy"] = rt.net_forward(N["decoder_y"], u8, training, save)
+        y_hat = torch.empty((B, 4, P // 2, P // 2), **f32)
+        rt.to_nchw(yh, y_hat, 4 * (P // 2) ** 2)
+
+        if save:
+            ctx.update(B=B, enc_u=enc_u, enc_z=enc_z, eps_u=eps_u, eps_z=eps_z, rng=RngState(**vars(self.rng)))
+        outs = dict(x_hat=x_hat, y_hat=y_hat, enc_z=enc_z, enc_u=enc_u, mu3=mu3, lv3=lv3)
+        return outs, ctx
+
+    # ---- backward --------------------------------------------------------------------------------
+    def backward(self, ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3):
+        """Gradients wrt the forward outputs (fp32, NCHW(-flat); None = zero; d_enc_* are MODIFIED in place).
+        Parameter gradients are accumulated into rt.store.grad (caller zeroes it)."""
+        rt = self.rt
+        N = self.nets
+        P, B = self.P, ctx["B"]
+        h8, h16 = P // 8, P // 16
+        Wz, Wu, c16 = self.Wz, self.Wu, self.c16
+        dev = ctx["enc_u"].device
+        f32 = dict(device=dev, dtype=torch.float32)
+        rows = B * h16 * h16
+        rng = ctx["rng"]
+
+        def zeros(*shape):
+            t = torch.empty(shape, **f32)
+            lib.fill_zero(_p(t), t.numel() * 4, _st())
+            rt.launches += 1
+            return t
+
+        # decoder_x
+        d_stack = None
+        if d_xhat is not None:
+            g = rt.to_nhwc(d_xhat.contiguous(), 4 * P * P, B, 4, P, P)
+            ds8 = rt.net_backward(N["decoder_x"], ctx["t_dx"], g, True)
+            d_stack = torch.empty((B, 2 * Wz), **f32)
+            rt.to_nchw(ds8, d_stack, 2 * Wz)
+        # decoder_y
+        d_u = None
+        if d_yhat is not None:
+            g = rt.to_nhwc(d_yhat.contiguous(), 4 * (P // 2) ** 2, B, 4, P // 2, P // 2)
+            du8 = rt.net_backward(N["decoder_y"], ctx["t_dy"], g, True)
+            d_u = torch.empty((B, Wu), **f32)
+            rt.to_nchw(du8, d_u, Wu)
+        # prior heads
+        d_joint = None
+        for key, tape, net in ((d_mu3, "t_mu", "mu_u_y_to_z"), (d_lv3, "t_lv", "logvar_u_y_to_z")):
+            if key is None:
+                continue
+            g = rt.to_nhwc(key.contiguous(), Wz, B, c16, h16, h16)
+            dj = rt.net_backward(N[net], ctx[tape], g, True)
+            if d_joint is None:
+                d_joint = dj
+            else:
+                rt.copy2d(dj, 2 * c16, d_joint, 2 * c16, rows, 2 * c16, accumulate=True)
+        # gradient wrt y_to_z output (NHWC) and u_to_z output
+        d_yz = None
+        if d_joint is not None:
+            es = d_joint.element_size()
+            d_yz = torch.empty((B, h16, h16, c16), device=dev, dtype=rt.dtype)
+            d_uz = torch.empty((B, h16, h16, c16), device=dev, dtype=rt.dtype)
+            rt.copy2d(d_joint, 2 * c16, d_yz, c16, rows, c16)
+            lib.copy2d(d_joint.data_ptr() + es * c16, rt.dt, 2 * c16, _p(d_uz), rt.dt, c16, rows, c16, 0, _st())
+            rt.launches += 1
+            du16 = rt.net_backward(N["u_to_z"], ctx["t_uz"], d_uz, True)
+            if d_u is None:
+                d_u = zeros(B, Wu)
+            rt.to_nchw(du16, d_u, Wu, accumulate=True)
+        if d_stack is not None:
+            g = rt.to_nhwc(d_stack, 2 * Wz, B, c16, h16, h16)   # left half rows: y_enc as (L/16, P/16, P/16)
+            if d_yz is None:
+                d_yz = g
+            else:
+                rt.copy2d(g, c16, d_yz, c16, rows, c16, accumulate=True)
+        if d_yz is not None:
+            rt.net_backward(N["y_to_z"], ctx["t_yz"], d_yz, False)
+        # encoder_x through reparameterize(z)
+        if d_enc_z is None and d_stack is not None:
+            d_enc_z = zeros(B, 2 * Wz)
+        if d_enc_z is not None:
+            if d_stack is not None:
+                reparam_bwd(rt, ctx["enc_z"], ctx["eps_z"], d_stack.data_ptr() + 4 * Wz, 2 * Wz, d_enc_z, B, Wz, rng, 1)
+            g = rt.to_nhwc(d_enc_z, 2 * Wz, B, 2 * self.cz, h8, h8)
+            rt.net_backward(N["encoder_x"], ctx["t_ex"], g, False)
+        # encoder_y through reparameterize(u)
+        if d_enc_u is None and d_u is not None:
+            d_enc_u = zeros(B, 2 * Wu)
+        if d_enc_u is not None:
+            if d_u is not None:
+                reparam_bwd(rt, ctx["enc_u"], ctx["eps_u"], d_u, Wu, d_enc_u, B, Wu, rng, 0)
+            g = rt.to_nhwc(d_enc_u, 2 * Wu, B, 2 * self.cu, h8, h8)
+            rt.net_backward(N["encoder_y"], ctx["t_ey"], g, False)
+
+    # ---- inference: Cond_SRVAE.sample (cond_vae.py:299-318) ---------------------------------------
+    def sample(self, y: torch.Tensor, samples: int, eps_u=None, eps_s=None, training: bool = False):
+        """S posterior-predictive decodes of ONE LR patch y [1,4,P/2,P/2] -> [S,4,P,P].
+        y_to_z(y) is identical for every sample, so it is computed once and broadcast (the reference
+        recomputes it on S expanded copies)."""
+        rt = self.rt
+        _require_cuda(y, "y")
+        rt.ensure()
+        rt.packs_dirty = True
+        rt.pack_weights()
+        P = self.P
+        if y.ndim == 3:
+            y = y.unsqueeze(0)
+        assert y.shape == (1, 4, P // 2, P // 2), "sample() takes a single LR patch"
+        y = y.contiguous().float()
+        dev = y.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        h8, h16 = P // 8, P // 16
+        Wz, Wu, c16, S = self.Wz, self.Wu, self.c16, samples
+        N = self.nets
+        y_nhwc = rt.to_nhwc(y, 4 * (P // 2) ** 2, 1, 4, P // 2, P // 2)
+        ey, _ = rt.net_forward(N["encoder_y"], y_nhwc, training, False)
+        enc_u = torch.empty((1, 2 * Wu), **f32)
+        rt.to_nchw(ey, enc_u, 2 * Wu)
+        u = torch.empty((1, Wu), **f32)
+        reparam_fwd(rt, enc_u, eps_u, u, Wu, 1, Wu, self.rng, 0)
+        yz, _ = rt.net_forward(N["y_to_z"], y_nhwc, training, False, bn_updates=2)
+        u16 = rt.to_nhwc(u, Wu, 1, self.cu16, h16, h16)
+        uz, _ = rt.net_forward(N["u_to_z"], u16, training, False)
+        joint = torch.empty((1, h16, h16, 2 * c16), device=dev, dtype=rt.dtype)
+        rows = h16 * h16
+        es = joint.element_size()
+        rt.copy2d(yz, c16, joint, 2 * c16, rows, c16)
+        lib.copy2d(_p(uz), rt.dt, c16, joint.data_ptr() + es * c16, rt.dt, 2 * c16, rows, c16, 0, _st())
+        m3, _ = rt.net_forward(N["mu_u_y_to_z"], joint, training, False)
+        l3, _ = rt.net_forward(N["logvar_u_y_to_z"], joint, training, False)
+        # enc3 rows = [mu3 | lv3] replicated S times so the reparam kernel can treat samples as batch rows
+        enc3 = torch.empty((S, 2 * Wz), **f32)
+        one = torch.empty((1, 2 * Wz), **f32)
+        rt.to_nchw(m3, one, 2 * Wz)
+        lib.nhwc_to_nchw(_p(l3), rt.dt, one.data_ptr() + 4 * Wz, F32, 2 * Wz, 1, c16, h16, h16, 0, _st())
+        lib.copy2d(_p(one), F32, 0, _p(enc3), F32, 2 * Wz, S, 2 * Wz, 0, _st())
+        stack = torch.empty((S, 2 * Wz), **f32)
+        yflat = torch.empty((1, Wz), **f32)
+        rt.to_nchw(yz, yflat, Wz)
+        lib.copy2d(_p(yflat), F32, 0, _p(stack), F32, 2 * Wz, S, Wz, 0, _st())
+        reparam_fwd(rt, enc3, eps_s, stack.data_ptr() + 4 * Wz, 2 * Wz, S, Wz, self.rng, 2)
+        rt.launches += 3
+        s8 = rt.to_nhwc(stack, 2 * Wz, S, 2 * self.cz, h8, h8)
+        xh, _ = rt.net_forward(N["decoder_x"], s8, training, False)
+        out = torch.empty((S, 4, P, P), **f32)
+        rt.to_nchw(xh, out, 4 * P * P)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE engine (vae.py:36-107)
+# ------------------------------------------------------------------------------------------------
+class VaeEngine:
+    def __init__(self, model: nn.Module, compute_dtype=torch.float32):
+        self.model = model
+        self.P = model.patch_size
+        self.L = model.latent_size
+        self.nets = {n: plan_sequential(n, getattr(model, n)) for n in ("encoder", "decoder")}
+        self.rt = Runtime(model, list(self.nets.values()), compute_dtype)
+        assert self.P % 4 == 0
+        self.c = self.L // 64
+        self.Wd = self.c * (self.P // 4) ** 2
+        if self.Wd % 4:
+            raise SvrsError("latent width must be a multiple of 4")
+        self.rng = RngState()
+
+    def forward(self, x, eps, training: bool, save: bool, repack: bool = True):
+        rt = self.rt
+        _require_cuda(x, "x")
+        rt.ensure()
+        if repack:
+            rt.packs_dirty = True
+        rt.pack_weights()
+        P, B, Wd = self.P, x.shape[0], self.Wd
+        assert x.shape[1:] == (4, P, P)
+        x = x.contiguous().float()
+        f32 = dict(device=x.device, dtype=torch.float32)
+        ctx = {}
+        x_nhwc = rt.to_nhwc(x, 4 * P * P, B, 4, P, P)
+        e, ctx["t_e"] = rt.net_forward(self.nets["encoder"], x_nhwc, training, save)
+        enc = torch.empty((B, 2 * Wd), **f32)
+        rt.to_nchw(e, enc, 2 * Wd)
+        z = torch.empty((B, Wd), **f32)
+        reparam_fwd(rt, enc, eps, z, Wd, B, Wd, self.rng, 0)
+        z4 = rt.to_nhwc(z, Wd, B, self.c, P // 4, P // 4)
+        d, ctx["t_d"] = rt.net_forward(self.nets["decoder"], z4, training, save)
+        x_hat = torch.empty((B, 4, P, P), **f32)
+        rt.to_nchw(d, x_hat, 4 * P * P)
+        if save:
+            ctx.update(B=B, enc=enc, eps=eps, rng=RngState(**vars(self.rng)))
+        return dict(x_hat=x_hat, enc=enc), ctx
+
+    def backward(self, ctx, d_xhat, d_enc):
+        rt = self.rt
+        P, B, Wd = self.P, ctx["B"], self.Wd
+        f32 = dict(device=ctx["enc"].device, dtype=torch.float32)
+        d_z = None
+        if d_xhat is not None:
+            g = rt.to_nhwc(d_xhat.contiguous(), 4 * P * P, B, 4, P, P)
+            dz4 = rt.net_backward(self.nets["decoder"], ctx["t_d"], g, True)
+            d_z = torch.empty((B, Wd), **f32)
+            rt.to_nchw(dz4, d_z, Wd)
+        if d_enc is None and d_z is not None:
+            d_enc = torch.empty((B, 2 * Wd), **f32)
+            lib.fill_zero(_p(d_enc), d_enc.numel() * 4, _st())
+            rt.launches += 1
+        if d_enc is not None:
+            if d_z is not None:
+                reparam_bwd(rt, ctx["enc"], ctx["eps"], d_z, Wd, d_enc, B, Wd, ctx["rng"], 0)
+            g = rt.to_nhwc(d_enc, 2 * Wd, B, 2 * self.c, P // 4, P // 4)
+            rt.net_backward(self.nets["encoder"], ctx["t_e"], g, False)

@@ -1,0 +1,80 @@
+"""Per-kernel device timing of the training step (CUDA events around every C-ABI launch, eager mode) and the
+roofline of the dominant kernel family for bench.py.  Not used on the timed path."""
+from __future__ import annotations
+
+from collections import defaultdict
+
+import torch
+
+from .lib import lib
+
+_ARGS = {n: [a for _, a in args] for n, (_, args) in lib.protos.items()}
+
+
+def _flops(name, a):
+    """Algorithmic FLOPs of one conv launch from its C-ABI arguments (2*M*K*N*taps)."""
+    d = dict(zip(_ARGS[name], a))
+    if name in ("svrs_conv2d_fprop", "svrs_conv2d_dgrad", "svrs_conv2d_wgrad"):
+        k = d["ksize"]
+        s = 1 if k == 3 else 2
+        return 2.0 * d["N"] * (d["H"] // s) * (d["W"] // s) * d["Cin"] * d["Cout"] * k * k
+    if name in ("svrs_convT2d_fprop", "svrs_convT2d_dgrad", "svrs_convT2d_wgrad"):
+        return 2.0 * d["N"] * d["H"] * d["W"] * d["Cin"] * d["Cout"] * 16
+    return 0.0
+
+
+FAMILY = {
+    "svrs_conv2d_fprop": "conv_taps (fprop/dgrad implicit GEMM)", "svrs_conv2d_dgrad": "conv_taps (fprop/dgrad implicit GEMM)",
+    "svrs_convT2d_fprop": "conv_taps (fprop/dgrad implicit GEMM)", "svrs_convT2d_dgrad": "conv_taps (fprop/dgrad implicit GEMM)",
+    "svrs_conv2d_wgrad": "wgrad_taps (weight-gradient implicit GEMM)", "svrs_convT2d_wgrad": "wgrad_taps (weight-gradient implicit GEMM)",
+}
+
+
+def time_step(run_eager_step, steps: int = 2):
+    """-> {abi function: (total ms, launches, total flops)} averaged per step."""
+    run_eager_step()                      # warm (allocator)
+    torch.cuda.synchronize()
+    lib.timing = []
+    try:
+        for _ in range(steps):
+            run_eager_step()
+        torch.cuda.synchronize()
+        rec = lib.timing
+    finally:
+        lib.timing = None
+    agg = defaultdict(lambda: [0.0, 0, 0.0])
+    for name, a, e0, e1 in rec:
+        r = agg[name]
+        r[0] += e0.elapsed_time(e1) / steps
+        r[1] += 1.0 / steps
+        r[2] += _flops(name, a) / steps
+    return {k: tuple(v) for k, v in agg.items()}
+
+
+def dominant_kernel_roofline(tr, step_from_device, inputs, pk, steps: int = 2):
+    import dataset
+
+    def eager():
+        lr, hr = inputs
+        P = tr.eng.P
+        if hasattr(tr.eng, "Wz"):
+            y = dataset.grid_patch_normalize(lr, P // 2)
+            x = dataset.grid_patch_normalize(hr, P)
+            tr.step(x, y, use_graph=False)
+        else:
+            tr.step(dataset.grid_patch_normalize(hr, P), use_graph=False)
+
+    per = time_step(eager, steps)
+    fam = defaultdict(lambda: [0.0, 0.0, 0.0])
+    total_ms = sum(v[0] for v in per.values())
+    for name, (ms, n, fl) in per.items():
+        f = fam[FAMILY.get(name, name)]
+        f[0] += ms; f[1] += n; f[2] += fl
+    top = max(fam.items(), key=lambda kv: kv[1][0])
+    name, (ms, n, fl) = top
+    achieved = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    shares = {k: round(v[0] / total_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])[:6]}
+    return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": pk["tf_sus"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tf_sus"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+            "launches_per_step": n, "ms_per_step_in_kernel": ms, "ms_per_step_all_kernels_eager": total_ms,
+            "share_of_step_by_family": shares}

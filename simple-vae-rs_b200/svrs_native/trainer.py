@@ -1,0 +1,234 @@
+"""The fused optimisation step: models/base.py:103-107 of the reference
+(zero_grad -> train_step -> backward -> clip_grad_norm_(1.0) -> Adam.step) as one kernel chain with no
+host synchronisation, optionally replayed from a CUDA graph and data-parallel over NCCL.
+
+Semantics kept from the reference:
+  * loss = mse_x + kld_u + mse_y + kld_z, NLL terms are SUMS, KL terms batch MEANS
+  * clipping covers module parameters only; gammas are a second Adam group, unclipped
+  * Adam: lr 1e-4, betas (0.9, 0.999), eps 1e-8 unless the torch optimizer passed to fit() says otherwise
+Data parallel (new capability, SURVEY 8.4 row e): every rank holds B_local samples; gradients are SUM
+all-reduced with the KL upstream gradients pre-scaled by 1/world so the result equals the single-process
+gradient on the global batch (up to per-rank BatchNorm statistics).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .elbo import elbo_forward
+from .engine import CondEngine, VaeEngine, _p, _st
+from .lib import F32, lib
+
+
+class _AdamCfg:
+    def __init__(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
+        self.lr, self.b1, self.b2, self.eps, self.max_norm = lr, betas[0], betas[1], eps, max_norm
+
+    def read(self, optimizer):
+        if optimizer is None:
+            return
+        g = optimizer.param_groups[0]
+        self.lr = float(g["lr"])
+        self.b1, self.b2 = (float(b) for b in g.get("betas", (self.b1, self.b2)))
+        self.eps = float(g.get("eps", self.eps))
+
+
+class _FusedBase:
+    n_gammas = 2
+
+    def __init__(self, engine, optimizer=None, max_norm: float = 1.0, process_group=None, overlap: bool = True):
+        self.eng = engine
+        self.rt = engine.rt
+        self.cfg = _AdamCfg(max_norm=max_norm)
+        self.cfg.read(optimizer)
+        self.optimizer = optimizer
+        self.pg = process_group
+        self.world = 1
+        self.rank = 0
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        self.overlap = overlap and self.world > 1
+        self.m = self.v = None
+        self._graphs: Dict[tuple, dict] = {}
+        self._comm_stream = None
+        self.steps_done = 0
+
+    # ---- state ----------------------------------------------------------------------------------
+    def _ensure_state(self):
+        rt = self.rt
+        rt.ensure()
+        store = rt.store
+        if self.m is None or self.m.device != store.flat.device or self.m.numel() != store.flat.numel():
+            dev = store.flat.device
+            self.m = torch.zeros_like(store.flat)
+            self.v = torch.zeros_like(store.flat)
+            self.step_ptr = torch.zeros(1, device=dev, dtype=torch.int64)
+            self.normacc = torch.zeros(1, device=dev, dtype=torch.float64)
+            self.gam = torch.ones(2, device=dev, dtype=torch.float32)
+            self.gam_m = torch.zeros(2, device=dev, dtype=torch.float32)
+            self.gam_v = torch.zeros(2, device=dev, dtype=torch.float32)
+            self.dgam = torch.zeros(2, device=dev, dtype=torch.float32)
+            self.gout = torch.tensor([1.0, 1.0 / self.world, 1.0, 1.0 / self.world], device=dev)
+            self._load_gammas_from_model()
+            self.eng.rng.step_ptr = self.step_ptr
+            self._graphs.clear()
+            rt.packs_dirty = True
+            if self.world > 1:
+                self._comm_stream = torch.cuda.Stream(device=dev)
+
+    def _gamma_attrs(self):
+        raise NotImplementedError
+
+    def _load_gammas_from_model(self):
+        vals = [float(getattr(self.eng.model, a).detach()) for a in self._gamma_attrs()]
+        while len(vals) < 2:
+            vals.append(1.0)
+        self.gam.copy_(torch.tensor(vals))
+
+    def sync_to_model(self):
+        """Write the device-resident gammas back to the model's (CPU) attributes; one D2H sync."""
+        if self.m is None:
+            return
+        host = self.gam.detach().cpu()
+        for i, a in enumerate(self._gamma_attrs()):
+            getattr(self.eng.model, a).data.fill_(float(host[i]))
+
+    # ---- optimizer tail ----------------------------------------------------------------------------
+    def _optim_tail(self):
+        rt, cfg, st = self.rt, self.cfg, _st()
+        store = rt.store
+        lib.fill_zero(_p(self.normacc), 8, st)
+        lib.sumsq(_p(store.grad), store.grad.numel(), _p(self.normacc), st)
+        lib.clip_adam(_p(store.flat), _p(store.grad), _p(self.m), _p(self.v), store.flat.numel(), _p(self.normacc),
+                      cfg.max_norm, 1.0, cfg.lr, cfg.b1, cfg.b2, cfg.eps, _p(self.step_ptr), st)
+        lib.clip_adam(_p(self.gam), _p(self.dgam), _p(self.gam_m), _p(self.gam_v), self.n_gammas, None,
+                      cfg.max_norm, 1.0, cfg.lr, cfg.b1, cfg.b2, cfg.eps, _p(self.step_ptr), st)
+        rt.launches += 4
+        rt.packs_dirty = True
+        rt.pack_weights()
+
+    def _allreduce_all(self):
+        if self.world == 1:
+            return
+        torch.distributed.all_reduce(self.rt.store.grad, group=self.pg)
+        torch.distributed.all_reduce(self.dgam, group=self.pg)
+
+    # ---- public ------------------------------------------------------------------------------------
+    def grad_norm(self) -> torch.Tensor:
+        return self.normacc.sqrt().float()
+
+    def _step_impl(self, *inputs):
+        raise NotImplementedError
+
+    def step(self, *inputs, use_graph: bool = False) -> torch.Tensor:
+        """One optimisation step on device-resident inputs.  Returns the device tensor
+        [mse_x, kld_u, mse_y, kld_z, loss] (Cond) / [mse, kld, 0, 0, loss] (VAE) of THIS rank's batch."""
+        self._ensure_state()
+        self.cfg.read(self.optimizer)
+        self.steps_done += 1
+        if not use_graph:
+            return self._step_impl(*inputs)
+        key = tuple((tuple(t.shape), t.dtype) for t in inputs) + (self.cfg.lr, self.rt.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            if self.steps_done == 1:
+                # first step runs eagerly (module loading, allocator warm-up); capture on the next one
+                return self._step_impl(*inputs)
+            static_in = [torch.empty_like(t) for t in inputs]
+            for s, t in zip(static_in, inputs):
+                s.copy_(t)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            l0 = self.rt.launches
+            with torch.cuda.graph(graph):
+                out = self._step_impl(*static_in)
+            g = dict(graph=graph, inputs=static_in, out=out, launches=self.rt.launches - l0)
+            self._graphs[key] = g
+        else:
+            for s, t in zip(g["inputs"], inputs):
+                if s.data_ptr() != t.data_ptr():
+                    s.copy_(t, non_blocking=True)
+            self.rt.launches += g["launches"]
+        g["graph"].replay()
+        return g["out"]
+
+    def static_inputs(self, *like):
+        """Device buffers a caller may fill directly (avoids the extra device copy before a replay)."""
+        key = tuple((tuple(t.shape), t.dtype) for t in like) + (self.cfg.lr, self.rt.dtype)
+        g = self._graphs.get(key)
+        return None if g is None else g["inputs"]
+
+
+class FusedCondTrainer(_FusedBase):
+    def __init__(self, model, optimizer=None, compute_dtype=None, **kw):
+        eng = model._engine(compute_dtype)
+        super().__init__(eng, optimizer, **kw)
+
+    def _gamma_attrs(self):
+        return ("gammax", "gammay")
+
+    def _step_impl(self, x, y, eps_u=None, eps_z=None):
+        eng, rt, st = self.eng, self.rt, _st()
+        B = x.shape[0]
+        Wz, Wu = eng.Wz, eng.Wu
+        lib.step_increment(_p(self.step_ptr), st)
+        rt.zero_grads()
+        rt.launches += 1
+        outs, ctx = eng.forward(x, y, eps_u, eps_z, training=True, save=True, repack=False)
+        enc_u, enc_z = outs["enc_u"], outs["enc_z"]
+        x_hat, y_hat, mu3, lv3 = outs["x_hat"], outs["y_hat"], outs["mu3"], outs["lv3"]
+        xf, yf = x.contiguous().float(), y.contiguous().float()
+        mu_u, lv_u = enc_u[:, :Wu], enc_u[:, Wu:]
+        mu_z, lv_z = enc_z[:, :Wz], enc_z[:, Wz:]
+        terms, acc = elbo_forward(x_hat, xf, y_hat, yf, mu_u, lv_u, mu_z, lv_z, mu3, lv3, self.gam, B)
+        d_xhat, d_yhat = torch.empty_like(x_hat), torch.empty_like(y_hat)
+        d_enc_u, d_enc_z = torch.empty_like(enc_u), torch.empty_like(enc_z)
+        d_mu3, d_lv3 = torch.empty_like(mu3), torch.empty_like(lv3)
+        lib.elbo_bwd(_p(x_hat), _p(xf), F32, x_hat.numel(), _p(d_xhat),
+                     _p(y_hat), _p(yf), F32, y_hat.numel(), _p(d_yhat),
+                     _p(mu_u), _p(lv_u), 2 * Wu, Wu, d_enc_u.data_ptr(), d_enc_u.data_ptr() + 4 * Wu, 2 * Wu,
+                     _p(mu_z), _p(lv_z), 2 * Wz, d_enc_z.data_ptr(), d_enc_z.data_ptr() + 4 * Wz, 2 * Wz,
+                     _p(mu3), _p(lv3), Wz, Wz, _p(d_mu3), _p(d_lv3), Wz,
+                     B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), st)
+        rt.launches += 3
+        eng.backward(ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3)
+        self._allreduce_all()
+        self._optim_tail()
+        return terms
+
+
+class FusedVaeTrainer(_FusedBase):
+    n_gammas = 1
+
+    def __init__(self, model, optimizer=None, compute_dtype=None, **kw):
+        eng = model._engine(compute_dtype)
+        super().__init__(eng, optimizer, **kw)
+
+    def _gamma_attrs(self):
+        return ("gamma",)
+
+    def _step_impl(self, x, eps=None):
+        eng, rt, st = self.eng, self.rt, _st()
+        B, Wd = x.shape[0], eng.Wd
+        lib.step_increment(_p(self.step_ptr), st)
+        rt.zero_grads()
+        rt.launches += 1
+        outs, ctx = eng.forward(x, eps, training=True, save=True, repack=False)
+        enc, x_hat = outs["enc"], outs["x_hat"]
+        xf = x.contiguous().float()
+        mu, lv = enc[:, :Wd], enc[:, Wd:]
+        terms, acc = elbo_forward(x_hat, xf, None, None, mu, lv, None, None, None, None, self.gam, B)
+        d_xhat, d_enc = torch.empty_like(x_hat), torch.empty_like(enc)
+        lib.elbo_bwd(_p(x_hat), _p(xf), F32, x_hat.numel(), _p(d_xhat),
+                     None, None, F32, 0, None,
+                     _p(mu), _p(lv), 2 * Wd, Wd, d_enc.data_ptr(), d_enc.data_ptr() + 4 * Wd, 2 * Wd,
+                     None, None, 0, None, None, 0,
+                     None, None, 0, 0, None, None, 0,
+                     B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), st)
+        rt.launches += 3
+        eng.backward(ctx, d_xhat, d_enc)
+        self._allreduce_all()
+        self._optim_tail()
+        return terms

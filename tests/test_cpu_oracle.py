@@ -1,0 +1,176 @@
+"""CPU tests (-m "not gpu"): the oracle restatement against the golden fixtures minted from the reference
+(oracle/make_golden.py), the first-principles numpy primitives against torch, and API-surface parity of the
+product's modules (state_dict keys/shapes, constructor geometry)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import np_primitives as npp
+from oracle import ref_oracle as O
+
+
+def _seeded_sd(kind, cr, P, seed=0):
+    """The product's constructors build layers in the reference's order, so a seed reproduces the reference's
+    initial weights (torch default init); `param_checksum` in the fixture detects RNG drift."""
+    import models
+    torch.manual_seed(seed)
+    m = models.Cond_SRVAE(cr, P) if kind == "cond" else models.VAE(cr, P)
+    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def _checksum_ok(sd, ref):
+    for k, v in ref.items():
+        d = sd[k].double()
+        if not torch.allclose(torch.stack([d.sum(), d.abs().sum()]), v, rtol=0, atol=0):
+            return False
+    return True
+
+
+@pytest.mark.parametrize("name", ["cond_cr2_p64_b2", "cond_cr1p5_p64_b2"])
+def test_oracle_cond_matches_golden(golden_dir, name):
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"))
+    model, sd = _seeded_sd("cond", fx["cr"], fx["P"])
+    assert list(sd.keys()) == list(fx["final_checksum"].keys()) or set(fx["param_checksum"]) <= set(sd)
+    if not _checksum_ok(sd, fx["param_checksum"]):
+        pytest.skip("torch RNG/init differs from the build that minted the fixture; re-mint with oracle/make_golden.py")
+    x, y = fx["x"], fx["y"]
+    outs = O.cond_forward({k: v.clone() for k, v in sd.items()}, fx["cr"], fx["P"], x, y, fx["eps_u"], fx["eps_z"], True)
+    names = ["x_hat", "y_hat", "mu_z", "logvar_z", "mu_u", "logvar_u", "mu_z_uy", "logvar_z_uy"]
+    for n, t in zip(names, outs):
+        torch.testing.assert_close(t, fx["outputs"][n], rtol=1e-5, atol=1e-5)
+    gam = {"gammax": torch.tensor(1.0), "gammay": torch.tensor(1.0)}
+    opt = O.AdamState(lr=fx["lr"])
+    terms, _, grads = O.cond_train_step(sd, gam, opt, fx["cr"], fx["P"], x, y, fx["eps_u"], fx["eps_z"], return_grads=True)
+    ref = fx["curve"][0]
+    for i, k in enumerate(["loss", "mse_x", "kld_u", "mse_y", "kld_z", "grad_norm"]):
+        assert abs(float(terms[k]) - float(ref[i])) <= 1e-5 * abs(float(ref[i])) + 1e-6, k
+    for k, v in fx["grads_small"].items():
+        torch.testing.assert_close(grads[k], v, rtol=1e-4, atol=1e-6)
+    assert abs(float(grads["gammax"]) - fx["grad_gammax"]) <= 1e-4 * abs(fx["grad_gammax"])
+    # BN running stats after ONE step: y_to_z advanced twice
+    if fx["steps"] == 1:
+        for k, v in fx["final_bn"].items():
+            torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6)
+        assert int(sd["y_to_z.0.bn.num_batches_tracked"]) == 2 and int(sd["encoder_x.0.bn.num_batches_tracked"]) == 1
+
+
+def test_oracle_vae_matches_golden(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "vae_cr2_p32_b4.pt"))
+    model, sd = _seeded_sd("vae", fx["cr"], fx["P"])
+    if not _checksum_ok(sd, fx["param_checksum"]):
+        pytest.skip("torch RNG/init differs from the build that minted the fixture")
+    gam, opt = {"gamma": torch.tensor(1.0)}, O.AdamState(lr=fx["lr"])
+    torch.manual_seed(fx["seed_step"])
+    Wd = fx["eps"].shape[1]
+    for it in range(fx["steps"]):
+        eps = torch.randn(fx["B"], Wd)     # the reference's torch.randn_like draws, replayed in order
+        if it == 0:
+            assert torch.equal(eps, fx["eps"])
+        terms = O.vae_train_step(sd, gam, opt, fx["cr"], fx["P"], fx["x"], eps)
+        assert abs(float(terms["loss"]) - float(fx["curve"][it][0])) <= 2e-5 * abs(float(fx["curve"][it][0]))
+    for k, v in fx["final_small"].items():
+        if k.endswith(("downsample.bias", "upsample.bias")):
+            # a conv bias that feeds a BatchNorm has a mathematically ZERO gradient; Adam turns its rounding noise
+            # into +-lr steps of random sign, so these entries are not reproducible even between two CPU runs.
+            assert float((sd[k] - v).abs().max()) <= 2.5 * fx["steps"] * fx["lr"]
+            continue
+        torch.testing.assert_close(sd[k], v, rtol=1e-4, atol=2e-6)
+    assert abs(float(gam["gamma"]) - fx["final_gamma"]) < 1e-6
+
+
+def test_baseline_md_golden_value(golden_dir):
+    """loss 6905.3315 for the seeded config-1 recipe."""
+    fx = torch.load(os.path.join(golden_dir, "cond_cr2_p64_b8.pt"))
+    assert abs(float(fx["curve"][0][0]) - 6905.33154296875) < 1e-2
+    assert fx["oracle_vs_reference_maxabs"] <= 1e-4
+
+
+def test_np_primitives_match_torch():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 3, 6, 8))
+    w3, w4, wt = rng.standard_normal((5, 3, 3, 3)), rng.standard_normal((5, 3, 4, 4)), rng.standard_normal((3, 5, 4, 4))
+    b = rng.standard_normal(5)
+    tx = torch.from_numpy(x)
+    np.testing.assert_allclose(npp.conv2d(x, w3, b, 1, 1), F.conv2d(tx, torch.from_numpy(w3), torch.from_numpy(b), 1, 1).numpy(), atol=1e-12)
+    np.testing.assert_allclose(npp.conv2d(x, w4, b, 2, 1), F.conv2d(tx, torch.from_numpy(w4), torch.from_numpy(b), 2, 1).numpy(), atol=1e-12)
+    np.testing.assert_allclose(npp.conv_transpose2d_k4s2p1(x, wt, b),
+                               F.conv_transpose2d(tx, torch.from_numpy(wt), torch.from_numpy(b), 2, 1).numpy(), atol=1e-12)
+    g, be = rng.standard_normal(3), rng.standard_normal(3)
+    rm, rv = torch.zeros(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64)
+    ref = F.batch_norm(tx, rm, rv, torch.from_numpy(g), torch.from_numpy(be), True, 0.1, 1e-5)
+    y, mean, unb = npp.batchnorm_train(x, g, be)
+    np.testing.assert_allclose(y, ref.numpy(), atol=1e-10)
+    np.testing.assert_allclose(0.1 * mean, rm.numpy(), atol=1e-12)
+    np.testing.assert_allclose(0.9 + 0.1 * unb, rv.numpy(), atol=1e-12)
+    p = torch.randn(50, dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([p], lr=1e-4)
+    pn, m, v = p.detach().numpy().copy(), np.zeros(50), np.zeros(50)
+    for t in range(1, 4):
+        gr = rng.standard_normal(50)
+        p.grad = torch.from_numpy(gr.copy())
+        opt.step()
+        pn, m, v = npp.adam_step(pn, gr, m, v, t)
+    np.testing.assert_allclose(pn, p.detach().numpy(), atol=1e-12)
+    grads = [rng.standard_normal(7), rng.standard_normal((3, 4))]
+    tg = [torch.from_numpy(a.copy()).requires_grad_(True) for a in grads]
+    for a, gnp in zip(tg, grads):
+        a.grad = torch.from_numpy(gnp.copy())
+    tot = torch.nn.utils.clip_grad_norm_(tg, 1.0)
+    total, coef = npp.clip_coef(grads)
+    assert abs(total - float(tot)) < 1e-12 and abs(coef - 1.0 / (total + 1e-6)) < 1e-12
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors from the Random123 distribution (kat_vectors):
+    counter = key = 0 and counter = key = 0xffffffff."""
+    assert npp.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert npp.philox4x32_10([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+
+
+def test_grid_oracle_matches_golden(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "grid_vectors.pt"))
+    y, x = O.grid_batch(fx["lr"].float(), fx["hr"].float(), 64)
+    assert torch.equal(y, fx["y"]) and torch.equal(x, fx["x"])
+    assert x.shape == (32, 4, 64, 64) and y.shape == (32, 4, 32, 32)
+    # patch index = tile*16 + row*4 + col, HR patch at (row*64, col*64) (dataset.py:220-228)
+    p = O.select_crop(fx["hr"][1].float(), 64, 6)
+    assert torch.equal(O.normalize_image(p), x[16 + 6])
+    assert float(x.min()) == 0.0 and float(x.max()) <= 1.0
+
+
+@pytest.mark.parametrize("cr,P,nkeys,nparams", [(2, 64, 165, 20586020), (1.5, 64, 165, 32430350)])
+def test_cond_api_surface(cr, P, nkeys, nparams):
+    model, sd = _seeded_sd("cond", cr, P)
+    assert len(sd) == nkeys and model.num_params == nparams
+    assert model.latent_size == O.cond_latent_sizes(cr, P)[0] and model.latent_size_y == model.latent_size // 4
+    assert sd["decoder_x.1.upsample.weight"].shape[1] == 256        # ConvTranspose2d weight is [Cin, Cout, 4, 4]
+    assert not isinstance(model.gammax, torch.nn.Parameter) and model.gammax.requires_grad and model.gammax.device.type == "cpu"
+    assert "gammax" not in sd
+    for n in ("forward", "encode_x", "encode_y", "reparameterize", "z_cond", "decode_x", "decode_y", "conditional_generation",
+              "sample", "generation", "train_step", "val_step", "evaluate", "on_train_start", "on_train_epoch_end",
+              "get_task_data", "fit", "task", "log"):
+        assert callable(getattr(model, n)), n
+
+
+def test_vae_api_surface():
+    model, sd = _seeded_sd("vae", 2, 64)
+    assert len(sd) == 52 and model.num_params == 1311672
+    assert model.latent_size == O.vae_latent_size(2, 64) == 8192
+    m2, _ = _seeded_sd("vae", 1.28, 32)
+    assert m2.latent_size == 3184                                   # script_vae.sh geometry
+
+
+def test_plan_matches_reference_layer_table():
+    """The kernel plan derived from the modules reproduces SURVEY 8.2's layer list for Cond_SRVAE(2, 64)."""
+    from svrs_native.engine import BNOp, ConvOp, plan_sequential
+    model, _ = _seeded_sd("cond", 2, 64)
+    net = plan_sequential("decoder_x", model.decoder_x)
+    kinds = [(op.kind, op.cin, op.cout) if isinstance(op, ConvOp) else ("bn", op.mod.num_features) for op in net.ops]
+    assert kinds == [("c3", 256, 256), ("ct", 256, 256), ("bn", 256), ("c3", 256, 256), ("ct", 256, 128), ("bn", 128),
+                     ("c3", 128, 128), ("ct", 128, 64), ("bn", 64), ("c3", 64, 64), ("c3", 64, 16), ("c3", 16, 16), ("c3", 16, 4)]
+    assert net.ops[-1].act == 1                                       # Sigmoid fused into the last conv
+    lv = plan_sequential("logvar_u_y_to_z", model.logvar_u_y_to_z)
+    assert [(o.cin, o.cout) for o in lv.ops] == [(1024, 512), (512, 512)] and lv.ops[-1].act == 2   # Hardtanh(-7,7)
