@@ -428,3 +428,40 @@ def grid_batch(lr_tiles: Tensor, hr_tiles: Tensor, patch_size: int) -> Tuple[Ten
         ys.append(normalize_image(grid_crop(lr_tiles[t], patch_size // 2)))
         xs.append(normalize_image(grid_crop(hr_tiles[t], patch_size)))
     return torch.cat(ys, dim=0), torch.cat(xs, dim=0)
+
+
+# ----------------------------------------------------------------------------
+# portable seeded tensors for fixtures
+# ----------------------------------------------------------------------------
+# torch's CPU generator is NOT bit-stable across hosts for large tensors (the vectorised fill depends on the
+# CPU's ISA / thread split: fixtures minted in the build container did not reproduce on the GPU box).  Fixtures
+# therefore derive weights, inputs and eps from numpy's PCG64, which is.
+def portable_state_dict(template: SD, seed: int) -> SD:
+    """Same distribution as torch's default Conv/ConvT init (kaiming_uniform(a=sqrt 5) == U(-1/sqrt(fan_in), .),
+    fan_in = weight.size(1)*k*k); BatchNorm weight/bias/buffers keep their defaults."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out, bound = {}, None
+    for k, v in template.items():
+        if v.dim() == 4:
+            bound = 1.0 / math.sqrt(v.shape[1] * v.shape[2] * v.shape[3])
+            out[k] = torch.from_numpy(rng.uniform(-bound, bound, size=tuple(v.shape)).astype(np.float32))
+        elif k.endswith(".bias") and ".bn." not in k:
+            out[k] = torch.from_numpy(rng.uniform(-bound, bound, size=tuple(v.shape)).astype(np.float32))
+        else:
+            out[k] = v.detach().clone()
+    return out
+
+
+class PortableRng:
+    def __init__(self, seed: int):
+        import numpy as np
+        self._rng = np.random.default_rng(seed)
+
+    def rand(self, *shape) -> Tensor:
+        import numpy as np
+        return torch.from_numpy(self._rng.random(size=shape).astype(np.float32))
+
+    def randn(self, *shape) -> Tensor:
+        import numpy as np
+        return torch.from_numpy(self._rng.standard_normal(size=shape).astype(np.float32))

@@ -74,7 +74,8 @@ class Cond_SRVAE(BaseVAE):
     def _run(self, x, y, eps_u=None, eps_z=None):
         from svrs_native.autograd import CondForwardFn
         eng = self._engine()
-        return CondForwardFn.apply(self._grad_anchor(x.device), eng, x, y, eps_u, eps_z, self.training)
+        return CondForwardFn.apply(self._grad_anchor(x.device), eng, x, y, eps_u, eps_z, self.training,
+                                   torch.is_grad_enabled())
 
     # ------------------------------------------------------------------ reference API
     def forward(self, x, y, eps_u=None, eps_z=None):

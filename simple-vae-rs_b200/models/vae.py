@@ -42,7 +42,8 @@ class VAE(BaseVAE):
     # ------------------------------------------------------------------ reference API
     def forward(self, x, eps=None):
         from svrs_native.autograd import VaeForwardFn
-        x_hat, enc = VaeForwardFn.apply(self._grad_anchor(x.device), self._engine(), x, eps, self.training)
+        x_hat, enc = VaeForwardFn.apply(self._grad_anchor(x.device), self._engine(), x, eps, self.training,
+                                        torch.is_grad_enabled())
         mu, logvar = enc.chunk(2, dim=1)                                   # vae.py:89-92
         return x_hat, mu, logvar
 

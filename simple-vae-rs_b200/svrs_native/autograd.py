@@ -23,8 +23,8 @@ def _publish_grads(rt):
 
 class CondForwardFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, eng: CondEngine, x, y, eps_u, eps_z, training: bool):
-        need = torch.is_grad_enabled() and training
+    def forward(ctx, anchor, eng: CondEngine, x, y, eps_u, eps_z, training: bool, need: bool):
+        # `need` is decided by the caller: grad mode is always off inside Function.forward
         outs, ectx = eng.forward(x, y, eps_u, eps_z, training=training, save=need)
         ctx.eng, ctx.ectx = eng, ectx
         return outs["x_hat"], outs["y_hat"], outs["enc_z"], outs["enc_u"], outs["mu3"], outs["lv3"]
@@ -38,13 +38,12 @@ class CondForwardFn(torch.autograd.Function):
         eng.backward(ctx.ectx, d_xhat, d_yhat, cl(d_enc_z), cl(d_enc_u), d_mu3, d_lv3)
         _publish_grads(rt)
         ctx.ectx = None
-        return (None,) * 7
+        return (None,) * 8
 
 
 class VaeForwardFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, eng: VaeEngine, x, eps, training: bool):
-        need = torch.is_grad_enabled() and training
+    def forward(ctx, anchor, eng: VaeEngine, x, eps, training: bool, need: bool):
         outs, ectx = eng.forward(x, eps, training=training, save=need)
         ctx.eng, ctx.ectx = eng, ectx
         return outs["x_hat"], outs["enc"]
@@ -57,4 +56,4 @@ class VaeForwardFn(torch.autograd.Function):
         eng.backward(ctx.ectx, d_xhat, None if d_enc is None else d_enc.contiguous().clone())
         _publish_grads(rt)
         ctx.ectx = None
-        return (None,) * 5
+        return (None,) * 6

@@ -12,64 +12,60 @@ from oracle import np_primitives as npp
 from oracle import ref_oracle as O
 
 
+import fixtures as FX
+
+
 def _seeded_sd(kind, cr, P, seed=0):
-    """The product's constructors build layers in the reference's order, so a seed reproduces the reference's
-    initial weights (torch default init); `param_checksum` in the fixture detects RNG drift."""
-    import models
-    torch.manual_seed(seed)
-    m = models.Cond_SRVAE(cr, P) if kind == "cond" else models.VAE(cr, P)
-    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
-
-
-def _checksum_ok(sd, ref):
-    for k, v in ref.items():
-        d = sd[k].double()
-        if not torch.allclose(torch.stack([d.sum(), d.abs().sum()]), v, rtol=0, atol=0):
-            return False
-    return True
+    return FX.build(kind, cr, P, seed)
 
 
 @pytest.mark.parametrize("name", ["cond_cr2_p64_b2", "cond_cr1p5_p64_b2"])
 def test_oracle_cond_matches_golden(golden_dir, name):
-    fx = torch.load(os.path.join(golden_dir, name + ".pt"))
-    model, sd = _seeded_sd("cond", fx["cr"], fx["P"])
-    assert list(sd.keys()) == list(fx["final_checksum"].keys()) or set(fx["param_checksum"]) <= set(sd)
-    if not _checksum_ok(sd, fx["param_checksum"]):
-        pytest.skip("torch RNG/init differs from the build that minted the fixture; re-mint with oracle/make_golden.py")
-    x, y = fx["x"], fx["y"]
-    outs = O.cond_forward({k: v.clone() for k, v in sd.items()}, fx["cr"], fx["P"], x, y, fx["eps_u"], fx["eps_z"], True)
+    fx = FX.load(golden_dir, name)
+    model, sd = FX.build(fx)
+    assert FX.checksum_ok(sd, fx["param_checksum"]), "portable weights did not reproduce"
+    x, y = FX.inputs(fx)
+    eu, ez = fx["eps"]
+    outs = O.cond_forward({k: v.clone() for k, v in sd.items()}, fx["cr"], fx["P"], x, y, eu, ez, True)
     names = ["x_hat", "y_hat", "mu_z", "logvar_z", "mu_u", "logvar_u", "mu_z_uy", "logvar_z_uy"]
     for n, t in zip(names, outs):
         torch.testing.assert_close(t, fx["outputs"][n], rtol=1e-5, atol=1e-5)
     gam = {"gammax": torch.tensor(1.0), "gammay": torch.tensor(1.0)}
     opt = O.AdamState(lr=fx["lr"])
-    terms, _, grads = O.cond_train_step(sd, gam, opt, fx["cr"], fx["P"], x, y, fx["eps_u"], fx["eps_z"], return_grads=True)
-    ref = fx["curve"][0]
-    for i, k in enumerate(["loss", "mse_x", "kld_u", "mse_y", "kld_z", "grad_norm"]):
-        assert abs(float(terms[k]) - float(ref[i])) <= 1e-5 * abs(float(ref[i])) + 1e-6, k
+    stream = FX.eps_stream(fx, (eu.shape[1], ez.shape[1]))
+    for it in range(fx["steps"]):
+        e = next(stream)
+        if it == 0:
+            assert torch.equal(e[0], eu) and torch.equal(e[1], ez)
+        res = O.cond_train_step(sd, gam, opt, fx["cr"], fx["P"], x, y, e[0], e[1], return_grads=(it == 0))
+        terms = res[0] if it == 0 else res
+        if it == 0:
+            grads = res[2]
+        ref = fx["curve"][it]
+        for i, k in enumerate(["loss", "mse_x", "kld_u", "mse_y", "kld_z", "grad_norm"]):
+            assert abs(float(terms[k]) - float(ref[i])) <= 2e-5 * abs(float(ref[i])) + 1e-6, (it, k)
     for k, v in fx["grads_small"].items():
         torch.testing.assert_close(grads[k], v, rtol=1e-4, atol=1e-6)
-    assert abs(float(grads["gammax"]) - fx["grad_gammax"]) <= 1e-4 * abs(fx["grad_gammax"])
-    # BN running stats after ONE step: y_to_z advanced twice (SURVEY Q1)
-    if fx["steps"] == 1:
-        for k, v in fx["final_bn"].items():
-            torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6)
-        assert int(sd["y_to_z.0.bn.num_batches_tracked"]) == 2 and int(sd["encoder_x.0.bn.num_batches_tracked"]) == 1
+    assert abs(float(grads["gammax"]) - fx["grad_gammas"]["gammax"]) <= 1e-4 * abs(fx["grad_gammas"]["gammax"])
+    # BN running stats: y_to_z advanced twice per step
+    for k, v in fx["final_bn"].items():
+        torch.testing.assert_close(sd[k].float(), v.float(), rtol=1e-4, atol=1e-5)
+    assert int(sd["y_to_z.0.bn.num_batches_tracked"]) == 2 * fx["steps"]
+    assert int(sd["encoder_x.0.bn.num_batches_tracked"]) == fx["steps"]
 
 
 def test_oracle_vae_matches_golden(golden_dir):
-    fx = torch.load(os.path.join(golden_dir, "vae_cr2_p32_b4.pt"))
-    model, sd = _seeded_sd("vae", fx["cr"], fx["P"])
-    if not _checksum_ok(sd, fx["param_checksum"]):
-        pytest.skip("torch RNG/init differs from the build that minted the fixture")
+    fx = FX.load(golden_dir, "vae_cr2_p32_b4")
+    model, sd = FX.build(fx)
+    assert FX.checksum_ok(sd, fx["param_checksum"])
+    x, _ = FX.inputs(fx)
     gam, opt = {"gamma": torch.tensor(1.0)}, O.AdamState(lr=fx["lr"])
-    torch.manual_seed(fx["seed_step"])
-    Wd = fx["eps"].shape[1]
+    stream = FX.eps_stream(fx, (fx["eps"][0].shape[1],))
     for it in range(fx["steps"]):
-        eps = torch.randn(fx["B"], Wd)     # the reference's torch.randn_like draws, replayed in order
+        (eps,) = next(stream)
         if it == 0:
-            assert torch.equal(eps, fx["eps"])
-        terms = O.vae_train_step(sd, gam, opt, fx["cr"], fx["P"], fx["x"], eps)
+            assert torch.equal(eps, fx["eps"][0])
+        terms = O.vae_train_step(sd, gam, opt, fx["cr"], fx["P"], x, eps)
         assert abs(float(terms["loss"]) - float(fx["curve"][it][0])) <= 2e-5 * abs(float(fx["curve"][it][0]))
     for k, v in fx["final_small"].items():
         if k.endswith(("downsample.bias", "upsample.bias")):
@@ -78,14 +74,14 @@ def test_oracle_vae_matches_golden(golden_dir):
             assert float((sd[k] - v).abs().max()) <= 2.5 * fx["steps"] * fx["lr"]
             continue
         torch.testing.assert_close(sd[k], v, rtol=1e-4, atol=2e-6)
-    assert abs(float(gam["gamma"]) - fx["final_gamma"]) < 1e-6
+    assert abs(float(gam["gamma"]) - fx["final_gammas"]["gamma"]) < 1e-6
 
 
 def test_baseline_md_golden_value(golden_dir):
-    """loss 6905.3315 for the seeded config-1 recipe."""
-    fx = torch.load(os.path.join(golden_dir, "cond_cr2_p64_b8.pt"))
-    assert abs(float(fx["curve"][0][0]) - 6905.33154296875) < 1e-2
-    assert fx["oracle_vs_reference_maxabs"] <= 1e-4
+    """loss 6905.3315 for the torch-seeded config-1 recipe, minted from the reference."""
+    fx = FX.load(golden_dir, "baseline_md_recipe")
+    assert abs(fx["loss"] - 6905.33154296875) < 1e-2
+    assert abs(fx["mse_x"] - 5484.6904296875) < 1e-2 and abs(fx["kld_z"] - 43.54631805419922) < 1e-3
 
 
 def test_np_primitives_match_torch():

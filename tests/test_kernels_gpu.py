@@ -106,16 +106,17 @@ def test_conv_first_principles_numpy():
     wt = torch.randn(3, 5, 4, 4, generator=g)
     b = torch.randn(5, generator=g)
     xd = nhwc(x.to(DEV))
+    bd = b.to(DEV)          # keep device tensors alive: a temporary's storage is recycled as soon as data_ptr() returns
     for ks, w in ((3, w3), (4, w4)):
         ref = npp.conv2d(x.numpy(), w.numpy(), b.numpy(), 1 if ks == 3 else 2, 1)
         pf, _ = pack(w.to(DEV), torch.float32)
         y = torch.empty((2, ref.shape[2], ref.shape[3], 5), device=DEV)
-        lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), b.to(DEV).data_ptr(), y.data_ptr(), F32, 2, 6, 6, 3, 5, ks, 0, st())
+        lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), bd.data_ptr(), y.data_ptr(), F32, 2, 6, 6, 3, 5, ks, 0, st())
         report(f"conv{ks} vs numpy definition", nchw(y), torch.from_numpy(ref), 1e-5)
     ref = npp.conv_transpose2d_k4s2p1(x.numpy(), wt.numpy(), b.numpy())
     pf, _ = pack(wt.to(DEV), torch.float32, convT=True)
     y = torch.empty((2, 12, 12, 5), device=DEV)
-    lib.convT2d_fprop(xd.data_ptr(), pf.data_ptr(), b.to(DEV).data_ptr(), y.data_ptr(), F32, 2, 6, 6, 3, 5, 0, st())
+    lib.convT2d_fprop(xd.data_ptr(), pf.data_ptr(), bd.data_ptr(), y.data_ptr(), F32, 2, 6, 6, 3, 5, 0, st())
     report("convT vs numpy definition", nchw(y), torch.from_numpy(ref), 1e-5)
 
 
@@ -131,8 +132,9 @@ def test_conv_epilogue_activation_and_backward(act, fn):
     yr.backward(gy)
     pf, _ = pack(w.to(DEV), torch.float32)
     xd = nhwc(x.to(DEV))
+    bd = b.to(DEV)
     y = torch.empty((2, 4, 4, 12), device=DEV)
-    lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), b.to(DEV).data_ptr(), y.data_ptr(), F32, 2, 4, 4, 8, 12, 3, act, st())
+    lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), bd.data_ptr(), y.data_ptr(), F32, 2, 4, 4, 8, 12, 3, act, st())
     report(f"conv + act {act}", nchw(y), yr, 1e-5)
     gyd = nhwc(gy.float().to(DEV))
     lib.act_bwd(y.data_ptr(), gyd.data_ptr(), gyd.data_ptr(), F32, act, gyd.numel(), st())
@@ -161,8 +163,9 @@ def test_batchnorm_train_fwd_bwd(shape, dtype):
     rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
     nbt = torch.zeros((), device=DEV, dtype=torch.int64)
     scale, shift, mean, invstd = (torch.empty(C, device=DEV) for _ in range(4))
+    gam_d, bet_d = gam.to(DEV), bet.to(DEV)
     lib.bn_stats(xd.data_ptr(), dt(dtype), M, C, sums.data_ptr(), st())
-    lib.bn_finalize_train(sums.data_ptr(), M, C, gam.to(DEV).data_ptr(), bet.to(DEV).data_ptr(), 1e-5, 0.1, rm.data_ptr(),
+    lib.bn_finalize_train(sums.data_ptr(), M, C, gam_d.data_ptr(), bet_d.data_ptr(), 1e-5, 0.1, rm.data_ptr(),
                           rv.data_ptr(), nbt.data_ptr(), 1, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), st())
     y = torch.empty_like(xd)
     lib.bn_apply(xd.data_ptr(), y.data_ptr(), dt(dtype), M, C, scale.data_ptr(), shift.data_ptr(), 1, st())
@@ -172,7 +175,6 @@ def test_batchnorm_train_fwd_bwd(shape, dtype):
     assert int(nbt) == 1
     sums2 = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
     dgam, dbet = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-    gam_d = gam.to(DEV)
     lib.bn_bwd_reduce(xd.data_ptr(), gyd.data_ptr(), dt(dtype), M, C, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
                       invstd.data_ptr(), 1, sums2.data_ptr(), st())
     dx = torch.empty_like(xd)
@@ -183,7 +185,7 @@ def test_batchnorm_train_fwd_bwd(shape, dtype):
     report("bn dbeta", dbet, bn.bias.grad, 2e-5)
     # second running-stat update in one call (y_to_z runs twice per forward)
     rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
-    lib.bn_finalize_train(sums.data_ptr(), M, C, gam_d.data_ptr(), bet.to(DEV).data_ptr(), 1e-5, 0.1, rm2.data_ptr(),
+    lib.bn_finalize_train(sums.data_ptr(), M, C, gam_d.data_ptr(), bet_d.data_ptr(), 1e-5, 0.1, rm2.data_ptr(),
                           rv2.data_ptr(), nbt.data_ptr(), 2, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), st())
     bn(x.double())
     report("bn running_mean after 2 updates", rm2, bn.running_mean, 1e-6)
@@ -334,7 +336,8 @@ def test_elbo_against_golden_vectors(golden_dir):
     l2 = {k: t[k].clone().requires_grad_(True) for k in ("recon_x", "mu2", "lv2")}
     g1 = torch.tensor(b["gamma"], requires_grad=True)
     mse, kld = base_loss(l2["recon_x"], t["x"], l2["mu2"], l2["lv2"], g1)
-    report("base_loss mse", mse.reshape(1), torch.tensor([b["terms"][0]]), 1e-6)
+    # d*(ssq/(2 g^2 d) + log g) with g < 1 cancels two ~3e2 numbers down to ~0.2: compare against that magnitude
+    report("base_loss mse", mse.reshape(1), torch.tensor([b["terms"][0]]), 1e-6, atol=3e-7 * t["recon_x"].numel() * 0.106)
     report("base_loss kld", kld.reshape(1), torch.tensor([b["terms"][1]]), 1e-6)
     (mse + kld).backward()
     for k, ref in b["grads"].items():
