@@ -57,14 +57,25 @@ int svrs_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, 
 int svrs_pack_weights(const float* w, int d0, int d1, int kk, void* p01, void* p10, int dtype,
                       void* stream);
 
+/* Two kernels sit behind each fprop/dgrad entry point:
+ *   - conv_tc   (csrc/conv_tc.cu): tcgen05.mma + TMEM accumulators + TMA-fed SWIZZLE_128B operands; taken when
+ *     dtype == BF16, the reduction channels are a multiple of 64, the written channels a multiple of 16 and the
+ *     output map tiles into 128-pixel boxes; it consumes the NK pack `w_nk` = [tap][N][K] (K contiguous).
+ *   - conv_simt (csrc/conv_simt.cu): fp32-FMA multi-tap GEMM for everything else (fp32 parity mode, 4/16-channel
+ *     layers, odd channel counts); it consumes the KN pack `w_kn` = [tap][K][N].
+ * The two packs of a layer are each other's transposes, i.e. the (p01, p10) pair of svrs_pack_weights: the KN pack
+ * of fprop is the NK pack of dgrad and vice versa.  w_nk may be NULL (forces the SIMT kernel). */
+void svrs_set_tc_enabled(int enabled);   /* default 1; 0 forces the SIMT kernels everywhere (A/B tests) */
+int svrs_tc_would_run(int dtype, int K, int Nc, int OH, int OW); /* 1 if conv_tc takes a GEMM of these dims */
+
 /* ---- nn.Conv2d k3 s1 p1 / k4 s2 p1 (layers.py:231-236; every bare nn.Conv2d of cond_vae.py / vae.py)
  *      x [N,H,W,Cin] -> y [N,H/s,W/s,Cout];  w_kn = p10 pack [tap][Cin][Cout]; bias fp32 [Cout] or NULL.
  *      ksize 3 => stride 1, ksize 4 => stride 2 (pad 1 both). */
-int svrs_conv2d_fprop(const void* x, const void* w_kn, const float* bias, void* y, int dtype,
+int svrs_conv2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
                       int N, int H, int W, int Cin, int Cout, int ksize, int act, void* stream);
 /* dgrad: dy [N,H/s,W/s,Cout] -> dx [N,H,W,Cin]; w_kn = p01 pack [tap][Cout][Cin].
  * (autograd of the same call sites, reached through loss.backward() models/base.py:105) */
-int svrs_conv2d_dgrad(const void* dy, const void* w_kn, void* dx, int dtype,
+int svrs_conv2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
                       int N, int H, int W, int Cin, int Cout, int ksize, void* stream);
 /* wgrad: dw[Cout][Cin][k][k] += sum x (*) dy  (fp32, torch layout, ATOMIC accumulate - zero it first);
  * db[Cout] += column sums of dy when db != NULL.  `ksplit` <= 0 picks a split automatically. */
@@ -73,10 +84,10 @@ int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float* db, int d
 
 /* ---- nn.ConvTranspose2d k4 s2 p1 (layers.py:275-277): x [N,H,W,Cin] -> y [N,2H,2W,Cout].
  *      four output-parity sub-convolutions of 2x2 taps.  w_kn = p01 pack [tap][Cin][Cout]. */
-int svrs_convT2d_fprop(const void* x, const void* w_kn, const float* bias, void* y, int dtype,
+int svrs_convT2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
                        int N, int H, int W, int Cin, int Cout, int act, void* stream);
 /* dgrad: dy [N,2H,2W,Cout] -> dx [N,H,W,Cin]; w_kn = p10 pack [tap][Cout][Cin]. */
-int svrs_convT2d_dgrad(const void* dy, const void* w_kn, void* dx, int dtype,
+int svrs_convT2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
                        int N, int H, int W, int Cin, int Cout, void* stream);
 /* wgrad: dw[Cin][Cout][4][4] += ... ; db[Cout] += column sums of dy. */
 int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, float* db, int dtype,

@@ -349,15 +349,32 @@ static int launch_colsum(const void* x, int dtype, long long M, int C, float* ou
 
 }  // namespace svrs
 
+namespace svrs {
+bool tc_supported(int dtype, int K, int Nc, int OW, int OH);
+int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
+                   int act, cudaStream_t st);
+static int g_tc_enabled = 1;
+static inline bool use_tc(const void* w_nk, int dtype, int K, int Nc, int OW, int OH) {
+    return g_tc_enabled && w_nk != nullptr && tc_supported(dtype, K, Nc, OW, OH);
+}
+}  // namespace svrs
+
 using namespace svrs;
 
 static bool dtype_ok(int d) { return d == SVRS_F32 || d == SVRS_BF16; }
 
-extern "C" int svrs_conv2d_fprop(const void* x, const void* w_kn, const float* bias, void* y, int dtype,
+extern "C" void svrs_set_tc_enabled(int enabled) { svrs::g_tc_enabled = enabled; }
+extern "C" int svrs_tc_would_run(int dtype, int K, int Nc, int OH, int OW) {
+    return svrs::g_tc_enabled && svrs::tc_supported(dtype, K, Nc, OW, OH) ? 1 : 0;
+}
+
+extern "C" int svrs_conv2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
                                  int N, int H, int W, int Cin, int Cout, int ksize, int act, void* stream) {
     SVRS_CHECK_ARG(x && w_kn && y && dtype_ok(dtype), "conv2d_fprop: null pointer or bad dtype");
     SVRS_CHECK_ARG(ksize == 3 || (ksize == 4 && H % 2 == 0 && W % 2 == 0), "conv2d_fprop: ksize must be 3, or 4 with even H,W");
     SVRS_CHECK_ARG(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv2d_fprop: bad dims");
+    if (N > 0 && use_tc(w_nk, dtype, Cin, Cout, ksize == 3 ? W : W / 2, ksize == 3 ? H : H / 2))
+        return launch_conv_tc(ksize == 3 ? 0 : 2, x, w_nk, bias, y, N, H, W, Cin, Cout, act, (cudaStream_t)stream);
     ConvArgs a;
     a.in = x; a.out = y; a.w = w_kn; a.bias = bias; a.act = act;
     if (ksize == 3) geom_conv3(a.g, N, H, W, Cin, Cout, false);
@@ -365,10 +382,14 @@ extern "C" int svrs_conv2d_fprop(const void* x, const void* w_kn, const float* b
     return launch_conv(a, dtype, (cudaStream_t)stream);
 }
 
-extern "C" int svrs_conv2d_dgrad(const void* dy, const void* w_kn, void* dx, int dtype,
+extern "C" int svrs_conv2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
                                  int N, int H, int W, int Cin, int Cout, int ksize, void* stream) {
     SVRS_CHECK_ARG(dy && w_kn && dx && dtype_ok(dtype), "conv2d_dgrad: null pointer or bad dtype");
     SVRS_CHECK_ARG(ksize == 3 || (ksize == 4 && H % 2 == 0 && W % 2 == 0), "conv2d_dgrad: ksize must be 3, or 4 with even H,W");
+    if (N > 0 && ksize == 3 && use_tc(w_nk, dtype, Cout, Cin, W, H))
+        return launch_conv_tc(1, dy, w_nk, nullptr, dx, N, H, W, Cout, Cin, SVRS_ACT_NONE, (cudaStream_t)stream);
+    if (N > 0 && ksize == 4 && use_tc(w_nk, dtype, Cout, Cin, W / 2, H / 2))     // per-parity output grid == coarse grid
+        return launch_conv_tc(3, dy, w_nk, nullptr, dx, N, H / 2, W / 2, Cout, Cin, SVRS_ACT_NONE, (cudaStream_t)stream);
     ConvArgs a;
     a.in = dy; a.out = dx; a.w = w_kn; a.bias = nullptr; a.act = SVRS_ACT_NONE;
     if (ksize == 3) geom_conv3(a.g, N, H, W, Cout, Cin, true);
@@ -376,18 +397,22 @@ extern "C" int svrs_conv2d_dgrad(const void* dy, const void* w_kn, void* dx, int
     return launch_conv(a, dtype, (cudaStream_t)stream);
 }
 
-extern "C" int svrs_convT2d_fprop(const void* x, const void* w_kn, const float* bias, void* y, int dtype,
+extern "C" int svrs_convT2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
                                   int N, int H, int W, int Cin, int Cout, int act, void* stream) {
     SVRS_CHECK_ARG(x && w_kn && y && dtype_ok(dtype), "convT2d_fprop: null pointer or bad dtype");
+    if (N > 0 && use_tc(w_nk, dtype, Cin, Cout, W, H))
+        return launch_conv_tc(3, x, w_nk, bias, y, N, H, W, Cin, Cout, act, (cudaStream_t)stream);
     ConvArgs a;
     a.in = x; a.out = y; a.w = w_kn; a.bias = bias; a.act = act;
     geom_convT4s2(a.g, N, H, W, Cin, Cout);
     return launch_conv(a, dtype, (cudaStream_t)stream);
 }
 
-extern "C" int svrs_convT2d_dgrad(const void* dy, const void* w_kn, void* dx, int dtype,
+extern "C" int svrs_convT2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
                                   int N, int H, int W, int Cin, int Cout, void* stream) {
     SVRS_CHECK_ARG(dy && w_kn && dx && dtype_ok(dtype), "convT2d_dgrad: null pointer or bad dtype");
+    if (N > 0 && use_tc(w_nk, dtype, Cout, Cin, W, H))
+        return launch_conv_tc(2, dy, w_nk, nullptr, dx, N, 2 * H, 2 * W, Cout, Cin, SVRS_ACT_NONE, (cudaStream_t)stream);
     ConvArgs a;
     a.in = dy; a.out = dx; a.w = w_kn; a.bias = nullptr; a.act = SVRS_ACT_NONE;
     geom_conv4s2(a.g, N, 2 * H, 2 * W, Cout, Cin);

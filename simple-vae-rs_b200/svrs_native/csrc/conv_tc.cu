@@ -1,0 +1,422 @@
+// conv_tc.cu - tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 in, fp32 accumulate in TMEM).
+//
+// One persistent, warp-specialised kernel runs every "multi-tap GEMM" conv form of taps.cuh
+// (k3s1 fprop/dgrad, k4s2 fprop/dgrad, transposed k4s2 fprop/dgrad):
+//
+//   D[128 output pixels, n_tile channels] = sum over taps t, 64-channel chunks c
+//        A_t,c [128 pixels shifted by (dy_t, dx_t), 64 ch]  x  W_t,c [n_tile, 64 ch]^T
+//
+//   * A tiles are fetched by TMA from the NHWC activation tensor with a 4-D box
+//     (64 ch, BW, BH, BN images; BW*BH*BN = 128) whose start coordinate carries the tap shift;
+//     out-of-range rows/columns are ZERO-FILLED by the TMA unit, which implements the conv padding.
+//     Stride-2 forms read through one of four "parity" tensor maps (element stride 2 in W and H).
+//   * both operands land in shared memory in the canonical K-major SWIZZLE_128B layout
+//     (128-byte rows = 64 bf16 channels, 8-row groups 1024 B apart), consumed directly by
+//     tcgen05.mma (M=128, N=n_tile, K=16) through shared-memory descriptors.
+//   * accumulators live in TMEM (2 stages x 256 columns) so the epilogue of tile i overlaps the
+//     main loop of tile i+1; the epilogue (4 warps) does tcgen05.ld -> +bias -> activation -> bf16 ->
+//     128-bit global stores, one output pixel (row) per thread.
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include "common.cuh"
+#include "taps.cuh"
+#include <cuda.h>
+#include <string.h>
+
+namespace svrs {
+
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = 128 * 128;        // 128 pixels x 64 bf16
+constexpr int TC_B_BYTES = 256 * 128;        // up to 256 output channels x 64 bf16
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+
+struct TcTap {
+    int map;    // which input tensor map (parity class)
+    int dy, dx; // shift of the box start
+    int wtap;   // tap index in the packed weights
+};
+struct TcProb {
+    int ntaps;
+    int pad_;
+    long long out_off;
+    TcTap taps[16];
+};
+struct alignas(64) TcParams {
+    CUtensorMap in_maps[4];
+    CUtensorMap w_map;
+    __nv_bfloat16* out;
+    const float* bias;
+    long long o_sn, o_sy, o_sx;
+    int N, OH, OW;
+    int BW, BH, BNI;
+    int tiles_x, tiles_y, tiles_n;
+    int Nc, n_tile, n_tiles, kchunks;
+    int act, nprob;
+    TcProb prob[4];
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: 128-byte rows, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address       bits [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset  bits [16,30) (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset   bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                         // layout type: SWIZZLE_128B
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+    // barriers: full[4] empty[4] tmem_full[2] tmem_empty[2], then the TMEM base address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) prefetch_tmap(&p.in_maps[i]);
+        prefetch_tmap(&p.w_map);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int tiles_pix = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int tiles_per_prob = tiles_pix * p.n_tiles;
+    const int total_tiles = tiles_per_prob * p.nprob;
+    const uint32_t b_bytes = (uint32_t)p.n_tile * 128u;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int pr = tile / tiles_per_prob;
+                int rem = tile % tiles_per_prob;
+                const int nt = rem % p.n_tiles;
+                int pt = rem / p.n_tiles;
+                const int tx = pt % p.tiles_x; pt /= p.tiles_x;
+                const int ty = pt % p.tiles_y;
+                const int tn = pt / p.tiles_y;
+                const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = tn * p.BNI;
+                const TcProb& pb = p.prob[pr];
+                for (int t = 0; t < pb.ntaps; ++t) {
+                    const TcTap tp = pb.taps[t];
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+                        mbar_expect_tx(full_bar(stage), (uint32_t)TC_A_BYTES + b_bytes);
+                        tma_load_4d(sa, &p.in_maps[tp.map], full_bar(stage), kc * 64, x0 + tp.dx, y0 + tp.dy, n0);
+                        tma_load_3d(sa + TC_A_BYTES, &p.w_map, full_bar(stage), kc * 64, nt * p.n_tile, tp.wtap);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        // instruction descriptor: D=f32, A=B=bf16, both K-major, N = n_tile, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int pr = tile / tiles_per_prob;
+            const int iters = p.prob[pr].ntaps * p.kchunks;
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256u;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle span
+                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                    tc_commit(empty_bar(stage));                 // frees the smem stage when these MMAs retire
+                    if (it == iters - 1) tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+                }
+                __syncwarp();
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else {
+        // ================================ epilogue (4 warps) ================================
+        const int q = warp % 4;                         // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;                    // accumulator row == pixel within the tile
+        const int ix = r % p.BW, iy = (r / p.BW) % p.BH, in = r / (p.BW * p.BH);
+        uint32_t acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int pr = tile / tiles_per_prob;
+            int rem = tile % tiles_per_prob;
+            const int nt = rem % p.n_tiles;
+            int pt = rem / p.n_tiles;
+            const int tx = pt % p.tiles_x; pt /= p.tiles_x;
+            const int ty = pt % p.tiles_y;
+            const int tn = pt / p.tiles_y;
+            const int n = tn * p.BNI + in;
+            const int c_base = nt * p.n_tile;
+            __nv_bfloat16* orow = p.out + p.prob[pr].out_off + (long long)n * p.o_sn +
+                                  (long long)(ty * p.BH + iy) * p.o_sy + (long long)(tx * p.BW + ix) * p.o_sx + c_base;
+            const bool row_ok = n < p.N;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                uint32_t v[32];
+                const int cols = (p.n_tile - c0 >= 32) ? 32 : 16;
+                if (cols == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (j < cols && c_base + c0 + j < p.Nc) {
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                float b = p.bias ? __ldg(p.bias + c_base + c0 + j + e) : 0.f;
+                                f[e] = apply_act(__uint_as_float(v[j + e]) + b, p.act);
+                            }
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+                            uint4 o;
+                            o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+                            o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(orow + c0 + j) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)ptr;
+    }
+    return fn;
+}
+
+// 4-D activation view map: dims (C, W, H, N) with arbitrary element strides for W/H/N; box (64, BW, BH, BNI); SWIZZLE_128B.
+static int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sx, long long sy, long long sn,
+                        int BW, int BH, int BNI) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SVRS_E_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sn * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BNI};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation) failed: %d (C=%d W=%d H=%d N=%d)", (int)r, C, W, H, N); return SVRS_E_CUDA; }
+    return 0;
+}
+
+// weights in NK pack [tap][Nc][K] (K contiguous): dims (K, Nc, taps), box (64, n_tile, 1)
+static int make_w_map(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SVRS_E_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Nc, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * Nc * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)n_tile, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d (K=%d Nc=%d taps=%d)", (int)r, K, Nc, taps); return SVRS_E_CUDA; }
+    return 0;
+}
+
+static bool pick_box(int OW, int OH, int& BW, int& BH, int& BNI) {
+    BW = OW < 128 ? OW : 128;
+    if (128 % BW || OW % BW) return false;
+    BH = 128 / BW;
+    if (BH > OH) BH = OH;
+    if (OH % BH) return false;
+    BNI = 128 / (BW * BH);
+    return BW * BH * BNI == 128 && BW <= 256 && BH <= 256 && BNI <= 256;
+}
+
+bool tc_supported(int dtype, int K, int Nc, int OW, int OH) {
+    int bw, bh, bn;
+    return dtype == SVRS_BF16 && K % 64 == 0 && Nc % 16 == 0 && Nc >= 16 && pick_box(OW, OH, bw, bh, bn);
+}
+
+// form: 0 conv3 fprop, 1 conv3 dgrad, 2 conv4s2 (strided read), 3 convT4s2 (strided write).
+// in: tensor being read [N, H, W, Cr] ; out: tensor written ; w_nk: NK pack [tap][Cw][Cr]
+int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
+                   int act, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
+        attr_set = true;
+    }
+    TapGeom g;
+    int ntaps_total;
+    if (form == 0) { geom_conv3(g, N, H, W, Cr, Cw, false); ntaps_total = 9; }
+    else if (form == 1) { geom_conv3(g, N, H, W, Cr, Cw, true); ntaps_total = 9; }
+    else if (form == 2) { geom_conv4s2(g, N, H, W, Cr, Cw); ntaps_total = 16; }
+    else { geom_convT4s2(g, N, H, W, Cr, Cw); ntaps_total = 16; }
+
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    if (!pick_box(g.OW, g.OH, p.BW, p.BH, p.BNI)) { set_error("conv_tc: unsupported spatial dims %dx%d", g.OW, g.OH); return SVRS_E_UNSUPPORTED; }
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.bias = bias;
+    p.o_sn = g.o_sn; p.o_sy = g.o_sy; p.o_sx = g.o_sx;
+    p.N = N; p.OH = g.OH; p.OW = g.OW;
+    p.tiles_x = g.OW / p.BW; p.tiles_y = g.OH / p.BH; p.tiles_n = (N + p.BNI - 1) / p.BNI;
+    p.Nc = Cw;
+    p.n_tile = Cw <= 256 ? Cw : 256;
+    p.n_tiles = (Cw + p.n_tile - 1) / p.n_tile;
+    p.kchunks = Cr / 64;
+    p.act = act; p.nprob = g.nprob;
+
+    // input maps: distinct in_off values become distinct tensor maps (parity classes of a stride-2 read)
+    long long offs[4]; int nmaps = 0;
+    for (int pr = 0; pr < g.nprob; ++pr) {
+        p.prob[pr].ntaps = g.prob[pr].ntaps;
+        p.prob[pr].out_off = g.prob[pr].out_off;
+        for (int t = 0; t < g.prob[pr].ntaps; ++t) {
+            const Tap& tp = g.prob[pr].taps[t];
+            int mi = -1;
+            for (int i = 0; i < nmaps; ++i) if (offs[i] == tp.in_off) mi = i;
+            if (mi < 0) { if (nmaps == 4) { set_error("conv_tc: too many input views"); return SVRS_E_ARG; } offs[nmaps] = tp.in_off; mi = nmaps++; }
+            TcTap& o = p.prob[pr].taps[t];
+            o.map = mi; o.dy = tp.dy; o.dx = tp.dx;
+            o.wtap = (int)(tp.w_off / ((long long)Cr * Cw));
+        }
+    }
+    const __nv_bfloat16* inb = reinterpret_cast<const __nv_bfloat16*>(in);
+    for (int i = 0; i < 4; ++i) {
+        long long off = i < nmaps ? offs[i] : offs[0];
+        int rc = make_act_map(&p.in_maps[i], inb + off, Cr, g.IW, g.IH, N, g.i_sx, g.i_sy, g.i_sn, p.BW, p.BH, p.BNI);
+        if (rc) return rc;
+    }
+    int rc = make_w_map(&p.w_map, w_nk, Cr, Cw, ntaps_total, p.n_tile);
+    if (rc) return rc;
+
+    long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * p.nprob;
+    int grid = (int)(total < num_sms() ? total : num_sms());
+    if (grid < 1) return 0;
+    conv_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
+    return check_launch("conv_tc_kernel");
+}
+
+}  // namespace svrs

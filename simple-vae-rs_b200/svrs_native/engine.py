@@ -310,9 +310,9 @@ class Runtime:
                 y = torch.empty((n, oh, ow, op.cout), device=x.device, dtype=self.dtype)
                 bias = op.mod.bias
                 if op.kind == "ct":
-                    lib.convT2d_fprop(_p(x), _p(op.pack_f), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout, op.act, st)
+                    lib.convT2d_fprop(_p(x), _p(op.pack_f), _p(op.pack_b), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout, op.act, st)
                 else:
-                    lib.conv2d_fprop(_p(x), _p(op.pack_f), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout,
+                    lib.conv2d_fprop(_p(x), _p(op.pack_f), _p(op.pack_b), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout,
                                      3 if op.kind == "c3" else 4, op.act, st)
                 self.launches += 1
                 if save:
@@ -377,9 +377,9 @@ class Runtime:
                 if idx > 0 or need_dx:
                     dx = torch.empty_like(x)
                     if op.kind == "ct":
-                        lib.convT2d_dgrad(_p(dy), _p(op.pack_b), _p(dx), self.dt, n, h, w, op.cin, op.cout, st)
+                        lib.convT2d_dgrad(_p(dy), _p(op.pack_b), _p(op.pack_f), _p(dx), self.dt, n, h, w, op.cin, op.cout, st)
                     else:
-                        lib.conv2d_dgrad(_p(dy), _p(op.pack_b), _p(dx), self.dt, n, h, w, op.cin, op.cout,
+                        lib.conv2d_dgrad(_p(dy), _p(op.pack_b), _p(op.pack_f), _p(dx), self.dt, n, h, w, op.cin, op.cout,
                                          3 if op.kind == "c3" else 4, st)
                     self.launches += 1
                     dy = dx

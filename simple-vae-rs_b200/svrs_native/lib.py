@@ -37,7 +37,7 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     src = re.sub(r"//[^\n]*", " ", src)
     protos = {}
-    for m in re.finditer(r"(const\s+char\s*\*|int)\s+(svrs_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(const\s+char\s*\*|int|void)\s+(svrs_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         arglist = []
         args = " ".join(args.split())
@@ -47,7 +47,7 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str
                 mm = re.match(r"(.*?)(\w+)$", a)
                 ty, an = mm.group(1).strip(), mm.group(2)
                 arglist.append((ty.replace(" *", "*"), an))
-        protos[name] = ("char*" if "char" in ret else "int", arglist)
+        protos[name] = ("char*" if "char" in ret else ret.strip(), arglist)
     return protos
 
 
@@ -75,7 +75,7 @@ class _Lib:
         for name, (ret, args) in self.protos.items():
             fn = getattr(dll, name)  # AttributeError => header/library mismatch, fail loudly
             fn.argtypes = [_ctype(t) for t, _ in args]
-            fn.restype = ctypes.c_char_p if ret == "char*" else ctypes.c_int
+            fn.restype = ctypes.c_char_p if ret == "char*" else (None if ret == "void" else ctypes.c_int)
         self._dll = dll
         return dll
 
@@ -88,7 +88,7 @@ class _Lib:
         if full not in self.protos:
             raise AttributeError(name)
         fn = getattr(self.load(), full)
-        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry"):
+        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run"):
             setattr(self, name, fn)
             return fn
 

@@ -55,11 +55,11 @@ def test_conv2d_fprop_dgrad_wgrad(case, ksize, dtype):
     pf, pb = pack(wd, dtype)
     OH, OW = yr.shape[2], yr.shape[3]
     y = torch.empty((N, OH, OW, Cout), device=DEV, dtype=dtype)
-    lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), bd.data_ptr(), y.data_ptr(), dt(dtype), N, H, W, Cin, Cout, ksize, 0, st())
+    lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), pb.data_ptr(), bd.data_ptr(), y.data_ptr(), dt(dtype), N, H, W, Cin, Cout, ksize, 0, st())
     report(f"conv{ksize} fprop {case} {dtype}", nchw(y), yr, TOL[dtype])
 
     dx = torch.empty_like(xd)
-    lib.conv2d_dgrad(gyd.data_ptr(), pb.data_ptr(), dx.data_ptr(), dt(dtype), N, H, W, Cin, Cout, ksize, st())
+    lib.conv2d_dgrad(gyd.data_ptr(), pb.data_ptr(), pf.data_ptr(), dx.data_ptr(), dt(dtype), N, H, W, Cin, Cout, ksize, st())
     report(f"conv{ksize} dgrad {case} {dtype}", nchw(dx), xr.grad, TOL[dtype])
 
     dw = torch.zeros_like(wd)
@@ -85,10 +85,10 @@ def test_convT2d_fprop_dgrad_wgrad(case, dtype):
     xd, wd, bd, gyd = nhwc(x.to(DEV), dtype), w.to(DEV), b.to(DEV), nhwc(gy.to(DEV), dtype)
     pf, pb = pack(wd, dtype, convT=True)
     y = torch.empty((N, 2 * H, 2 * W, Cout), device=DEV, dtype=dtype)
-    lib.convT2d_fprop(xd.data_ptr(), pf.data_ptr(), bd.data_ptr(), y.data_ptr(), dt(dtype), N, H, W, Cin, Cout, 0, st())
+    lib.convT2d_fprop(xd.data_ptr(), pf.data_ptr(), pb.data_ptr(), bd.data_ptr(), y.data_ptr(), dt(dtype), N, H, W, Cin, Cout, 0, st())
     report(f"convT fprop {case} {dtype}", nchw(y), yr, TOL[dtype])
     dx = torch.empty_like(xd)
-    lib.convT2d_dgrad(gyd.data_ptr(), pb.data_ptr(), dx.data_ptr(), dt(dtype), N, H, W, Cin, Cout, st())
+    lib.convT2d_dgrad(gyd.data_ptr(), pb.data_ptr(), pf.data_ptr(), dx.data_ptr(), dt(dtype), N, H, W, Cin, Cout, st())
     report(f"convT dgrad {case} {dtype}", nchw(dx), xr.grad, TOL[dtype])
     dw, db = torch.zeros_like(wd), torch.zeros_like(bd)
     lib.convT2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), db.data_ptr(), dt(dtype), N, H, W, Cin, Cout, 0, st())
@@ -109,14 +109,14 @@ def test_conv_first_principles_numpy():
     bd = b.to(DEV)          # keep device tensors alive: a temporary's storage is recycled as soon as data_ptr() returns
     for ks, w in ((3, w3), (4, w4)):
         ref = npp.conv2d(x.numpy(), w.numpy(), b.numpy(), 1 if ks == 3 else 2, 1)
-        pf, _ = pack(w.to(DEV), torch.float32)
+        pf, pb = pack(w.to(DEV), torch.float32)
         y = torch.empty((2, ref.shape[2], ref.shape[3], 5), device=DEV)
-        lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), bd.data_ptr(), y.data_ptr(), F32, 2, 6, 6, 3, 5, ks, 0, st())
+        lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), pb.data_ptr(), bd.data_ptr(), y.data_ptr(), F32, 2, 6, 6, 3, 5, ks, 0, st())
         report(f"conv{ks} vs numpy definition", nchw(y), torch.from_numpy(ref), 1e-5)
     ref = npp.conv_transpose2d_k4s2p1(x.numpy(), wt.numpy(), b.numpy())
-    pf, _ = pack(wt.to(DEV), torch.float32, convT=True)
+    pf, pb = pack(wt.to(DEV), torch.float32, convT=True)
     y = torch.empty((2, 12, 12, 5), device=DEV)
-    lib.convT2d_fprop(xd.data_ptr(), pf.data_ptr(), bd.data_ptr(), y.data_ptr(), F32, 2, 6, 6, 3, 5, 0, st())
+    lib.convT2d_fprop(xd.data_ptr(), pf.data_ptr(), pb.data_ptr(), bd.data_ptr(), y.data_ptr(), F32, 2, 6, 6, 3, 5, 0, st())
     report("convT vs numpy definition", nchw(y), torch.from_numpy(ref), 1e-5)
 
 
@@ -130,11 +130,11 @@ def test_conv_epilogue_activation_and_backward(act, fn):
     yr = fn(pre)
     gy = torch.randn(yr.shape, generator=g).double()
     yr.backward(gy)
-    pf, _ = pack(w.to(DEV), torch.float32)
+    pf, pb = pack(w.to(DEV), torch.float32)
     xd = nhwc(x.to(DEV))
     bd = b.to(DEV)
     y = torch.empty((2, 4, 4, 12), device=DEV)
-    lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), bd.data_ptr(), y.data_ptr(), F32, 2, 4, 4, 8, 12, 3, act, st())
+    lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), pb.data_ptr(), bd.data_ptr(), y.data_ptr(), F32, 2, 4, 4, 8, 12, 3, act, st())
     report(f"conv + act {act}", nchw(y), yr, 1e-5)
     gyd = nhwc(gy.float().to(DEV))
     lib.act_bwd(y.data_ptr(), gyd.data_ptr(), gyd.data_ptr(), F32, act, gyd.numel(), st())
@@ -394,7 +394,64 @@ def test_error_reporting_is_loud():
     from svrs_native.lib import SvrsError
     x = torch.zeros(4, device=DEV)
     with pytest.raises(SvrsError):
-        lib.conv2d_fprop(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), 7, 1, 2, 2, 1, 1, 3, 0, st())   # bad dtype
+        lib.conv2d_fprop(x.data_ptr(), x.data_ptr(), None, None, x.data_ptr(), 7, 1, 2, 2, 1, 1, 3, 0, st())   # bad dtype
     with pytest.raises(SvrsError):
-        lib.conv2d_fprop(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), F32, 1, 3, 3, 1, 1, 4, 0, st())  # odd H with k4s2
+        lib.conv2d_fprop(x.data_ptr(), x.data_ptr(), None, None, x.data_ptr(), F32, 1, 3, 3, 1, 1, 4, 0, st())  # odd H with k4s2
     assert "conv2d_fprop" in lib.last_error()
+
+
+TC_CASES = [
+    # N, H, W, Cin, Cout   (bf16, reduction channels % 64 == 0 -> tcgen05 kernel)
+    (2, 8, 8, 64, 64),
+    (3, 16, 16, 128, 64),     # N not a multiple of the images-per-tile
+    (2, 4, 4, 256, 512),      # two N tiles of 256, 8 images per 128-pixel tile, N < box
+    (1, 64, 64, 64, 16),      # decoder tail 64 -> 16 at 64x64 (N tile 16)
+    (2, 32, 32, 128, 128),
+    (9, 4, 4, 64, 48),        # N tile 48 = 32 + 16 column loads, 9 images over two tiles
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_all_forms(case):
+    """tcgen05/TMA kernel (conv_tc) for every conv form vs float64 torch, and vs the SIMT kernel on the same inputs."""
+    N, H, W, Cin, Cout = case
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(sum(case))
+    x = _rand((N, Cin, H, W), g, dtype)
+    b = torch.randn(Cout, generator=g)
+    for form in ("c3", "c4", "ct"):
+        ks = 3 if form == "c3" else 4
+        if form == "ct":
+            w = (_rand((Cin, Cout, 4, 4), g, dtype) * 0.1).to(dtype).float()
+            fwd = lambda xx, ww, bb: F.conv_transpose2d(xx, ww, bb, stride=2, padding=1)
+        else:
+            w = (_rand((Cout, Cin, ks, ks), g, dtype) * 0.1).to(dtype).float()
+            fwd = (lambda xx, ww, bb: F.conv2d(xx, ww, bb, stride=1, padding=1)) if form == "c3" else \
+                  (lambda xx, ww, bb: F.conv2d(xx, ww, bb, stride=2, padding=1))
+        xr = x.double().requires_grad_(True)
+        yr = fwd(xr, w.double(), b.double())
+        gy = _rand(tuple(yr.shape), g, dtype)
+        yr.backward(gy.double())
+        xd, wd, bd, gyd = nhwc(x.to(DEV), dtype), w.to(DEV), b.to(DEV), nhwc(gy.to(DEV), dtype)
+        pf, pb = pack(wd, dtype, convT=(form == "ct"))
+        OH, OW = yr.shape[2], yr.shape[3]
+        res = {}
+        for tc in (1, 0):
+            lib.set_tc_enabled(tc)
+            y = torch.full((N, OH, OW, Cout), float("nan"), device=DEV, dtype=dtype)
+            dx = torch.full_like(xd, float("nan"))
+            if form == "ct":
+                lib.convT2d_fprop(xd.data_ptr(), pf.data_ptr(), pb.data_ptr(), bd.data_ptr(), y.data_ptr(), BF16, N, H, W, Cin, Cout, 0, st())
+                lib.convT2d_dgrad(gyd.data_ptr(), pb.data_ptr(), pf.data_ptr(), dx.data_ptr(), BF16, N, H, W, Cin, Cout, st())
+            else:
+                lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), pb.data_ptr(), bd.data_ptr(), y.data_ptr(), BF16, N, H, W, Cin, Cout, ks, 0, st())
+                lib.conv2d_dgrad(gyd.data_ptr(), pb.data_ptr(), pf.data_ptr(), dx.data_ptr(), BF16, N, H, W, Cin, Cout, ks, st())
+            torch.cuda.synchronize()
+            res[tc] = (y, dx)
+        lib.set_tc_enabled(1)
+        ran_f = lib.tc_would_run(BF16, Cin, Cout, OH if form != "ct" else H, OW if form != "ct" else W)
+        print(f"[parity] {form} {case}: conv_tc taken for fprop: {bool(ran_f)}")
+        report(f"conv_tc {form} fprop {case} vs fp64", nchw(res[1][0]), yr, 1e-2)
+        report(f"conv_tc {form} dgrad {case} vs fp64", nchw(res[1][1]), xr.grad, 1e-2)
+        report(f"conv_tc {form} fprop {case} vs simt", res[1][0].float(), res[0][0].float(), 8e-3)
+        report(f"conv_tc {form} dgrad {case} vs simt", res[1][1].float(), res[0][1].float(), 8e-3)

@@ -52,16 +52,12 @@ def test_cond_forward_loss_backward_fp32(golden_dir, name):
         report(f"{name} {k} vs oracle", got.reshape(1), terms_o[k].reshape(1), 1e-5)
         report(f"{name} {k} vs golden", got.reshape(1), fx["curve"][0][i].reshape(1), 1e-5)
     loss.backward()
-    worst = 0.0
     for k, p in model.named_parameters():
-        g, r = p.grad, grads_o[k]
         if k.endswith(ZERO_GRAD_BIAS):      # true gradient is 0: both sides hold rounding noise only
-            assert float(g.abs().max()) < 1e-3 * max(1.0, fx["grad_total_norm"]), k
-            continue
-        worst = max(worst, report(f"{name} grad {k}", g, r, 2e-4, atol=1e-6))
-        if k in fx["grads_full"]:
-            report(f"{name} grad {k} vs golden", g, fx["grads_full"][k], 2e-4, atol=1e-6)
-    print(f"[parity] {name}: worst parameter-gradient error relative to max = {worst:.3e}")
+            assert float(p.grad.abs().max()) < 1e-3 * max(1.0, fx["grad_total_norm"]), k
+    FX.check_grads(name, list(model.named_parameters()), grads_o, FX.grads_fp64(fx, sd, x, y, fx["eps"]), ZERO_GRAD_BIAS, report)
+    for k, ref in fx["grads_full"].items():      # layout check of full tensors against the reference's own values
+        report(f"{name} grad {k} vs golden", dict(model.named_parameters())[k].grad, ref, 2e-3, atol=1e-6)
     report("grad gammax", model.gammax.grad.reshape(1), grads_o["gammax"].reshape(1), 1e-5)
     report("grad gammay", model.gammay.grad.reshape(1), grads_o["gammay"].reshape(1), 1e-5)
     report("grad gammax vs golden", model.gammax.grad.reshape(1), torch.tensor([fx["grad_gammas"]["gammax"]]), 1e-5)
@@ -95,9 +91,9 @@ def test_cond_fused_steps_fp32(golden_dir):
         to = O.cond_train_step(osd, ogam, oopt, fx["cr"], fx["P"], x, y, eu, ez)
         for i, k in enumerate(["mse_x", "kld_u", "mse_y", "kld_z", "loss"]):
             report(f"step {it} {k} vs oracle", t[i].reshape(1), to[k].reshape(1), 2e-5)
-        report(f"step {it} grad norm", tr.grad_norm().reshape(1), to["grad_norm"].reshape(1), 1e-4)
+        report(f"step {it} grad norm", tr.grad_norm().reshape(1), to["grad_norm"].reshape(1), 5e-4)
         report(f"step {it} loss vs golden", t[4].reshape(1), fx["curve"][it][0].reshape(1), 2e-5)
-        report(f"step {it} grad norm vs golden", tr.grad_norm().reshape(1), fx["curve"][it][5].reshape(1), 1e-4)
+        report(f"step {it} grad norm vs golden", tr.grad_norm().reshape(1), fx["curve"][it][5].reshape(1), 5e-4)
     tr.sync_to_model()
     msd = model.state_dict()
     for k, v in osd.items():
@@ -176,10 +172,7 @@ def test_vae_fp32(golden_dir, name):
     report("vae mse", mse.reshape(1), terms_o["mse"].reshape(1), 1e-5)
     report("vae kld", kld.reshape(1), terms_o["kld"].reshape(1), 1e-5)
     (mse + kld).backward()
-    for k, p in model.named_parameters():
-        if k.endswith(ZERO_GRAD_BIAS):
-            continue
-        report(f"{name} grad {k}", p.grad, grads_o[k], 2e-4, atol=1e-6)
+    FX.check_grads(name, list(model.named_parameters()), grads_o, FX.grads_fp64(fx, sd, x, None, fx["eps"]), ZERO_GRAD_BIAS, report)
     report("grad gamma", model.gamma.grad.reshape(1), grads_o["gamma"].reshape(1), 1e-5)
     # fused multi-step on a fresh model vs the golden curve
     model2, _ = FX.build(fx, device=DEV)
