@@ -353,6 +353,8 @@ namespace svrs {
 bool tc_supported(int dtype, int K, int Nc, int OW, int OH);
 int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
                    int act, cudaStream_t st);
+bool wgrad_tc_supported(int dtype, int Ca, int Cb, int OW, int OH);
+int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int KK, cudaStream_t st);
 static int g_tc_enabled = 1;
 static inline bool use_tc(const void* w_nk, int dtype, int K, int Nc, int OW, int OH) {
     return g_tc_enabled && w_nk != nullptr && tc_supported(dtype, K, Nc, OW, OH);
@@ -429,7 +431,10 @@ extern "C" int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float
         a.gmat = dy; a.x = x; a.dw = dw; a.KK = ksize * ksize;
         if (ksize == 3) geom_conv3(a.g, N, H, W, Cin, Cout, false);
         else geom_conv4s2(a.g, N, H, W, Cin, Cout);
-        rc = launch_wgrad(a, dtype, ksplit, (cudaStream_t)stream);
+        if (g_tc_enabled && N > 0 && wgrad_tc_supported(dtype, Cout, Cin, a.g.OW, a.g.OH))
+            rc = launch_wgrad_tc(a.g, dy, x, dw, a.KK, (cudaStream_t)stream);
+        else
+            rc = launch_wgrad(a, dtype, ksplit, (cudaStream_t)stream);
         if (rc) return rc;
     }
     if (db) {
@@ -448,7 +453,10 @@ extern "C" int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, floa
         WgradArgs a;
         a.gmat = x; a.x = dy; a.dw = dw; a.KK = 16;
         geom_conv4s2(a.g, N, 2 * H, 2 * W, Cout, Cin);
-        rc = launch_wgrad(a, dtype, ksplit, (cudaStream_t)stream);
+        if (g_tc_enabled && N > 0 && wgrad_tc_supported(dtype, Cin, Cout, a.g.OW, a.g.OH))
+            rc = launch_wgrad_tc(a.g, x, dy, dw, 16, (cudaStream_t)stream);
+        else
+            rc = launch_wgrad(a, dtype, ksplit, (cudaStream_t)stream);
         if (rc) return rc;
     }
     if (db) rc = launch_colsum(dy, dtype, (long long)N * 4 * H * W, Cout, db, (cudaStream_t)stream);

@@ -1,0 +1,234 @@
+// wgrad_tc.cu - tcgen05 / TMEM / TMA weight-gradient kernel for sm_100a (bf16 in, fp32 accumulate).
+//
+//   dW_t[a][b] = sum over output-grid pixels m of  G[m][a] * X_t[m shifted by tap t][b]
+//
+// GEMM view per CTA:  D[(tap, b) rows, a columns] += Xstack^T * G, reduction (K) over pixels.
+//   * M (128 rows of one "M-block") = two 64-channel boxes of X taken at one or two taps; the boxes are the same
+//     TMA tiles the forward kernel reads (64 ch x 128 pixels, SWIZZLE_128B) and are fed to tcgen05.mma as an
+//     MN-MAJOR A operand (channels contiguous, pixels = K), the two boxes one LBO apart.
+//   * N = up to 128 channels of G (MN-major B operand, same box shape).
+//   * K = 128 pixels per pipeline stage (8 MMAs of K=16); the pixel range is split over CTAs.
+//   * every CTA keeps up to 512/N M-blocks of accumulators resident in TMEM for its whole pixel range and
+//     finishes with fp32 atomics into the torch-layout gradient dw[(a*Cb + b)*KK + tap].
+// TMA zero-fill implements the convolution padding for X and masks out-of-range images for G.
+#include "common.cuh"
+#include "taps.cuh"
+#include "tc_ptx.cuh"
+#include <string.h>
+
+namespace svrs {
+
+constexpr int WG_STAGES = 3;
+constexpr int WG_X_BYTES = 2 * 16384;      // one M-block: two boxes of 128 pixels x 64 ch
+constexpr int WG_G_BYTES = 2 * 16384;      // up to 128 channels of G
+constexpr int WG_STAGE_BYTES = WG_X_BYTES + WG_G_BYTES;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+constexpr int WG_THREADS = 192;
+
+struct WgTap { int map, dy, dx, tapid; };
+struct alignas(64) WgParams {
+    CUtensorMap x_maps[4];    // input views (parity classes)
+    CUtensorMap g_map;        // output-grid operand
+    float* dw;
+    int N, OH, OW, BW, BH, BNI;
+    int tiles_x, tiles_y, tiles_n;     // pixel tiling of the output grid
+    int Ca, Cb, KK;
+    int n_tile, n_tiles;               // columns (a) per CTA
+    int cb_chunks;                     // Cb / 64
+    int nboxes, nblocks, group, ngroups;
+    int ksplit, ksteps_total;
+    int ntaps;
+    WgTap taps[16];
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + WG_STAGES * WG_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (WG_STAGES + s); };
+    const uint32_t done_bar = bar_base + 8u * (2 * WG_STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * WG_STAGES + 1);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) prefetch_tmap(&p.x_maps[i]);
+        prefetch_tmap(&p.g_map);
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    // work item: (pixel split ks, column tile nt, M-block group grp)
+    int w = blockIdx.x;
+    const int grp = w % p.ngroups; w /= p.ngroups;
+    const int nt = w % p.n_tiles; w /= p.n_tiles;
+    const int ks = w;
+    const int blk0 = grp * p.group;
+    const int nblk = (p.nblocks - blk0) < p.group ? (p.nblocks - blk0) : p.group;
+    const int steps_per = (p.ksteps_total + p.ksplit - 1) / p.ksplit;
+    const int k_begin = ks * steps_per;
+    const int k_end = (k_begin + steps_per) < p.ksteps_total ? (k_begin + steps_per) : p.ksteps_total;
+    const int nsteps = k_end > k_begin ? k_end - k_begin : 0;
+    const int g_boxes = p.n_tile / 64;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int kstep = k_begin; kstep < k_end; ++kstep) {
+                int pt = kstep;
+                const int tx = pt % p.tiles_x; pt /= p.tiles_x;
+                const int ty = pt % p.tiles_y;
+                const int tn = pt / p.tiles_y;
+                const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = tn * p.BNI;
+                for (int b = 0; b < nblk; ++b) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
+                    const uint32_t sg = sx + WG_X_BYTES;
+                    mbar_expect_tx(full_bar(stage), (uint32_t)(2 + g_boxes) * 16384u);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int box = 2 * (blk0 + b) + h;
+                        if (box >= p.nboxes) box = p.nboxes - 1;       // odd tail: duplicate (rows are ignored by the epilogue)
+                        const WgTap tp = p.taps[box / p.cb_chunks];
+                        const int cj = box % p.cb_chunks;
+                        tma_load_4d(sx + h * 16384u, &p.x_maps[tp.map], full_bar(stage), cj * 64, x0 + tp.dx, y0 + tp.dy, n0);
+                    }
+                    for (int gbx = 0; gbx < g_boxes; ++gbx)
+                        tma_load_4d(sg + gbx * 16384u, &p.g_map, full_bar(stage), nt * p.n_tile + gbx * 64, x0, y0, n0);
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = n_tile, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+        uint32_t stage = 0, phase = 0;
+        for (int kstep = 0; kstep < nsteps; ++kstep) {
+            for (int b = 0; b < nblk; ++b) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
+                    const uint32_t sg = sx + WG_X_BYTES;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(b * p.n_tile);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {     // 8 x (K = 16 pixels = 16 rows of 128 B)
+                        const uint64_t adesc = make_sw128_mn_desc(sx + k * 2048u, 16384u, 1024u);
+                        const uint64_t bdesc = make_sw128_mn_desc(sg + k * 2048u, 16384u, 1024u);
+                        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kstep | k) != 0);
+                    }
+                    tc_commit(empty_bar(stage));
+                    if (kstep == nsteps - 1 && b == nblk - 1) tc_commit(done_bar);
+                }
+                __syncwarp();
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (nsteps > 0) {
+        const int q = warp % 4;
+        const int m = q * 32 + lane;
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        for (int b = 0; b < nblk; ++b) {
+            const int box = 2 * (blk0 + b) + (m >= 64 ? 1 : 0);
+            const bool row_ok = box < p.nboxes;
+            const int bx = row_ok ? box : 0;
+            const int tapid = p.taps[bx / p.cb_chunks].tapid;
+            const int cb = (bx % p.cb_chunks) * 64 + (m & 63);
+            const uint32_t taddr = tmem_base + (uint32_t)(b * p.n_tile) + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int ca = nt * p.n_tile + c0 + j;
+                        if (ca < p.Ca) atomicAdd(p.dw + ((long long)ca * p.Cb + cb) * p.KK + tapid, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+bool wgrad_tc_supported(int dtype, int Ca, int Cb, int OW, int OH) {
+    int bw, bh, bn;
+    return dtype == SVRS_BF16 && Ca % 64 == 0 && Cb % 64 == 0 && pick_box(OW, OH, bw, bh, bn);
+}
+
+// g: geometry of the forward-form conv whose output grid carries `gmat` (channels Ca = g.Nc) and whose input view
+// carries `x` (channels Cb = g.K);  dw torch layout [(a*Cb + b)*KK + tap]
+int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int KK, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
+        attr_set = true;
+    }
+    WgParams p;
+    memset(&p, 0, sizeof(p));
+    if (!pick_box(g.OW, g.OH, p.BW, p.BH, p.BNI)) { set_error("wgrad_tc: unsupported spatial dims"); return SVRS_E_UNSUPPORTED; }
+    p.dw = dw;
+    p.N = g.N; p.OH = g.OH; p.OW = g.OW;
+    p.tiles_x = g.OW / p.BW; p.tiles_y = g.OH / p.BH; p.tiles_n = (g.N + p.BNI - 1) / p.BNI;
+    p.Ca = g.Nc; p.Cb = g.K; p.KK = KK;
+    p.n_tile = p.Ca < 128 ? p.Ca : 128;
+    p.n_tiles = (p.Ca + p.n_tile - 1) / p.n_tile;
+    p.cb_chunks = p.Cb / 64;
+    const Prob& pb = g.prob[0];
+    p.ntaps = pb.ntaps;
+    p.nboxes = pb.ntaps * p.cb_chunks;
+    p.nblocks = (p.nboxes + 1) / 2;
+    p.group = 512 / p.n_tile;
+    if (p.group > p.nblocks) p.group = p.nblocks;
+    p.ngroups = (p.nblocks + p.group - 1) / p.group;
+    p.ksteps_total = p.tiles_x * p.tiles_y * p.tiles_n;
+    int base = p.ngroups * p.n_tiles;
+    int ksplit = (2 * num_sms() + base - 1) / base;
+    if (ksplit > p.ksteps_total) ksplit = p.ksteps_total;
+    if (ksplit < 1) ksplit = 1;
+    p.ksplit = ksplit;
+
+    long long offs[4]; int nmaps = 0;
+    for (int t = 0; t < pb.ntaps; ++t) {
+        const Tap& tp = pb.taps[t];
+        int mi = -1;
+        for (int i = 0; i < nmaps; ++i) if (offs[i] == tp.in_off) mi = i;
+        if (mi < 0) { if (nmaps == 4) { set_error("wgrad_tc: too many input views"); return SVRS_E_ARG; } offs[nmaps] = tp.in_off; mi = nmaps++; }
+        p.taps[t].map = mi; p.taps[t].dy = tp.dy; p.taps[t].dx = tp.dx; p.taps[t].tapid = t;
+    }
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+    for (int i = 0; i < 4; ++i) {
+        long long off = i < nmaps ? offs[i] : offs[0];
+        int rc = make_act_map(&p.x_maps[i], xb + off, p.Cb, g.IW, g.IH, g.N, g.i_sx, g.i_sy, g.i_sn, p.BW, p.BH, p.BNI);
+        if (rc) return rc;
+    }
+    const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(gmat) + pb.out_off;
+    int rc = make_act_map(&p.g_map, gb, p.Ca, g.OW, g.OH, g.N, g.o_sx, g.o_sy, g.o_sn, p.BW, p.BH, p.BNI);
+    if (rc) return rc;
+
+    int grid = p.ngroups * p.n_tiles * p.ksplit;
+    wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(p);
+    return check_launch("wgrad_tc_kernel");
+}
+
+}  // namespace svrs

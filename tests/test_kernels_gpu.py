@@ -455,3 +455,41 @@ def test_conv_tc_all_forms(case):
         report(f"conv_tc {form} dgrad {case} vs fp64", nchw(res[1][1]), xr.grad, 1e-2)
         report(f"conv_tc {form} fprop {case} vs simt", res[1][0].float(), res[0][0].float(), 8e-3)
         report(f"conv_tc {form} dgrad {case} vs simt", res[1][1].float(), res[0][1].float(), 8e-3)
+
+
+@pytest.mark.parametrize("case", [(2, 8, 8, 64, 64), (3, 16, 16, 128, 64), (2, 4, 4, 256, 512), (2, 32, 32, 128, 128),
+                                  (5, 8, 8, 64, 192)])
+def test_wgrad_tc_all_forms(case):
+    """tcgen05 weight-gradient kernel (MN-major operands, split-K over pixels) vs float64 torch autograd."""
+    N, H, W, Cin, Cout = case
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = _rand((N, Cin, H, W), g, dtype)
+    for form in ("c3", "c4", "ct"):
+        ks = 3 if form == "c3" else 4
+        if form == "ct":
+            w = (_rand((Cin, Cout, 4, 4), g, dtype) * 0.1).to(dtype).float()
+            fwd = lambda xx, ww: F.conv_transpose2d(xx, ww, None, stride=2, padding=1)
+        else:
+            w = (_rand((Cout, Cin, ks, ks), g, dtype) * 0.1).to(dtype).float()
+            fwd = (lambda xx, ww: F.conv2d(xx, ww, None, stride=1, padding=1)) if form == "c3" else \
+                  (lambda xx, ww: F.conv2d(xx, ww, None, stride=2, padding=1))
+        wr = w.double().requires_grad_(True)
+        yr = fwd(x.double(), wr)
+        gy = _rand(tuple(yr.shape), g, dtype)
+        yr.backward(gy.double())
+        xd, gyd = nhwc(x.to(DEV), dtype), nhwc(gy.to(DEV), dtype)
+        res = {}
+        for tc in (1, 0):
+            lib.set_tc_enabled(tc)
+            dw = torch.zeros(w.shape, device=DEV)
+            db = torch.zeros(Cout, device=DEV)
+            if form == "ct":
+                lib.convT2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), db.data_ptr(), BF16, N, H, W, Cin, Cout, 0, st())
+            else:
+                lib.conv2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), db.data_ptr(), BF16, N, H, W, Cin, Cout, ks, 0, st())
+            torch.cuda.synchronize()
+            res[tc] = dw
+        lib.set_tc_enabled(1)
+        report(f"wgrad_tc {form} {case} vs fp64", res[1], wr.grad, 2e-5)
+        report(f"wgrad_tc {form} {case} vs simt", res[1], res[0], 2e-5)
