@@ -314,10 +314,147 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad for narrow layers (min(Ca, Cb) <= 16: the 4- and 16-channel layers at full resolution).  These are
+// pure streaming reductions (a few hundred outputs, half a million pixels): every thread owns one 4x4 (a, b)
+// register tile of one tap and walks its own strided pixel subset straight from global memory (the 4-channel
+// vectors of neighbouring taps hit L1), so the loop has no shared memory and no barriers; the per-thread tiles
+// are combined by warp shuffles + one shared-memory pass and a single atomic per output per CTA.
+// grid = (taps, pixel splits, sub-tile groups); block = SUB sub-tiles x (256 / SUB) pixel lanes.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int SUB>
+__global__ void __launch_bounds__(256) wgrad_direct_kernel(const __grid_constant__ WgradArgs a) {
+    constexpr int L = 256 / SUB;   // pixel lanes per sub-tile
+    __shared__ float red[(L > 32 ? L / 32 : 1)][SUB][16];
+    const TapGeom& g = a.g;
+    const Prob& pb = g.prob[0];
+    const T* __restrict__ G = reinterpret_cast<const T*>(a.gmat) + pb.out_off;
+    const T* __restrict__ X = reinterpret_cast<const T*>(a.x);
+    const int Ca = g.Nc, Cb = g.K;
+    const int qa = (Ca + 3) / 4, qb = (Cb + 3) / 4;
+    const int t = blockIdx.x;
+    const Tap tp = pb.taps[t];
+    const int lane = threadIdx.x % L;
+    const int sub = threadIdx.x / L + blockIdx.z * SUB;
+    const bool sub_ok = sub < qa * qb;
+    const int a0 = (sub_ok ? sub / qb : 0) * 4, b0 = (sub_ok ? sub % qb : 0) * 4;
+    const long long M = (long long)g.N * g.OH * g.OW;
+    long long chunk = (M + gridDim.y - 1) / gridDim.y;
+    const long long mbeg = (long long)blockIdx.y * chunk;
+    const long long mend = mbeg + chunk < M ? mbeg + chunk : M;
+    const bool vecG = (Ca % 4 == 0), vecX = (Cb % 4 == 0);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    if (sub_ok) {
+        const int ohw = g.OH * g.OW;
+        for (long long m = mbeg + lane; m < mend; m += L) {
+            const int n = (int)(m / ohw);
+            const int r = (int)(m - (long long)n * ohw);
+            const int oy = r / g.OW, ox = r - oy * g.OW;
+            const int iy = oy + tp.dy, ix = ox + tp.dx;
+            if (iy < 0 || iy >= g.IH || ix < 0 || ix >= g.IW) continue;
+            const T* pg = G + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx + a0;
+            const T* px = X + tp.in_off + (long long)n * g.i_sn + (long long)iy * g.i_sy + (long long)ix * g.i_sx + b0;
+            float4 gv, xv;
+            if (vecG) gv = ld4(pg);
+            else {
+                gv.x = Cvt<T>::to_f(pg[0]);
+                gv.y = a0 + 1 < Ca ? Cvt<T>::to_f(pg[1]) : 0.f;
+                gv.z = a0 + 2 < Ca ? Cvt<T>::to_f(pg[2]) : 0.f;
+                gv.w = a0 + 3 < Ca ? Cvt<T>::to_f(pg[3]) : 0.f;
+            }
+            if (vecX) xv = ld4(px);
+            else {
+                xv.x = Cvt<T>::to_f(px[0]);
+                xv.y = b0 + 1 < Cb ? Cvt<T>::to_f(px[1]) : 0.f;
+                xv.z = b0 + 2 < Cb ? Cvt<T>::to_f(px[2]) : 0.f;
+                xv.w = b0 + 3 < Cb ? Cvt<T>::to_f(px[3]) : 0.f;
+            }
+            const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, xb[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ga[i], xb[j], acc[i][j]);
+        }
+    }
+    // reduce over the pixel lanes of each sub-tile
+    constexpr int WL = L < 32 ? L : 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = acc[i][j];
+#pragma unroll
+            for (int o = WL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[i][j] = v;
+        }
+    if (L > 32) {
+        const int wsub = lane / 32;   // warp index within the sub-tile
+        if (lane % 32 == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) red[wsub][threadIdx.x / L][i * 4 + j] = acc[i][j];
+        }
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v = 0.f;
+                    for (int w2 = 0; w2 < L / 32; ++w2) v += red[w2][threadIdx.x / L][i * 4 + j];
+                    acc[i][j] = v;
+                }
+        }
+    }
+    if (lane == 0 && sub_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (a0 + i >= Ca) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (b0 + j >= Cb) continue;
+                atomicAdd(&a.dw[((long long)(a0 + i) * Cb + b0 + j) * a.KK + t], acc[i][j]);
+            }
+        }
+    }
+}
+
+template <typename T>
+static int launch_wgrad_direct(const WgradArgs& a, cudaStream_t st) {
+    const TapGeom& g = a.g;
+    const long long M = (long long)g.N * g.OH * g.OW;
+    const int subs = ((g.Nc + 3) / 4) * ((g.K + 3) / 4);
+    const int ntaps = g.prob[0].ntaps;
+    int SUB = subs <= 1 ? 1 : subs <= 4 ? 4 : subs <= 16 ? 16 : 64;
+    int groups = (subs + SUB - 1) / SUB;
+    const int L = 256 / SUB;
+    long long want = 8LL * num_sms();
+    long long split = (want + (long long)ntaps * groups - 1) / ((long long)ntaps * groups);
+    long long maxsplit = (M + 8LL * L - 1) / (8LL * L);      // >= 8 pixels per thread
+    if (split > maxsplit) split = maxsplit;
+    if (split < 1) split = 1;
+    if (split > 65535) split = 65535;
+    dim3 grid(ntaps, (unsigned)split, groups);
+    if (SUB == 1) wgrad_direct_kernel<T, 1><<<grid, 256, 0, st>>>(a);
+    else if (SUB == 4) wgrad_direct_kernel<T, 4><<<grid, 256, 0, st>>>(a);
+    else if (SUB == 16) wgrad_direct_kernel<T, 16><<<grid, 256, 0, st>>>(a);
+    else wgrad_direct_kernel<T, 64><<<grid, 256, 0, st>>>(a);
+    return check_launch("wgrad_direct_kernel");
+}
+
 static int launch_wgrad(WgradArgs& a, int dtype, int ksplit, cudaStream_t st) {
     const TapGeom& g = a.g;
     long long M = (long long)g.N * g.OH * g.OW;
     if (M == 0) return 0;
+    if ((g.Nc <= 16 || g.K <= 16) && ksplit <= 0) {
+        a.ksplit = 1;
+        return dtype == SVRS_F32 ? launch_wgrad_direct<float>(a, st) : launch_wgrad_direct<__nv_bfloat16>(a, st);
+    }
     int tiles = ((g.Nc + 63) / 64) * ((g.K + 63) / 64);
     int ntaps = g.prob[0].ntaps;
     if (ksplit <= 0) {

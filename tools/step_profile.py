@@ -1,0 +1,57 @@
+"""Per-launch device-time table of one eager training step (CUDA events around every C-ABI call).
+    python tools/step_profile.py [--dtype bf16] [--patches 128] [--top 40]
+"""
+import argparse
+import os
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "simple-vae-rs_b200")):
+    sys.path.insert(0, p)
+import torch
+
+import models
+from svrs_native import profile as prof
+from svrs_native.lib import lib
+from svrs_native.trainer import FusedCondTrainer
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--dtype", default="bf16")
+ap.add_argument("--patches", type=int, default=128)
+ap.add_argument("--top", type=int, default=45)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+model = models.Cond_SRVAE(2, 64).to(dev).train()
+model.set_compute_dtype(torch.bfloat16 if a.dtype == "bf16" else torch.float32)
+tr = FusedCondTrainer(model)
+x = torch.rand(a.patches, 4, 64, 64, device=dev)
+y = torch.rand(a.patches, 4, 32, 32, device=dev)
+for _ in range(2):
+    tr.step(x, y)
+torch.cuda.synchronize()
+lib.timing = []
+steps = 3
+for _ in range(steps):
+    tr.step(x, y)
+torch.cuda.synchronize()
+rec, lib.timing = lib.timing, None
+names = {n: [an for _, an in args] for n, (_, args) in lib.protos.items()}
+agg = defaultdict(lambda: [0.0, 0, 0.0])
+for name, args, e0, e1 in rec:
+    d = dict(zip(names[name], args))
+    key = name.replace("svrs_", "")
+    if "conv" in name:
+        key += f" N{d['N']} {d['H']}x{d['W']} {d['Cin']}->{d['Cout']}" + (f" k{d['ksize']}" if "ksize" in d else "")
+    elif "M" in d and "C" in d:
+        key += f" M{d['M']} C{d['C']}"
+    r = agg[key]
+    r[0] += e0.elapsed_time(e1) / steps
+    r[1] += 1
+    r[2] += prof._flops(name, args) / steps
+tot = sum(v[0] for v in agg.values())
+print(f"total kernel time per step (eager, event-timed): {tot:.3f} ms over {sum(v[1] for v in agg.values()) // steps} launches")
+for k, (ms, n, fl) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:a.top]:
+    tf = fl / (ms * 1e-3) / 1e12 if ms > 0 and fl > 0 else 0
+    print(f"{ms:8.3f} ms {100 * ms / tot:5.1f}%  x{n // steps:<3d} {tf:7.1f} TF/s  {k}")
