@@ -19,6 +19,7 @@ import torch
 from .elbo import elbo_forward
 from .engine import CondEngine, VaeEngine, _p, _st
 from .lib import F32, lib
+from .parallel import upstream_grad_scales
 
 
 class _AdamCfg:
@@ -70,7 +71,7 @@ class _FusedBase:
             self.gam_m = torch.zeros(2, device=dev, dtype=torch.float32)
             self.gam_v = torch.zeros(2, device=dev, dtype=torch.float32)
             self.dgam = torch.zeros(2, device=dev, dtype=torch.float32)
-            self.gout = torch.tensor([1.0, 1.0 / self.world, 1.0, 1.0 / self.world], device=dev)
+            self.gout = torch.tensor(upstream_grad_scales(self.world), device=dev)
             self._load_gammas_from_model()
             self.eng.rng.step_ptr = self.step_ptr
             self._graphs.clear()
