@@ -57,6 +57,13 @@ int svrs_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, 
 int svrs_pack_weights(const float* w, int d0, int d1, int kk, void* p01, void* p10, int dtype,
                       void* stream);
 
+/* All layers in one launch: `jobs` is a DEVICE array of njobs records
+ *   { const float* w; void* p01; void* p10; int d0, d1, kk; int tile0; int tiles_b; int pad; }   (svrs_pack_job_bytes() each)
+ * where a layer is cut into 32 x 16 tiles of its (d0, d1) plane, tiles_b = ceil(d1/16), and tile0 is the running sum of
+ * the tile counts of the preceding jobs; total_tiles = sum of all tile counts; max_kk = largest kk (<= 16). */
+int svrs_pack_job_bytes(void);
+int svrs_pack_weights_multi(const void* jobs, int njobs, int total_tiles, int max_kk, int dtype, void* stream);
+
 /* Two kernels sit behind each fprop/dgrad entry point:
  *   - conv_tc   (csrc/conv_tc.cu): tcgen05.mma + TMEM accumulators + TMA-fed SWIZZLE_128B operands; taken when
  *     dtype == BF16, the reduction channels are a multiple of 64, the written channels a multiple of 16 and the

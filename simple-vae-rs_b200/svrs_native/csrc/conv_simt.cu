@@ -472,8 +472,46 @@ static int launch_wgrad(WgradArgs& a, int dtype, int ksplit, cudaStream_t st) {
     return check_launch("wgrad_taps_kernel");
 }
 
+// vectorised variant: thread t owns channel quad (t % cg) and row lane (t / cg), cg = C/4 divides 256
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, long long M, int C,
+                                                          float* __restrict__ out, long long rows_per_block) {
+    __shared__ float red[256][4];
+    const int cg = C / 4;
+    const int q = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = 256 / cg;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long r = r0 + lane; r < r1; r += lanes) {
+        float4 v = ld4(x + r * C + q * 4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    red[threadIdx.x][0] = s.x; red[threadIdx.x][1] = s.y; red[threadIdx.x][2] = s.z; red[threadIdx.x][3] = s.w;
+    __syncthreads();
+    if (lane == 0) {
+        for (int l = 1; l < lanes; ++l) {
+            s.x += red[l * cg + q][0]; s.y += red[l * cg + q][1]; s.z += red[l * cg + q][2]; s.w += red[l * cg + q][3];
+        }
+        atomicAdd(&out[q * 4 + 0], s.x); atomicAdd(&out[q * 4 + 1], s.y);
+        atomicAdd(&out[q * 4 + 2], s.z); atomicAdd(&out[q * 4 + 3], s.w);
+    }
+}
+
 static int launch_colsum(const void* x, int dtype, long long M, int C, float* out, cudaStream_t st) {
     if (M == 0 || C == 0) return 0;
+    if (C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0) {
+        int lanes = 256 / (C / 4);
+        long long blocks = (M + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
+        long long cap = 4LL * num_sms();
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        long long rpb = (M + blocks - 1) / blocks;
+        blocks = (M + rpb - 1) / rpb;
+        if (dtype == SVRS_F32) colsum_vec_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, M, C, out, rpb);
+        else colsum_vec_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, M, C, out, rpb);
+        return check_launch("colsum_vec_kernel");
+    }
     long long blocks = (M + 511) / 512;
     long long cap = 8LL * num_sms();
     if (blocks > cap) blocks = cap;

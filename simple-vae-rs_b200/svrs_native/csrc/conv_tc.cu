@@ -3,19 +3,21 @@
 // One persistent, warp-specialised kernel runs every "multi-tap GEMM" conv form of taps.cuh
 // (k3s1 fprop/dgrad, k4s2 fprop/dgrad, transposed k4s2 fprop/dgrad):
 //
-//   D[128 output pixels, n_tile channels] = sum over taps t, 64-channel chunks c
-//        A_t,c [128 pixels shifted by (dy_t, dx_t), 64 ch]  x  W_t,c [n_tile, 64 ch]^T
+//   D[128 output pixels, n_tile channels] = sum over taps t, cw-channel chunks c
+//        A_t,c [128 pixels shifted by (dy_t, dx_t), cw ch]  x  W_t,c [n_tile, cw ch]^T
 //
 //   * A tiles are fetched by TMA from the NHWC activation tensor with a 4-D box
-//     (64 ch, BW, BH, BN images; BW*BH*BN = 128) whose start coordinate carries the tap shift;
+//     (cw ch, BW, BH, BN images; BW*BH*BN = 128) whose start coordinate carries the tap shift;
 //     out-of-range rows/columns are ZERO-FILLED by the TMA unit, which implements the conv padding.
 //     Stride-2 forms read through one of four "parity" tensor maps (element stride 2 in W and H).
-//   * both operands land in shared memory in the canonical K-major SWIZZLE_128B layout
-//     (128-byte rows = 64 bf16 channels, 8-row groups 1024 B apart), consumed directly by
-//     tcgen05.mma (M=128, N=n_tile, K=16) through shared-memory descriptors.
+//   * the channel chunk cw is 64, 32 or 16 (reduction channels % 64 / 32 / 16 == 0): rows of 128 / 64 / 32 bytes
+//     in the matching SWIZZLE_128B / 64B / 32B K-major layout (8-row groups 1024 / 512 / 256 B apart), consumed
+//     directly by tcgen05.mma (M=128, N=n_tile, K=16) through shared-memory descriptors.  For cw < 64 a pipeline
+//     stage carries 64/cw (tap, chunk) pairs so a stage always moves ~16 KB of activations.
 //   * accumulators live in TMEM (2 stages x 256 columns) so the epilogue of tile i overlaps the
 //     main loop of tile i+1; the epilogue (4 warps) does tcgen05.ld -> +bias -> activation -> bf16 ->
-//     128-bit global stores, one output pixel (row) per thread.
+//     128-bit global stores, one output pixel (row) per thread.  Output channels are padded to a multiple of 16
+//     for the MMA (weight rows beyond Nc are TMA zero fill) and masked at the store.
 //   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 #include "common.cuh"
 #include "taps.cuh"
@@ -26,7 +28,7 @@
 namespace svrs {
 
 constexpr int TC_STAGES = 4;
-constexpr int TC_A_BYTES = 128 * 128;        // 128 pixels x 64 bf16
+constexpr int TC_A_BYTES = 128 * 128;        // 128 pixels x 64 bf16 (or 64/cw pairs of 128 x cw)
 constexpr int TC_B_BYTES = 256 * 128;        // up to 256 output channels x 64 bf16
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -53,6 +55,7 @@ struct alignas(64) TcParams {
     int BW, BH, BNI;
     int tiles_x, tiles_y, tiles_n;
     int Nc, n_tile, n_tiles, kchunks;
+    int cw, tg;          // channel chunk width (16/32/64), (tap,chunk) pairs per pipeline stage (64/cw)
     int act, nprob;
     TcProb prob[4];
 };
@@ -91,7 +94,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int tiles_pix = p.tiles_x * p.tiles_y * p.tiles_n;
     const int tiles_per_prob = tiles_pix * p.n_tiles;
     const int total_tiles = tiles_per_prob * p.nprob;
-    const uint32_t b_bytes = (uint32_t)p.n_tile * 128u;
+    const uint32_t a_box = 128u * (uint32_t)p.cw * 2u;            // bytes of one activation box
+    const uint32_t b_box = (uint32_t)p.n_tile * (uint32_t)p.cw * 2u;  // bytes of one weight box
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -107,16 +111,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int tn = pt / p.tiles_y;
                 const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = tn * p.BNI;
                 const TcProb& pb = p.prob[pr];
-                for (int t = 0; t < pb.ntaps; ++t) {
-                    const TcTap tp = pb.taps[t];
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-                        mbar_expect_tx(full_bar(stage), (uint32_t)TC_A_BYTES + b_bytes);
-                        tma_load_4d(sa, &p.in_maps[tp.map], full_bar(stage), kc * 64, x0 + tp.dx, y0 + tp.dy, n0);
-                        tma_load_3d(sa + TC_A_BYTES, &p.w_map, full_bar(stage), kc * 64, nt * p.n_tile, tp.wtap);
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                const int npairs = pb.ntaps * p.kchunks;
+                for (int i0 = 0; i0 < npairs; i0 += p.tg) {
+                    const int cnt = (npairs - i0) < p.tg ? (npairs - i0) : p.tg;
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), (uint32_t)cnt * (a_box + b_box));
+                    for (int j = 0; j < cnt; ++j) {
+                        const int t = (i0 + j) / p.kchunks, kc = (i0 + j) % p.kchunks;
+                        const TcTap tp = pb.taps[t];
+                        tma_load_4d(sa + j * a_box, &p.in_maps[tp.map], full_bar(stage), kc * p.cw, x0 + tp.dx, y0 + tp.dy, n0);
+                        tma_load_3d(sa + TC_A_BYTES + j * b_box, &p.w_map, full_bar(stage), kc * p.cw, nt * p.n_tile, tp.wtap);
                     }
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -124,25 +131,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ================================ MMA issuer ================================
         // instruction descriptor: D=f32, A=B=bf16, both K-major, N = n_tile, M = 128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t sbo = 16u * (uint32_t)p.cw;                               // 8 rows x (cw * 2 B)
+        const uint32_t ltype = p.cw == 64 ? 2u : (p.cw == 32 ? 4u : 6u);         // SWIZZLE_128B / 64B / 32B
+        const int ksub = p.cw / 16;
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int pr = tile / tiles_per_prob;
-            const int iters = p.prob[pr].ntaps * p.kchunks;
+            const int npairs = p.prob[pr].ntaps * p.kchunks;
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256u;
-            for (int it = 0; it < iters; ++it) {
+            for (int i0 = 0; i0 < npairs; i0 += p.tg) {
+                const int cnt = (npairs - i0) < p.tg ? (npairs - i0) : p.tg;
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sa + TC_A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle span
-                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
-                    tc_commit(empty_bar(stage));                 // frees the smem stage when these MMAs retire
-                    if (it == iters - 1) tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint64_t adesc = make_kmajor_desc(sa + j * a_box, sbo, ltype);
+                        const uint64_t bdesc = make_kmajor_desc(sa + TC_A_BYTES + j * b_box, sbo, ltype);
+                        for (int k = 0; k < ksub; ++k)      // K = 16 bf16 = 32 B steps inside the swizzle span
+                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i0 | j | k) != 0);
+                    }
+                    tc_commit(empty_bar(stage));                          // frees the smem stage when these MMAs retire
+                    if (i0 + cnt >= npairs) tc_commit(tfull_bar(acc));    // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -154,6 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int q = warp % 4;                         // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                    // accumulator row == pixel within the tile
         const int ix = r % p.BW, iy = (r / p.BW) % p.BH, in = r / (p.BW * p.BH);
+        const bool vec_ok = (p.Nc % 8 == 0);
         uint32_t acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int pr = tile / tiles_per_prob;
@@ -179,19 +192,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
-                        if (j < cols && c_base + c0 + j < p.Nc) {
+                        const int c = c_base + c0 + j;
+                        if (j < cols && c < p.Nc) {
                             float f[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                float b = p.bias ? __ldg(p.bias + c_base + c0 + j + e) : 0.f;
+                                float b = (p.bias && c + e < p.Nc) ? __ldg(p.bias + c + e) : 0.f;
                                 f[e] = apply_act(__uint_as_float(v[j + e]) + b, p.act);
                             }
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-                            uint4 o;
-                            o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-                            o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(orow + c0 + j) = o;
+                            if (vec_ok) {
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+                                uint4 o;
+                                o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+                                o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+                                *reinterpret_cast<uint4*>(orow + c0 + j) = o;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e)
+                                    if (c + e < p.Nc) orow[c0 + j + e] = __float2bfloat16_rn(f[e]);
+                            }
                         }
                     }
                 }
@@ -227,32 +247,38 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// 4-D activation view map: dims (C, W, H, N) with arbitrary element strides for W/H/N; box (64, BW, BH, BNI); SWIZZLE_128B.
+static CUtensorMapSwizzle swizzle_for(int cw) {
+    return cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+int chunk_width(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 0)); }
+
+// 4-D activation view map: dims (C, W, H, N) with arbitrary element strides for W/H/N; box (cw, BW, BH, BNI)
 int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sx, long long sy, long long sn,
-                        int BW, int BH, int BNI) {
+                 int BW, int BH, int BNI, int cw) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SVRS_E_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sn * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BNI};
+    cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BNI};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation) failed: %d (C=%d W=%d H=%d N=%d)", (int)r, C, W, H, N); return SVRS_E_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation) failed: %d (C=%d W=%d H=%d N=%d cw=%d)", (int)r, C, W, H, N, cw); return SVRS_E_CUDA; }
     return 0;
 }
 
-// weights in NK pack [tap][Nc][K] (K contiguous): dims (K, Nc, taps), box (64, n_tile, 1)
-static int make_w_map(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile) {
+// weights in NK pack [tap][Nc][K] (K contiguous): dims (K, Nc, taps), box (cw, n_tile, 1)
+static int make_w_map(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile, int cw) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SVRS_E_CUDA; }
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Nc, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * Nc * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)n_tile, 1};
+    cuuint32_t box[3] = {(cuuint32_t)cw, (cuuint32_t)n_tile, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d (K=%d Nc=%d taps=%d)", (int)r, K, Nc, taps); return SVRS_E_CUDA; }
     return 0;
@@ -270,7 +296,8 @@ bool pick_box(int OW, int OH, int& BW, int& BH, int& BNI) {
 
 bool tc_supported(int dtype, int K, int Nc, int OW, int OH) {
     int bw, bh, bn;
-    return dtype == SVRS_BF16 && K % 64 == 0 && Nc % 16 == 0 && Nc >= 16 && pick_box(OW, OH, bw, bh, bn);
+    // K % 16: UMMA K; Nc % 4: 8-byte aligned output rows (N is padded to 16 for the MMA); K*2 B rows must be 16-B multiples
+    return dtype == SVRS_BF16 && chunk_width(K) != 0 && Nc % 4 == 0 && Nc >= 4 && pick_box(OW, OH, bw, bh, bn);
 }
 
 // form: 0 conv3 fprop, 1 conv3 dgrad, 2 conv4s2 (strided read), 3 convT4s2 (strided write).
@@ -299,9 +326,12 @@ int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias
     p.N = N; p.OH = g.OH; p.OW = g.OW;
     p.tiles_x = g.OW / p.BW; p.tiles_y = g.OH / p.BH; p.tiles_n = (N + p.BNI - 1) / p.BNI;
     p.Nc = Cw;
-    p.n_tile = Cw <= 256 ? Cw : 256;
+    int npad = (Cw + 15) / 16 * 16;
+    p.n_tile = npad <= 256 ? npad : 256;
     p.n_tiles = (Cw + p.n_tile - 1) / p.n_tile;
-    p.kchunks = Cr / 64;
+    p.cw = chunk_width(Cr);
+    p.tg = 64 / p.cw;
+    p.kchunks = Cr / p.cw;
     p.act = act; p.nprob = g.nprob;
 
     // input maps: distinct in_off values become distinct tensor maps (parity classes of a stride-2 read)
@@ -322,10 +352,10 @@ int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias
     const __nv_bfloat16* inb = reinterpret_cast<const __nv_bfloat16*>(in);
     for (int i = 0; i < 4; ++i) {
         long long off = i < nmaps ? offs[i] : offs[0];
-        int rc = make_act_map(&p.in_maps[i], inb + off, Cr, g.IW, g.IH, N, g.i_sx, g.i_sy, g.i_sn, p.BW, p.BH, p.BNI);
+        int rc = make_act_map(&p.in_maps[i], inb + off, Cr, g.IW, g.IH, N, g.i_sx, g.i_sy, g.i_sn, p.BW, p.BH, p.BNI, p.cw);
         if (rc) return rc;
     }
-    int rc = make_w_map(&p.w_map, w_nk, Cr, Cw, ntaps_total, p.n_tile);
+    int rc = make_w_map(&p.w_map, w_nk, Cr, Cw, ntaps_total, p.n_tile, p.cw);
     if (rc) return rc;
 
     long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * p.nprob;

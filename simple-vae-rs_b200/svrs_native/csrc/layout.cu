@@ -226,3 +226,68 @@ extern "C" int svrs_act_bwd(const void* y, const void* dy, void* dx, int dtype, 
     else { set_error("act_bwd: bad dtype"); return SVRS_E_ARG; }
     return check_launch("act_bwd");
 }
+
+// ------------------------------------------------------------------------------------------------
+// All layers' weight packs in ONE launch.  A CTA owns a 32 (d0) x 16 (d1) tile of one layer for all kk taps: it reads
+// 32 contiguous runs of 16*kk fp32 (coalesced), transposes through shared memory and writes both packs with
+// contiguous 16/32-element runs.  `jobs` is a device array built once by the host runtime.
+// ------------------------------------------------------------------------------------------------
+namespace svrs {
+struct PackJob {
+    const float* w;
+    void* p01;
+    void* p10;
+    int d0, d1, kk;
+    int tile0;     // first global tile index of this job
+    int tiles_b;   // tiles along d1
+    int pad_;
+};
+constexpr int PK_TA = 32, PK_TB = 16;
+
+template <typename TD>
+__global__ void __launch_bounds__(256) pack_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    extern __shared__ float tile[];
+    int j = 0;
+    while (j + 1 < njobs && jobs[j + 1].tile0 <= (int)blockIdx.x) ++j;
+    const PackJob jb = jobs[j];
+    const int lt = blockIdx.x - jb.tile0;
+    const int a0 = (lt / jb.tiles_b) * PK_TA, b0 = (lt % jb.tiles_b) * PK_TB;
+    const int kk = jb.kk, d0 = jb.d0, d1 = jb.d1;
+    const int na = d0 - a0 < PK_TA ? d0 - a0 : PK_TA, nb = d1 - b0 < PK_TB ? d1 - b0 : PK_TB;
+    const int ROW = PK_TB * (kk + 1) + 1;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int run = nb * kk;
+    for (int a = warp; a < na; a += 8) {
+        const float* src = jb.w + ((long long)(a0 + a) * d1 + b0) * kk;
+        for (int i = lane; i < run; i += 32) tile[a * ROW + (i / kk) * (kk + 1) + (i % kk)] = src[i];
+    }
+    __syncthreads();
+    TD* p01 = reinterpret_cast<TD*>(jb.p01);
+    TD* p10 = reinterpret_cast<TD*>(jb.p10);
+    const int total = kk * na * nb;
+    if (p01) {
+        for (int idx = threadIdx.x; idx < total; idx += 256) {
+            int b = idx % nb, a = (idx / nb) % na, t = idx / (nb * na);
+            p01[((long long)t * d0 + a0 + a) * d1 + b0 + b] = Cvt<TD>::from_f(tile[a * ROW + b * (kk + 1) + t]);
+        }
+    }
+    if (p10) {
+        for (int idx = threadIdx.x; idx < total; idx += 256) {
+            int a = idx % na, b = (idx / na) % nb, t = idx / (nb * na);
+            p10[((long long)t * d1 + b0 + b) * d0 + a0 + a] = Cvt<TD>::from_f(tile[a * ROW + b * (kk + 1) + t]);
+        }
+    }
+}
+}  // namespace svrs
+
+extern "C" int svrs_pack_job_bytes(void) { return (int)sizeof(svrs::PackJob); }
+
+extern "C" int svrs_pack_weights_multi(const void* jobs, int njobs, int total_tiles, int max_kk, int dtype, void* stream) {
+    SVRS_CHECK_ARG(jobs && njobs > 0 && total_tiles > 0 && max_kk > 0 && max_kk <= 16, "pack_weights_multi: bad args");
+    size_t smem = (size_t)svrs::PK_TA * (svrs::PK_TB * (max_kk + 1) + 1) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SVRS_F32) svrs::pack_multi_kernel<float><<<total_tiles, 256, smem, st>>>((const svrs::PackJob*)jobs, njobs);
+    else if (dtype == SVRS_BF16) svrs::pack_multi_kernel<__nv_bfloat16><<<total_tiles, 256, smem, st>>>((const svrs::PackJob*)jobs, njobs);
+    else { set_error("pack_weights_multi: bad dtype"); return SVRS_E_ARG; }
+    return check_launch("pack_weights_multi");
+}

@@ -80,33 +80,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: 128-byte rows, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+// Shared-memory matrix descriptors (tcgen05 "SmemDescriptor"): start address bits [0,14) (>>4), leading byte offset
+// bits [16,30) (>>4), stride byte offset bits [32,46) (>>4), version = 1 at bit 46, layout type bits [61,64):
+// 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
+//
+// K-major operand: rows of cw*2 bytes (cw = 64/32/16 bf16 -> 128/64/32-byte swizzle), 8-row groups `sbo` bytes apart.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t sbo, uint32_t ltype) {
     uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address       bits [0,14)
-    d |= (uint64_t)1 << 16;                         // leading byte offset  bits [16,30) (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset   bits [32,46)
-    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                         // layout type: SWIZZLE_128B
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                          // LBO unused for swizzled K-major layouts
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)ltype << 61;
     return d;
 }
-
-
-// MN-major, SWIZZLE_128B descriptor: the MN dimension is contiguous (64 bf16 per 128-byte row), K runs across rows;
-// 8-row (K) groups are `sbo` bytes apart and consecutive 64-element MN spans `lbo` bytes apart.
-__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+// MN-major operand: the MN dimension is contiguous inside a row (cw elements), K runs across rows; 8-row (K) groups
+// are `sbo` bytes apart and consecutive cw-element MN spans `lbo` bytes apart.
+__device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t ltype) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)ltype << 61;
     return d;
 }
 
 // host helpers (conv_tc.cu)
 int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sx, long long sy, long long sn,
-                 int BW, int BH, int BNI);
+                 int BW, int BH, int BNI, int cw);
 bool pick_box(int OW, int OH, int& BW, int& BH, int& BNI);
+int chunk_width(int C);   // 64 / 32 / 16 / 0 (unsupported)
 
 }  // namespace svrs

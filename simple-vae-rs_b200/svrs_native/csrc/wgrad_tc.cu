@@ -3,10 +3,10 @@
 //   dW_t[a][b] = sum over output-grid pixels m of  G[m][a] * X_t[m shifted by tap t][b]
 //
 // GEMM view per CTA:  D[(tap, b) rows, a columns] += Xstack^T * G, reduction (K) over pixels.
-//   * M (128 rows of one "M-block") = two 64-channel boxes of X taken at one or two taps; the boxes are the same
-//     TMA tiles the forward kernel reads (64 ch x 128 pixels, SWIZZLE_128B) and are fed to tcgen05.mma as an
-//     MN-MAJOR A operand (channels contiguous, pixels = K), the two boxes one LBO apart.
-//   * N = up to 128 channels of G (MN-major B operand, same box shape).
+//   * M (128 rows of one "M-block") = 128/cwx boxes of X, each cwx channels wide (cwx = 64/32/16) taken at one or
+//     more taps; the boxes are the same TMA tiles the forward kernel reads (cwx ch x 128 pixels, 128/64/32-byte
+//     swizzle) and are fed to tcgen05.mma as an MN-MAJOR A operand (channels contiguous, pixels = K), boxes one LBO apart.
+//   * N = up to 128 channels of G (MN-major B operand, boxes cwg = min(64, Ca) channels wide).
 //   * K = 128 pixels per pipeline stage (8 MMAs of K=16); the pixel range is split over CTAs.
 //   * every CTA keeps up to 512/N M-blocks of accumulators resident in TMEM for its whole pixel range and
 //     finishes with fp32 atomics into the torch-layout gradient dw[(a*Cb + b)*KK + tap].
@@ -19,11 +19,12 @@
 namespace svrs {
 
 constexpr int WG_STAGES = 3;
-constexpr int WG_X_BYTES = 2 * 16384;      // one M-block: two boxes of 128 pixels x 64 ch
-constexpr int WG_G_BYTES = 2 * 16384;      // up to 128 channels of G
+constexpr int WG_X_BYTES = 128 * 128 * 2;  // one M-block: 128 rows (box channels) x 128 pixels
+constexpr int WG_G_BYTES = 128 * 128 * 2;  // up to 128 channels of G x 128 pixels
 constexpr int WG_STAGE_BYTES = WG_X_BYTES + WG_G_BYTES;
 constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 constexpr int WG_THREADS = 192;
+constexpr int WG_MAX_GROUP = 16;
 
 struct WgTap { int map, dy, dx, tapid; };
 struct alignas(64) WgParams {
@@ -34,7 +35,9 @@ struct alignas(64) WgParams {
     int tiles_x, tiles_y, tiles_n;     // pixel tiling of the output grid
     int Ca, Cb, KK;
     int n_tile, n_tiles;               // columns (a) per CTA
-    int cb_chunks;                     // Cb / 64
+    int cwx, cwg;                      // box widths (channels) of the X and G operands
+    int cb_chunks;                     // Cb / cwx
+    int bpb;                           // boxes per M-block = 128 / cwx
     int nboxes, nblocks, group, ngroups;
     int ksplit, ksteps_total;
     int ntaps;
@@ -79,7 +82,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int k_begin = ks * steps_per;
     const int k_end = (k_begin + steps_per) < p.ksteps_total ? (k_begin + steps_per) : p.ksteps_total;
     const int nsteps = k_end > k_begin ? k_end - k_begin : 0;
-    const int g_boxes = p.n_tile / 64;
+    const int g_boxes = (p.n_tile + p.cwg - 1) / p.cwg;
+    const uint32_t x_box = 128u * (uint32_t)p.cwx * 2u;   // bytes of one X box  (128 pixels x cwx ch)
+    const uint32_t g_box = 128u * (uint32_t)p.cwg * 2u;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -94,17 +99,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
                     const uint32_t sg = sx + WG_X_BYTES;
-                    mbar_expect_tx(full_bar(stage), (uint32_t)(2 + g_boxes) * 16384u);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        int box = 2 * (blk0 + b) + h;
-                        if (box >= p.nboxes) box = p.nboxes - 1;       // odd tail: duplicate (rows are ignored by the epilogue)
+                    mbar_expect_tx(full_bar(stage), (uint32_t)p.bpb * x_box + (uint32_t)g_boxes * g_box);
+                    for (int h = 0; h < p.bpb; ++h) {
+                        int box = p.bpb * (blk0 + b) + h;
+                        if (box >= p.nboxes) box = p.nboxes - 1;       // tail: duplicate (rows are ignored by the epilogue)
                         const WgTap tp = p.taps[box / p.cb_chunks];
                         const int cj = box % p.cb_chunks;
-                        tma_load_4d(sx + h * 16384u, &p.x_maps[tp.map], full_bar(stage), cj * 64, x0 + tp.dx, y0 + tp.dy, n0);
+                        tma_load_4d(sx + h * x_box, &p.x_maps[tp.map], full_bar(stage), cj * p.cwx, x0 + tp.dx, y0 + tp.dy, n0);
                     }
                     for (int gbx = 0; gbx < g_boxes; ++gbx)
-                        tma_load_4d(sg + gbx * 16384u, &p.g_map, full_bar(stage), nt * p.n_tile + gbx * 64, x0, y0, n0);
+                        tma_load_4d(sg + gbx * g_box, &p.g_map, full_bar(stage), nt * p.n_tile + gbx * p.cwg, x0, y0, n0);
                     if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -113,6 +117,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = n_tile, M = 128
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t lt_x = p.cwx == 64 ? 2u : (p.cwx == 32 ? 4u : 6u);
+        const uint32_t lt_g = p.cwg == 64 ? 2u : (p.cwg == 32 ? 4u : 6u);
+        const uint32_t sbo_x = 16u * (uint32_t)p.cwx, sbo_g = 16u * (uint32_t)p.cwg;        // 8 pixel rows
+        const uint32_t kadv_x = 32u * (uint32_t)p.cwx, kadv_g = 32u * (uint32_t)p.cwg;      // 16 pixel rows per MMA
         uint32_t stage = 0, phase = 0;
         for (int kstep = 0; kstep < nsteps; ++kstep) {
             for (int b = 0; b < nblk; ++b) {
@@ -123,9 +131,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                     const uint32_t sg = sx + WG_X_BYTES;
                     const uint32_t d_tmem = tmem_base + (uint32_t)(b * p.n_tile);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {     // 8 x (K = 16 pixels = 16 rows of 128 B)
-                        const uint64_t adesc = make_sw128_mn_desc(sx + k * 2048u, 16384u, 1024u);
-                        const uint64_t bdesc = make_sw128_mn_desc(sg + k * 2048u, 16384u, 1024u);
+                    for (int k = 0; k < 8; ++k) {     // 8 x (K = 16 pixels)
+                        const uint64_t adesc = make_mn_desc(sx + k * kadv_x, x_box, sbo_x, lt_x);
+                        const uint64_t bdesc = make_mn_desc(sg + k * kadv_g, g_box, sbo_g, lt_g);
                         tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kstep | k) != 0);
                     }
                     tc_commit(empty_bar(stage));
@@ -141,21 +149,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         mbar_wait(done_bar, 0);
         tc_fence_after();
         for (int b = 0; b < nblk; ++b) {
-            const int box = 2 * (blk0 + b) + (m >= 64 ? 1 : 0);
+            const int box = p.bpb * (blk0 + b) + m / p.cwx;
             const bool row_ok = box < p.nboxes;
             const int bx = row_ok ? box : 0;
             const int tapid = p.taps[bx / p.cb_chunks].tapid;
-            const int cb = (bx % p.cb_chunks) * 64 + (m & 63);
+            const int cb = (bx % p.cb_chunks) * p.cwx + (m % p.cwx);
             const uint32_t taddr = tmem_base + (uint32_t)(b * p.n_tile) + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
+                const int cols = (p.n_tile - c0 >= 32) ? 32 : 16;
+                if (cols == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int ca = nt * p.n_tile + c0 + j;
-                        if (ca < p.Ca) atomicAdd(p.dw + ((long long)ca * p.Cb + cb) * p.KK + tapid, __uint_as_float(v[j]));
+                        if (j < cols && ca < p.Ca) atomicAdd(p.dw + ((long long)ca * p.Cb + cb) * p.KK + tapid, __uint_as_float(v[j]));
                     }
                 }
             }
@@ -172,7 +181,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
 bool wgrad_tc_supported(int dtype, int Ca, int Cb, int OW, int OH) {
     int bw, bh, bn;
-    return dtype == SVRS_BF16 && Ca % 64 == 0 && Cb % 64 == 0 && pick_box(OW, OH, bw, bh, bn);
+    // Ca: 16 / 32 (single narrow box) or a multiple of 64 ; Cb: any multiple of 16
+    const bool ca_ok = Ca == 16 || Ca == 32 || (Ca >= 64 && Ca % 64 == 0);
+    return dtype == SVRS_BF16 && ca_ok && chunk_width(Cb) != 0 && pick_box(OW, OH, bw, bh, bn);
 }
 
 // g: geometry of the forward-form conv whose output grid carries `gmat` (channels Ca = g.Nc) and whose input view
@@ -193,12 +204,16 @@ int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw
     p.Ca = g.Nc; p.Cb = g.K; p.KK = KK;
     p.n_tile = p.Ca < 128 ? p.Ca : 128;
     p.n_tiles = (p.Ca + p.n_tile - 1) / p.n_tile;
-    p.cb_chunks = p.Cb / 64;
+    p.cwg = p.Ca < 64 ? p.Ca : 64;
+    p.cwx = chunk_width(p.Cb);
+    p.cb_chunks = p.Cb / p.cwx;
+    p.bpb = 128 / p.cwx;
     const Prob& pb = g.prob[0];
     p.ntaps = pb.ntaps;
     p.nboxes = pb.ntaps * p.cb_chunks;
-    p.nblocks = (p.nboxes + 1) / 2;
+    p.nblocks = (p.nboxes + p.bpb - 1) / p.bpb;
     p.group = 512 / p.n_tile;
+    if (p.group > WG_MAX_GROUP) p.group = WG_MAX_GROUP;
     if (p.group > p.nblocks) p.group = p.nblocks;
     p.ngroups = (p.nblocks + p.group - 1) / p.group;
     p.ksteps_total = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -219,11 +234,11 @@ int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw
     const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
     for (int i = 0; i < 4; ++i) {
         long long off = i < nmaps ? offs[i] : offs[0];
-        int rc = make_act_map(&p.x_maps[i], xb + off, p.Cb, g.IW, g.IH, g.N, g.i_sx, g.i_sy, g.i_sn, p.BW, p.BH, p.BNI);
+        int rc = make_act_map(&p.x_maps[i], xb + off, p.Cb, g.IW, g.IH, g.N, g.i_sx, g.i_sy, g.i_sn, p.BW, p.BH, p.BNI, p.cwx);
         if (rc) return rc;
     }
     const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(gmat) + pb.out_off;
-    int rc = make_act_map(&p.g_map, gb, p.Ca, g.OW, g.OH, g.N, g.o_sx, g.o_sy, g.o_sn, p.BW, p.BH, p.BNI);
+    int rc = make_act_map(&p.g_map, gb, p.Ca, g.OW, g.OH, g.N, g.o_sx, g.o_sy, g.o_sn, p.BW, p.BH, p.BNI, p.cwg);
     if (rc) return rc;
 
     int grid = p.ngroups * p.n_tiles * p.ksplit;

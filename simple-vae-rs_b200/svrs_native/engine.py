@@ -199,6 +199,8 @@ class Runtime:
         self.dt = _dt(compute_dtype)
         self.store = ParamStore(module)
         self._scratch: Optional[torch.Tensor] = None
+        self._pack_jobs: Optional[torch.Tensor] = None
+        self._pack_key = None
         self.packs_dirty = True
         self.launches = 0          # kernels enqueued (our own), for bench.py's gpu_launches
 
@@ -250,27 +252,40 @@ class Runtime:
         self.launches += 1
 
     def pack_weights(self, force: bool = False):
-        """fp32 master weights (torch layout) -> per-tap KN packs in the compute dtype."""
+        """fp32 master weights (torch layout) -> per-tap KN/NK packs in the compute dtype, all layers in one launch."""
         if not (self.packs_dirty or force):
             return
-        dev, st = self.device, _st()
-        for net in self.nets:
-            for op in net.ops:
-                if not isinstance(op, ConvOp):
-                    continue
+        dev = self.device
+        convs = [op for net in self.nets for op in net.ops if isinstance(op, ConvOp)]
+        rebuild = self._pack_jobs is None or self._pack_jobs.device != dev
+        for op in convs:
+            if op.pack_f is None or op.pack_f.device != dev or op.pack_f.dtype != self.dtype:
+                n = op.mod.weight.numel()
+                op.pack_f = torch.empty(n, device=dev, dtype=self.dtype)
+                op.pack_b = torch.empty(n, device=dev, dtype=self.dtype)
+                rebuild = True
+        if rebuild or self._pack_key != self.store.flat.data_ptr():
+            import numpy as np
+            rec = np.dtype([("w", "<u8"), ("p01", "<u8"), ("p10", "<u8"), ("d0", "<i4"), ("d1", "<i4"), ("kk", "<i4"),
+                            ("tile0", "<i4"), ("tiles_b", "<i4"), ("pad", "<i4")])
+            assert rec.itemsize == lib.pack_job_bytes()
+            jobs = np.zeros(len(convs), dtype=rec)
+            tile0 = 0
+            for i, op in enumerate(convs):
                 w = op.mod.weight
-                n = w.numel()
-                if op.pack_f is None or op.pack_f.device != dev:
-                    op.pack_f = torch.empty(n, device=dev, dtype=self.dtype)
-                    op.pack_b = torch.empty(n, device=dev, dtype=self.dtype)
                 d0, d1 = w.shape[0], w.shape[1]
-                if op.kind == "ct":
-                    # weight [Cin][Cout][16]: fprop wants [t][Cin][Cout] = p01, dgrad wants [t][Cout][Cin] = p10
-                    lib.pack_weights(_p(w.data), d0, d1, op.kk, _p(op.pack_f), _p(op.pack_b), self.dt, st)
-                else:
-                    # weight [Cout][Cin][kk]: fprop wants [t][Cin][Cout] = p10, dgrad wants [t][Cout][Cin] = p01
-                    lib.pack_weights(_p(w.data), d0, d1, op.kk, _p(op.pack_b), _p(op.pack_f), self.dt, st)
-                self.launches += 1
+                # conv  weight [Cout][Cin][kk]: fprop KN pack [t][Cin][Cout] = p10, dgrad KN pack [t][Cout][Cin] = p01
+                # convT weight [Cin][Cout][16]: fprop KN pack [t][Cin][Cout] = p01, dgrad KN pack [t][Cout][Cin] = p10
+                p01, p10 = (op.pack_f, op.pack_b) if op.kind == "ct" else (op.pack_b, op.pack_f)
+                tiles_b = (d1 + 15) // 16
+                jobs[i] = (w.data.data_ptr(), p01.data_ptr(), p10.data_ptr(), d0, d1, op.kk, tile0, tiles_b, 0)
+                tile0 += ((d0 + 31) // 32) * tiles_b
+            self._pack_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).to(dev)
+            self._pack_tiles = tile0
+            self._pack_n = len(convs)
+            self._pack_key = self.store.flat.data_ptr()
+        lib.pack_weights_multi(_p(self._pack_jobs), self._pack_n, self._pack_tiles, 16, self.dt, _st())
+        self.launches += 1
         self.packs_dirty = False
 
     # -------------------------------------------------------------------------------------- layout glue

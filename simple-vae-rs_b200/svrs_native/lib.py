@@ -88,7 +88,7 @@ class _Lib:
         if full not in self.protos:
             raise AttributeError(name)
         fn = getattr(self.load(), full)
-        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run"):
+        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run", "svrs_pack_job_bytes"):
             setattr(self, name, fn)
             return fn
 

@@ -408,6 +408,11 @@ TC_CASES = [
     (1, 64, 64, 64, 16),      # decoder tail 64 -> 16 at 64x64 (N tile 16)
     (2, 32, 32, 128, 128),
     (9, 4, 4, 64, 48),        # N tile 48 = 32 + 16 column loads, 9 images over two tiles
+    (2, 16, 16, 16, 16),      # 16-channel chunks: SWIZZLE_32B operands, 4 (tap, chunk) pairs per stage
+    (1, 64, 64, 16, 4),       # last decoder conv: N padded 4 -> 16 for the MMA, masked scalar stores
+    (2, 8, 8, 32, 128),       # 32-channel chunks: SWIZZLE_64B
+    (3, 8, 8, 48, 16),        # 3 chunks of 16 channels
+    (2, 32, 32, 64, 16),      # decoder tail 64 -> 16
 ]
 
 
@@ -458,7 +463,8 @@ def test_conv_tc_all_forms(case):
 
 
 @pytest.mark.parametrize("case", [(2, 8, 8, 64, 64), (3, 16, 16, 128, 64), (2, 4, 4, 256, 512), (2, 32, 32, 128, 128),
-                                  (5, 8, 8, 64, 192)])
+                                  (5, 8, 8, 64, 192), (2, 16, 16, 16, 16), (2, 32, 32, 64, 16), (2, 8, 8, 32, 128),
+                                  (3, 8, 8, 48, 32), (2, 16, 16, 16, 64)])
 def test_wgrad_tc_all_forms(case):
     """tcgen05 weight-gradient kernel (MN-major operands, split-K over pixels) vs float64 torch autograd."""
     N, H, W, Cin, Cout = case
@@ -493,3 +499,25 @@ def test_wgrad_tc_all_forms(case):
         lib.set_tc_enabled(1)
         report(f"wgrad_tc {form} {case} vs fp64", res[1], wr.grad, 2e-5)
         report(f"wgrad_tc {form} {case} vs simt", res[1], res[0], 2e-5)
+
+
+def test_pack_weights_multi_matches_single():
+    """The one-launch, shared-memory-tiled pack of all layers equals the simple per-layer pack (both dtypes, conv + convT)."""
+    import models
+    from svrs_native.engine import ConvOp
+    for dtype in (torch.float32, torch.bfloat16):
+        m = models.VAE(2, 32).to(DEV)
+        m.set_compute_dtype(dtype)
+        eng = m._engine()
+        eng.rt.ensure()
+        eng.rt.pack_weights(force=True)
+        torch.cuda.synchronize()
+        n = 0
+        for net in eng.nets.values():
+            for op in net.ops:
+                if not isinstance(op, ConvOp):
+                    continue
+                pf, pb = pack(op.mod.weight.data, dtype, convT=(op.kind == "ct"))
+                assert torch.equal(op.pack_f, pf) and torch.equal(op.pack_b, pb), (net.name, op.kind, op.cin, op.cout)
+                n += 1
+        assert n == 16
