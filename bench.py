@@ -290,9 +290,15 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # Leave without tearing NCCL down: communicators captured inside CUDA graphs make destroy_process_group() hang
+        # (observed at N=2).  Everything is synchronised and flushed, so a hard exit is safe.
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

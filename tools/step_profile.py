@@ -55,3 +55,57 @@ print(f"total kernel time per step (eager, event-timed): {tot:.3f} ms over {sum(
 for k, (ms, n, fl) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:a.top]:
     tf = fl / (ms * 1e-3) / 1e12 if ms > 0 and fl > 0 else 0
     print(f"{ms:8.3f} ms {100 * ms / tot:5.1f}%  x{n // steps:<3d} {tf:7.1f} TF/s  {k}")
+byfn = defaultdict(lambda: [0.0, 0])
+for name, args, e0, e1 in rec:
+    byfn[name.replace("svrs_", "")][0] += e0.elapsed_time(e1) / steps
+    byfn[name.replace("svrs_", "")][1] += 1
+print("---- by C-ABI function")
+for k, (ms, n) in sorted(byfn.items(), key=lambda kv: -kv[1][0]):
+    print(f"{ms:8.3f} ms {100 * ms / tot:5.1f}%  x{n // steps:<3d} {k}")
+
+# ---- pure GPU time per launch: re-issue every recorded call 8x inside a captured CUDA graph (no host gaps)
+if os.environ.get("SVRS_REPLAY", "1") == "1":
+    first = [r for r in rec[: len(rec) // steps]]
+    keep = [x, y, tr]          # keep buffers alive; stale activations stay mapped in the caching allocator
+    reps = 8
+    table = []
+    side = torch.cuda.Stream()
+    for name, args, _, _ in first:
+        fn = getattr(lib, name.replace("svrs_", ""))
+        args = list(args)
+        with torch.cuda.stream(side):
+            args[-1] = side.cuda_stream
+            fn(*args)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                args[-1] = torch.cuda.current_stream().cuda_stream
+                for _ in range(reps):
+                    fn(*args)
+            g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            e1.synchronize()
+        d = dict(zip(names[name], args))
+        key = name.replace("svrs_", "")
+        if "conv" in name:
+            key += f" N{d['N']} {d['H']}x{d['W']} {d['Cin']}->{d['Cout']}" + (f" k{d['ksize']}" if "ksize" in d else "")
+        elif "M" in d and "C" in d:
+            key += f" M{d['M']} C{d['C']}"
+        table.append((e0.elapsed_time(e1) / reps, key, prof._flops(name, tuple(args))))
+    tot2 = sum(t[0] for t in table)
+    print(f"==== pure GPU time (graph-replayed, warm L2): {tot2:.3f} ms per step over {len(table)} launches")
+    agg2 = defaultdict(lambda: [0.0, 0, 0.0])
+    for ms, key, fl in table:
+        agg2[key][0] += ms; agg2[key][1] += 1; agg2[key][2] += fl
+    for k, (ms, n, fl) in sorted(agg2.items(), key=lambda kv: -kv[1][0])[:a.top]:
+        tf = fl / (ms * 1e-3) / 1e12 if fl > 0 else 0
+        print(f"{ms * 1e3:9.1f} us {100 * ms / tot2:5.1f}%  x{n:<3d} {tf:7.1f} TF/s  {k}")
+    byfn2 = defaultdict(float)
+    for ms, key, fl in table:
+        byfn2[key.split(" ")[0]] += ms
+    print("---- pure GPU time by function")
+    for k, ms in sorted(byfn2.items(), key=lambda kv: -kv[1]):
+        print(f"{ms * 1e3:9.1f} us {100 * ms / tot2:5.1f}%  {k}")
