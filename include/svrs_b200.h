@@ -73,6 +73,11 @@ int svrs_pack_weights_multi(const void* jobs, int njobs, int total_tiles, int ma
  * The two packs of a layer are each other's transposes, i.e. the (p01, p10) pair of svrs_pack_weights: the KN pack
  * of fprop is the NK pack of dgrad and vice versa.  w_nk may be NULL (forces the SIMT kernel). */
 void svrs_set_tc_enabled(int enabled);   /* default 1; 0 forces the SIMT kernels everywhere (A/B tests) */
+/* conv3_halo (csrc/conv_halo.cu): 3x3 stride-1 fprop/dgrad on maps tiling into 8x16 blocks load each tile's activation
+ * halo ONCE and address the nine taps as shared-memory descriptors.  mode 0 = off (per-tap TMA kernel), 1 = on (default),
+ * 2 = on WITH the descriptor base-offset field set to (start >> 7) & 7 (hardware experiment: gives wrong results on B200,
+ * which shows the UMMA swizzle is a function of the absolute shared-memory address). */
+void svrs_set_halo_mode(int mode);
 int svrs_tc_would_run(int dtype, int K, int Nc, int OH, int OW); /* 1 if conv_tc takes a GEMM of these dims */
 
 /* ---- nn.Conv2d k3 s1 p1 / k4 s2 p1 (layers.py:231-236; every bare nn.Conv2d of cond_vae.py / vae.py)

@@ -1,0 +1,278 @@
+// conv_halo.cu - halo-reuse variant of the tcgen05 implicit-GEMM kernel for the 3x3 stride-1 forms (conv3 fprop and
+// dgrad) on maps that tile into 8 x 16 pixel blocks.
+//
+// conv_tc.cu fetches one shifted 128-pixel A box PER TAP (9 x 16 KB per 64-channel chunk and tile), which makes the
+// 64/128-channel layers at 32x32 / 64x64 L2-bandwidth bound.  Here the activation HALO of a tile
+// (18 rows x 16 pixels x 64 channels, one TMA box, 36 KB) is loaded ONCE per channel chunk and the nine taps are nine
+// shared-memory matrix descriptors into that same tile:
+//     tile = 8 (W) x 16 (H) output pixels; M row r = (iy = r / 8, ix = r % 8)
+//     tap (dy, dx): descriptor start = halo + ((dy+1) * 16 + (dx+1)) * 128 B, 8-row groups 2048 B apart (one halo row)
+// The start address is 128-B but not 1024-B aligned.  MEASURED on B200: the UMMA applies the 128B-swizzle XOR to the
+// ABSOLUTE shared-memory address bits (same function TMA used when writing), so such a start needs NO descriptor
+// base-offset; filling the base-offset field with (start >> 7) & 7 produces wrong results (tests/test_kernels_gpu.py).
+// Weights are either RESIDENT in shared memory for the whole kernel (9 * Cin/64 * n_tile * 128 B <= 96 KB, e.g. the
+// 64->64 layers) or streamed through a 4-slot ring of (chunk, tap) slices.
+// Warp roles / TMEM double buffering / epilogue are those of conv_tc.cu.
+#include "common.cuh"
+#include "taps.cuh"
+#include <cuda.h>
+#include <string.h>
+#include "tc_ptx.cuh"
+
+namespace svrs {
+
+constexpr int HL_HALO_BYTES = 18 * 16 * 128;          // 36864
+constexpr int HL_HALO_SLOTS = 3;
+constexpr int HL_W_SLOT_BYTES = 128 * 128;            // one (chunk, tap) slice for n_tile <= 128
+constexpr int HL_W_SLOTS = 4;
+constexpr int HL_W_RESIDENT_MAX = 96 * 1024;
+constexpr int HL_THREADS = 192;
+// smem: halo ring | weights (resident region or ring) | barriers
+constexpr int HL_SMEM_BYTES = HL_HALO_SLOTS * HL_HALO_BYTES + HL_W_RESIDENT_MAX + 1024 + 256;
+
+struct alignas(64) HaloParams {
+    CUtensorMap in_map;     // (C, W, H, N) box (64, 16, 18, 1)
+    CUtensorMap w_map;      // (K, Nc, taps) box (64, n_tile, 1)
+    __nv_bfloat16* out;
+    const float* bias;
+    int N, OH, OW, tiles_x, tiles_y;
+    int Nc, n_tile, n_tiles, kchunks;
+    int act, resident, base_off_mode;
+    int hy[9], hx[9], wtap[9];      // tap -> halo offset (dy+1, dx+1) and packed-weight tap index
+};
+
+__device__ __forceinline__ uint64_t halo_desc(uint32_t saddr, int mode) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(2048 >> 4) << 32;                  // SBO: next 8-pixel group = next halo row
+    d |= (uint64_t)1 << 46;
+    if (mode) d |= (uint64_t)((saddr >> 7) & 7) << 49; // matrix base offset: phase of the 128B-swizzle pattern
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_constant__ HaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_base = smem_base + HL_HALO_SLOTS * HL_HALO_BYTES;
+    const uint32_t bar_base = w_base + HL_W_RESIDENT_MAX;
+    auto hfull = [&](int s) { return bar_base + 8u * s; };
+    auto hempty = [&](int s) { return bar_base + 8u * (HL_HALO_SLOTS + s); };
+    auto wfull = [&](int s) { return bar_base + 8u * (2 * HL_HALO_SLOTS + s); };
+    auto wempty = [&](int s) { return bar_base + 8u * (2 * HL_HALO_SLOTS + HL_W_SLOTS + s); };
+    auto tfull = [&](int s) { return bar_base + 8u * (2 * HL_HALO_SLOTS + 2 * HL_W_SLOTS + s); };
+    auto tempty = [&](int s) { return bar_base + 8u * (2 * HL_HALO_SLOTS + 2 * HL_W_SLOTS + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * HL_HALO_SLOTS + 2 * HL_W_SLOTS + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.in_map);
+        prefetch_tmap(&p.w_map);
+        for (int s = 0; s < HL_HALO_SLOTS; ++s) { mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); }
+        for (int s = 0; s < HL_W_SLOTS; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int tiles_pix = p.tiles_x * p.tiles_y * p.N;
+    const int total_tiles = tiles_pix * p.n_tiles;
+    const uint32_t w_slice = (uint32_t)p.n_tile * 128u;      // bytes of one (chunk, tap) weight slice
+
+    // tile order: n-tile outermost so that resident weights are loaded once per n-tile change
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t hs = 0, hph = 0, ws = 0, wph = 0, rel_ph = 0;
+            int cur_nt = -1;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile / tiles_pix;
+                int pt = tile % tiles_pix;
+                const int tx = pt % p.tiles_x; pt /= p.tiles_x;
+                const int ty = pt % p.tiles_y;
+                const int n = pt / p.tiles_y;
+                if (p.resident && nt != cur_nt) {
+                    // (re)load the whole weight set of this n-tile; a RE-load waits until the MMA warp's commit on
+                    // wempty(0) says every MMA that read the previous set has retired
+                    if (cur_nt >= 0) { mbar_wait(wempty(0), rel_ph); rel_ph ^= 1u; }
+                    mbar_expect_tx(wfull(0), (uint32_t)(9 * p.kchunks) * w_slice);
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        for (int t = 0; t < 9; ++t)
+                            tma_load_3d(w_base + (uint32_t)(kc * 9 + t) * w_slice, &p.w_map, wfull(0), kc * 64, nt * p.n_tile, p.wtap[t]);
+                    cur_nt = nt;
+                }
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(hempty(hs), hph ^ 1u);
+                    mbar_expect_tx(hfull(hs), (uint32_t)HL_HALO_BYTES);
+                    tma_load_4d(smem_base + hs * HL_HALO_BYTES, &p.in_map, hfull(hs), kc * 64, tx * 8 - 1, ty * 16 - 1, n);
+                    if (++hs == HL_HALO_SLOTS) { hs = 0; hph ^= 1u; }
+                    if (!p.resident) {
+                        for (int t = 0; t < 9; ++t) {
+                            mbar_wait(wempty(ws), wph ^ 1u);
+                            mbar_expect_tx(wfull(ws), w_slice);
+                            tma_load_3d(w_base + ws * HL_W_SLOT_BYTES, &p.w_map, wfull(ws), kc * 64, nt * p.n_tile, p.wtap[t]);
+                            if (++ws == HL_W_SLOTS) { ws = 0; wph ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+        uint32_t hs = 0, hph = 0, ws = 0, wph = 0, wres_ph = 0, acc = 0, acc_phase = 0;
+        int cur_nt = -1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile / tiles_pix;
+            if (p.resident && nt != cur_nt) {
+                if (cur_nt >= 0 && lane == 0) tc_commit(wempty(0));   // previous weight set is free once issued MMAs retire
+                __syncwarp();
+                mbar_wait(wfull(0), wres_ph);
+                tc_fence_after();
+                wres_ph ^= 1u;
+                cur_nt = nt;
+            }
+            mbar_wait(tempty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256u;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(hfull(hs), hph);
+                tc_fence_after();
+                const uint32_t sh = smem_base + hs * HL_HALO_BYTES;
+                for (int t = 0; t < 9; ++t) {
+                    uint32_t sw;
+                    if (p.resident) sw = w_base + (uint32_t)(kc * 9 + t) * w_slice;
+                    else {
+                        mbar_wait(wfull(ws), wph);
+                        tc_fence_after();
+                        sw = w_base + ws * HL_W_SLOT_BYTES;
+                    }
+                    if (lane == 0) {
+                        const uint64_t adesc = halo_desc(sh + (uint32_t)(p.hy[t] * 16 + p.hx[t]) * 128u, p.base_off_mode);
+                        const uint64_t bdesc = make_kmajor_desc(sw, 1024u, 2u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
+                        if (!p.resident) tc_commit(wempty(ws));
+                    }
+                    __syncwarp();
+                    if (!p.resident) { if (++ws == HL_W_SLOTS) { ws = 0; wph ^= 1u; } }
+                }
+                if (lane == 0) {
+                    tc_commit(hempty(hs));
+                    if (kc == p.kchunks - 1) tc_commit(tfull(acc));
+                }
+                __syncwarp();
+                if (++hs == HL_HALO_SLOTS) { hs = 0; hph ^= 1u; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else {
+        const int q = warp % 4;
+        const int r = q * 32 + lane;
+        const int ix = r % 8, iy = r / 8;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile / tiles_pix;
+            int pt = tile % tiles_pix;
+            const int tx = pt % p.tiles_x; pt /= p.tiles_x;
+            const int ty = pt % p.tiles_y;
+            const int n = pt / p.tiles_y;
+            const int c_base = nt * p.n_tile;
+            __nv_bfloat16* orow = p.out + (((long long)n * p.OH + ty * 16 + iy) * p.OW + tx * 8 + ix) * p.Nc + c_base;
+            mbar_wait(tfull(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                uint32_t v[32];
+                const int cols = (p.n_tile - c0 >= 32) ? 32 : 16;
+                if (cols == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const int c = c_base + c0 + j;
+                    if (j < cols && c < p.Nc) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float b = p.bias ? __ldg(p.bias + c + e) : 0.f;
+                            f[e] = apply_act(__uint_as_float(v[j + e]) + b, p.act);
+                        }
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+                        uint4 o;
+                        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+                        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(orow + c0 + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+static int g_halo_mode = 1;   // 0 = off, 1 = on (base-offset field 0), 2 = on WITH base-offset field (hardware experiment: wrong)
+void set_halo_mode(int m) { g_halo_mode = m; }
+int make_w_map_pub(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile, int cw);
+
+bool halo_supported(int form, int Cr, int Cw, int OW, int OH) {
+    return g_halo_mode != 0 && (form == 0 || form == 1) && Cr % 64 == 0 && Cw % 16 == 0 && Cw >= 16 && OW % 8 == 0 && OH % 16 == 0;
+}
+
+int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
+                      int act, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("conv3_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
+        attr_set = true;
+    }
+    HaloParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.bias = bias;
+    p.N = N; p.OH = H; p.OW = W; p.tiles_x = W / 8; p.tiles_y = H / 16;
+    p.Nc = Cw;
+    p.n_tile = Cw <= 128 ? Cw : 128;
+    p.n_tiles = (Cw + p.n_tile - 1) / p.n_tile;
+    p.kchunks = Cr / 64;
+    p.act = act;
+    p.resident = (9 * p.kchunks * p.n_tile * 128 <= HL_W_RESIDENT_MAX) ? 1 : 0;
+    p.base_off_mode = g_halo_mode == 2 ? 1 : 0;
+    for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+            int t = ky * 3 + kx;
+            int dy = form == 1 ? 1 - ky : ky - 1, dx = form == 1 ? 1 - kx : kx - 1;
+            p.hy[t] = dy + 1; p.hx[t] = dx + 1; p.wtap[t] = t;
+        }
+    // halo box: 16 pixels wide (x0-1 .. x0+14), 18 rows (y0-1 .. y0+16), one image
+    int rc = make_act_map(&p.in_map, in, Cr, W, H, N, Cr, (long long)W * Cr, (long long)H * W * Cr, 16, 18, 1, 64);
+    if (rc) return rc;
+    rc = make_w_map_pub(&p.w_map, w_nk, Cr, Cw, 9, p.n_tile, 64);
+    if (rc) return rc;
+    long long total = (long long)p.tiles_x * p.tiles_y * N * p.n_tiles;
+    int grid = (int)(total < num_sms() ? total : num_sms());
+    if (grid < 1) return 0;
+    conv3_halo_kernel<<<grid, HL_THREADS, HL_SMEM_BYTES, st>>>(p);
+    return check_launch("conv3_halo_kernel");
+}
+
+}  // namespace svrs

@@ -540,7 +540,9 @@ using namespace svrs;
 
 static bool dtype_ok(int d) { return d == SVRS_F32 || d == SVRS_BF16; }
 
+namespace svrs { void set_halo_mode(int m); }
 extern "C" void svrs_set_tc_enabled(int enabled) { svrs::g_tc_enabled = enabled; }
+extern "C" void svrs_set_halo_mode(int mode) { svrs::set_halo_mode(mode); }
 extern "C" int svrs_tc_would_run(int dtype, int K, int Nc, int OH, int OW) {
     return svrs::g_tc_enabled && svrs::tc_supported(dtype, K, Nc, OW, OH) ? 1 : 0;
 }

@@ -284,6 +284,13 @@ static int make_w_map(CUtensorMap* m, const void* base, int K, int Nc, int taps,
     return 0;
 }
 
+int make_w_map_pub(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile, int cw) {
+    return make_w_map(m, base, K, Nc, taps, n_tile, cw);
+}
+bool halo_supported(int form, int Cr, int Cw, int OW, int OH);
+int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
+                      int act, cudaStream_t st);
+
 bool pick_box(int OW, int OH, int& BW, int& BH, int& BNI) {
     BW = OW < 128 ? OW : 128;
     if (128 % BW || OW % BW) return false;
@@ -304,6 +311,7 @@ bool tc_supported(int dtype, int K, int Nc, int OW, int OH) {
 // in: tensor being read [N, H, W, Cr] ; out: tensor written ; w_nk: NK pack [tap][Cw][Cr]
 int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
                    int act, cudaStream_t st) {
+    if (halo_supported(form, Cr, Cw, W, H)) return launch_conv3_halo(form, in, w_nk, bias, out, N, H, W, Cr, Cw, act, st);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);

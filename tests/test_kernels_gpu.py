@@ -521,3 +521,43 @@ def test_pack_weights_multi_matches_single():
                 assert torch.equal(op.pack_f, pf) and torch.equal(op.pack_b, pb), (net.name, op.kind, op.cin, op.cout)
                 n += 1
         assert n == 16
+
+
+HALO_CASES = [(2, 16, 16, 64, 64), (1, 32, 32, 128, 128), (2, 16, 8, 64, 256), (1, 64, 64, 64, 16), (3, 16, 16, 128, 64),
+              (2, 32, 16, 256, 64)]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv3_halo_kernel(case):
+    """Halo-reuse kernel (one TMA load of the activation halo per tile, nine descriptor views) vs fp64 and vs the per-tap kernel."""
+    N, H, W, Cin, Cout = case
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(sum(case) + 7)
+    x = _rand((N, Cin, H, W), g, dtype)
+    w = (_rand((Cout, Cin, 3, 3), g, dtype) * 0.1).to(dtype).float()
+    b = torch.randn(Cout, generator=g)
+    xr = x.double().requires_grad_(True)
+    yr = F.conv2d(xr, w.double(), b.double(), stride=1, padding=1)
+    gy = _rand(tuple(yr.shape), g, dtype)
+    yr.backward(gy.double())
+    xd, wd, bd, gyd = nhwc(x.to(DEV), dtype), w.to(DEV), b.to(DEV), nhwc(gy.to(DEV), dtype)
+    pf, pb = pack(wd, dtype)
+    errs = {}
+    try:
+        for mode in (0, 1, 2):
+            lib.set_halo_mode(mode)
+            y = torch.full((N, H, W, Cout), float("nan"), device=DEV, dtype=dtype)
+            dx = torch.full_like(xd, float("nan"))
+            lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), pb.data_ptr(), bd.data_ptr(), y.data_ptr(), BF16, N, H, W, Cin, Cout, 3, 0, st())
+            lib.conv2d_dgrad(gyd.data_ptr(), pb.data_ptr(), pf.data_ptr(), dx.data_ptr(), BF16, N, H, W, Cin, Cout, 3, st())
+            torch.cuda.synchronize()
+            ef = float((nchw(y).double().cpu() - yr.detach()).abs().max() / yr.detach().abs().max())
+            ed = float((nchw(dx).double().cpu() - xr.grad).abs().max() / xr.grad.abs().max())
+            errs[mode] = (ef, ed)
+            print(f"[parity] conv3 halo mode {mode} {case}: fprop rel err {ef:.3e}, dgrad rel err {ed:.3e}")
+    finally:
+        lib.set_halo_mode(1)
+    assert max(errs[0]) < 1e-2, "per-tap kernel"
+    assert max(errs[1]) < 1e-2, f"halo kernel: {errs}"
+    # mode 2 (descriptor base-offset field = (start >> 7) & 7) is a hardware experiment: on B200 it is WRONG, i.e. the UMMA
+    # swizzle depends on absolute shared-memory address bits; reported, not asserted.
