@@ -26,7 +26,7 @@ constexpr int HL_HALO_SLOTS = 3;
 constexpr int HL_W_SLOT_BYTES = 128 * 128;            // one (chunk, tap) slice for n_tile <= 128
 constexpr int HL_W_SLOTS = 4;
 constexpr int HL_W_RESIDENT_MAX = 96 * 1024;
-constexpr int HL_THREADS = 192;
+constexpr int HL_THREADS = 64 + 32 * TC_EPI_WARPS;
 // smem: halo ring | weights (resident region or ring) | barriers
 constexpr int HL_SMEM_BYTES = HL_HALO_SLOTS * HL_HALO_BYTES + HL_W_RESIDENT_MAX + 1024 + 256;
 
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
         prefetch_tmap(&p.w_map);
         for (int s = 0; s < HL_HALO_SLOTS; ++s) { mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); }
         for (int s = 0; s < HL_W_SLOTS; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
         }
     } else {
         const int q = warp % 4;
+        const int half = (warp - 2) / 4;
         const int r = q * 32 + lane;
         const int ix = r % 8, iy = r / 8;
         uint32_t acc = 0, acc_phase = 0;
@@ -190,30 +191,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
             mbar_wait(tfull(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-                uint32_t v[32];
-                const int cols = (p.n_tile - c0 >= 32) ? 32 : 16;
-                if (cols == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    const int c = c_base + c0 + j;
-                    if (j < cols && c < p.Nc) {
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float b = p.bias ? __ldg(p.bias + c + e) : 0.f;
-                            f[e] = apply_act(__uint_as_float(v[j + e]) + b, p.act);
-                        }
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-                        uint4 o;
-                        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-                        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(orow + c0 + j) = o;
-                    }
-                }
-            }
+            epi_dispatch(p.act, taddr, p.n_tile, half, orow, p.bias, c_base, p.Nc, true);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(acc));

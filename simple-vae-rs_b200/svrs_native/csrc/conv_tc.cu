@@ -32,7 +32,7 @@ constexpr int TC_A_BYTES = 128 * 128;        // 128 pixels x 64 bf16 (or 64/cw p
 constexpr int TC_B_BYTES = 256 * 128;        // up to 256 output channels x 64 bf16
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + 8 epilogue warps
 
 struct TcTap {
     int map;    // which input tensor map (parity class)
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int i = 0; i < 4; ++i) prefetch_tmap(&p.in_maps[i]);
         prefetch_tmap(&p.w_map);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -162,11 +162,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
-        // ================================ epilogue (4 warps) ================================
+        // ================================ epilogue (8 warps) ================================
         const int q = warp % 4;                         // TMEM lane quarter this warp may access
+        const int half = (warp - 2) / 4;                // which half of the tile's column chunks
         const int r = q * 32 + lane;                    // accumulator row == pixel within the tile
         const int ix = r % p.BW, iy = (r / p.BW) % p.BH, in = r / (p.BW * p.BH);
-        const bool vec_ok = (p.Nc % 8 == 0);
         uint32_t acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int pr = tile / tiles_per_prob;
@@ -180,42 +180,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int c_base = nt * p.n_tile;
             __nv_bfloat16* orow = p.out + p.prob[pr].out_off + (long long)n * p.o_sn +
                                   (long long)(ty * p.BH + iy) * p.o_sy + (long long)(tx * p.BW + ix) * p.o_sx + c_base;
-            const bool row_ok = n < p.N;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-                uint32_t v[32];
-                const int cols = (p.n_tile - c0 >= 32) ? 32 : 16;
-                if (cols == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
-                tmem_ld_wait();
-                if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const int c = c_base + c0 + j;
-                        if (j < cols && c < p.Nc) {
-                            float f[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                float b = (p.bias && c + e < p.Nc) ? __ldg(p.bias + c + e) : 0.f;
-                                f[e] = apply_act(__uint_as_float(v[j + e]) + b, p.act);
-                            }
-                            if (vec_ok) {
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-                                uint4 o;
-                                o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-                                o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-                                *reinterpret_cast<uint4*>(orow + c0 + j) = o;
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 8; ++e)
-                                    if (c + e < p.Nc) orow[c0 + j + e] = __float2bfloat16_rn(f[e]);
-                            }
-                        }
-                    }
-                }
-            }
+            epi_dispatch(p.act, taddr, p.n_tile, half, orow, p.bias, c_base, p.Nc, n < p.N);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));

@@ -106,6 +106,71 @@ __device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr, uint32_t lbo, u
     return d;
 }
 
+// ------------------------------------------------------------------------------------------ shared conv epilogue
+// 8 epilogue warps: warp e = (lane quarter q = e % 4, column half = e / 4).  Each thread owns ONE accumulator row (pixel)
+// and walks its half of the tile's 32-column chunks: tcgen05.ld -> (+bias) -> (activation) -> bf16 -> 16-byte stores.
+// Specialised at compile time on (activation, bias) so the inner loop carries no per-element branches.
+constexpr int TC_EPI_WARPS = 8;
+
+template <int ACT, bool BIAS>
+__device__ __forceinline__ void epi_chunk8(const uint32_t* v, __nv_bfloat16* dst, const float* bias, int c, int Nc, bool vec_ok) {
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        float x = __uint_as_float(v[e]);
+        if (BIAS) x += (c + e < Nc) ? __ldg(bias + c + e) : 0.f;
+        if (ACT == SVRS_ACT_SIGMOID) x = 1.0f / (1.0f + __expf(-x));
+        else if (ACT == SVRS_ACT_HARDTANH7) x = fminf(fmaxf(x, -7.0f), 7.0f);
+        f[e] = x;
+    }
+    if (vec_ok) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst) = o;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (c + e < Nc) dst[e] = __float2bfloat16_rn(f[e]);
+    }
+}
+
+// taddr: TMEM address of (this warp's lane quarter, accumulator column 0); orow: output row pointer at channel c_base
+template <int ACT, bool BIAS>
+__device__ __forceinline__ void epi_rows(uint32_t taddr, int n_tile, int half, __nv_bfloat16* orow, const float* bias,
+                                         int c_base, int Nc, bool row_ok) {
+    const bool vec_ok = (Nc % 8 == 0);
+    const int chunks = (n_tile + 31) / 32;
+    const int cbeg = half == 0 ? 0 : (chunks + 1) / 2, cend = half == 0 ? (chunks + 1) / 2 : chunks;
+    for (int ch = cbeg; ch < cend; ++ch) {
+        const int c0 = ch * 32;
+        uint32_t v[32];
+        const int cols = (n_tile - c0 >= 32) ? 32 : 16;
+        if (cols == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const int c = c_base + c0 + j;
+                if (j < cols && c < Nc) epi_chunk8<ACT, BIAS>(v + j, orow + c0 + j, bias, c, Nc, vec_ok);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void epi_dispatch(int act, uint32_t taddr, int n_tile, int half, __nv_bfloat16* orow, const float* bias,
+                                             int c_base, int Nc, bool row_ok) {
+    if (bias) {
+        if (act == SVRS_ACT_SIGMOID) epi_rows<SVRS_ACT_SIGMOID, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok);
+        else if (act == SVRS_ACT_HARDTANH7) epi_rows<SVRS_ACT_HARDTANH7, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok);
+        else epi_rows<SVRS_ACT_NONE, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok);
+    } else {
+        epi_rows<SVRS_ACT_NONE, false>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok);
+    }
+}
+
 // host helpers (conv_tc.cu)
 int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sx, long long sy, long long sn,
                  int BW, int BH, int BNI, int cw);

@@ -63,6 +63,7 @@ class _Lib:
         self._dll = None
         self.protos = parse_header()
         self.timing = None      # when a list: every call is bracketed by CUDA events (svrs_native.profile)
+        self.timing_pad_cycles = 0
 
     def load(self):
         if self._dll is not None:
@@ -96,6 +97,10 @@ class _Lib:
             if self.timing is not None:
                 import torch
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                if self.timing_pad_cycles:
+                    # a short device-side spin ahead of the bracket hides the host launch latency of the timed kernel,
+                    # so e0 -> e1 is pure device time even for microsecond kernels
+                    torch.cuda._sleep(self.timing_pad_cycles)
                 e0.record()
                 rc = _fn(*a)
                 e1.record()

@@ -32,6 +32,7 @@ for _ in range(2):
     tr.step(x, y)
 torch.cuda.synchronize()
 lib.timing = []
+lib.timing_pad_cycles = int(os.environ.get("SVRS_PAD_CYCLES", "150000"))
 steps = 3
 for _ in range(steps):
     tr.step(x, y)
@@ -64,7 +65,7 @@ for k, (ms, n) in sorted(byfn.items(), key=lambda kv: -kv[1][0]):
     print(f"{ms:8.3f} ms {100 * ms / tot:5.1f}%  x{n // steps:<3d} {k}")
 
 # ---- pure GPU time per launch: re-issue every recorded call 8x inside a captured CUDA graph (no host gaps)
-if os.environ.get("SVRS_REPLAY", "1") == "1":
+if os.environ.get("SVRS_REPLAY", "0") == "1":
     first = [r for r in rec[: len(rec) // steps]]
     keep = [x, y, tr]          # keep buffers alive; stale activations stay mapped in the caching allocator
     reps = 8
