@@ -63,6 +63,8 @@ int svrs_pack_weights(const float* w, int d0, int d1, int kk, void* p01, void* p
  * the tile counts of the preceding jobs; total_tiles = sum of all tile counts; max_kk = largest kk (<= 16). */
 int svrs_pack_job_bytes(void);
 int svrs_pack_weights_multi(const void* jobs, int njobs, int total_tiles, int max_kk, int dtype, void* stream);
+/* inverse direction for gradients: same job records with w = torch-layout fp32 gradient (+=) and p01 = packed fp32 scratch */
+int svrs_unpack_grads_multi(const void* jobs, int njobs, int total_tiles, int max_kk, void* stream);
 
 /* Two kernels sit behind each fprop/dgrad entry point:
  *   - conv_tc   (csrc/conv_tc.cu): tcgen05.mma + TMEM accumulators + TMA-fed SWIZZLE_128B operands; taken when
@@ -89,9 +91,13 @@ int svrs_conv2d_fprop(const void* x, const void* w_kn, const void* w_nk, const f
  * (autograd of the same call sites, reached through loss.backward() models/base.py:105) */
 int svrs_conv2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
                       int N, int H, int W, int Cin, int Cout, int ksize, void* stream);
-/* wgrad: dw[Cout][Cin][k][k] += sum x (*) dy  (fp32, torch layout, ATOMIC accumulate - zero it first);
+/* dw_packed (may be NULL): a zeroed fp32 scratch of the weight's size.  When given, the tcgen05 kernels accumulate
+ * there in the per-tap layout [tap][d0][d1] (d0, d1 = the weight's first two torch dims), which turns their atomics into
+ * fully coalesced 128-byte reductions; svrs_unpack_grads_multi() later adds every layer's scratch into the torch-layout
+ * gradient in one launch.  The SIMT kernels always accumulate into dw directly.
+ * wgrad: dw[Cout][Cin][k][k] += sum x (*) dy  (fp32, torch layout, ATOMIC accumulate - zero it first);
  * db[Cout] += column sums of dy when db != NULL.  `ksplit` <= 0 picks a split automatically. */
-int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float* db, int dtype,
+int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float* dw_packed, float* db, int dtype,
                       int N, int H, int W, int Cin, int Cout, int ksize, int ksplit, void* stream);
 
 /* ---- nn.ConvTranspose2d k4 s2 p1 (layers.py:275-277): x [N,H,W,Cin] -> y [N,2H,2W,Cout].
@@ -102,7 +108,7 @@ int svrs_convT2d_fprop(const void* x, const void* w_kn, const void* w_nk, const 
 int svrs_convT2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
                        int N, int H, int W, int Cin, int Cout, void* stream);
 /* wgrad: dw[Cin][Cout][4][4] += ... ; db[Cout] += column sums of dy. */
-int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, float* db, int dtype,
+int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, float* dw_packed, float* db, int dtype,
                        int N, int H, int W, int Cin, int Cout, int ksplit, void* stream);
 
 /* ---- nn.BatchNorm2d (+ nn.ReLU) of down_block / up_block (layers.py:237-238,252-255,278-279,293-296)

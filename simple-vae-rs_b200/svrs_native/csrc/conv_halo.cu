@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
 
 static int g_halo_mode = 1;   // 0 = off, 1 = on (base-offset field 0), 2 = on WITH base-offset field (hardware experiment: wrong)
 void set_halo_mode(int m) { g_halo_mode = m; }
+int get_halo_mode() { return g_halo_mode; }
 int make_w_map_pub(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile, int cw);
 
 bool halo_supported(int form, int Cr, int Cw, int OW, int OH) {

@@ -280,6 +280,42 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackJob* __restri
 }
 }  // namespace svrs
 
+namespace svrs {
+// gradients: packed fp32 scratch [tap][d0][d1] -> torch layout [d0][d1][tap] (+=), same tiling as pack_multi_kernel
+__global__ void __launch_bounds__(256) unpack_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    extern __shared__ float tile[];
+    int j = 0;
+    while (j + 1 < njobs && jobs[j + 1].tile0 <= (int)blockIdx.x) ++j;
+    const PackJob jb = jobs[j];
+    const int lt = blockIdx.x - jb.tile0;
+    const int a0 = (lt / jb.tiles_b) * PK_TA, b0 = (lt % jb.tiles_b) * PK_TB;
+    const int kk = jb.kk, d0 = jb.d0, d1 = jb.d1;
+    const int na = d0 - a0 < PK_TA ? d0 - a0 : PK_TA, nb = d1 - b0 < PK_TB ? d1 - b0 : PK_TB;
+    const int ROW = PK_TB * (kk + 1) + 1;
+    const float* src = reinterpret_cast<const float*>(jb.p01);
+    float* dst = const_cast<float*>(jb.w);
+    const int total = kk * na * nb;
+    for (int idx = threadIdx.x; idx < total; idx += 256) {       // read packed: b fastest (contiguous runs of nb)
+        int b = idx % nb, a = (idx / nb) % na, t = idx / (nb * na);
+        tile[a * ROW + b * (kk + 1) + t] = src[((long long)t * d0 + a0 + a) * d1 + b0 + b];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int run = nb * kk;
+    for (int a = warp; a < na; a += 8) {                          // write torch layout: contiguous runs of nb*kk
+        float* d = dst + ((long long)(a0 + a) * d1 + b0) * kk;
+        for (int i = lane; i < run; i += 32) d[i] += tile[a * ROW + (i / kk) * (kk + 1) + (i % kk)];
+    }
+}
+}  // namespace svrs
+
+extern "C" int svrs_unpack_grads_multi(const void* jobs, int njobs, int total_tiles, int max_kk, void* stream) {
+    SVRS_CHECK_ARG(jobs && njobs > 0 && total_tiles > 0 && max_kk > 0 && max_kk <= 16, "unpack_grads_multi: bad args");
+    size_t smem = (size_t)svrs::PK_TA * (svrs::PK_TB * (max_kk + 1) + 1) * sizeof(float);
+    svrs::unpack_multi_kernel<<<total_tiles, 256, smem, (cudaStream_t)stream>>>((const svrs::PackJob*)jobs, njobs);
+    return check_launch("unpack_grads_multi");
+}
+
 extern "C" int svrs_pack_job_bytes(void) { return (int)sizeof(svrs::PackJob); }
 
 extern "C" int svrs_pack_weights_multi(const void* jobs, int njobs, int total_tiles, int max_kk, int dtype, void* stream) {

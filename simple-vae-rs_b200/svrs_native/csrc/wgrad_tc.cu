@@ -40,7 +40,7 @@ struct alignas(64) WgParams {
     int bpb;                           // boxes per M-block = 128 / cwx
     int nboxes, nblocks, group, ngroups;
     int ksplit, ksteps_total;
-    int ntaps;
+    int ntaps, packed;
     WgTap taps[16];
 };
 
@@ -164,7 +164,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int ca = nt * p.n_tile + c0 + j;
-                        if (j < cols && ca < p.Ca) atomicAdd(p.dw + ((long long)ca * p.Cb + cb) * p.KK + tapid, __uint_as_float(v[j]));
+                        if (j < cols && ca < p.Ca) {
+                            // packed scratch [tap][a][b]: a warp's 32 lanes (consecutive b) hit one 128-byte line
+                            float* dst = p.packed ? p.dw + ((long long)tapid * p.Ca + ca) * p.Cb + cb
+                                                  : p.dw + ((long long)ca * p.Cb + cb) * p.KK + tapid;
+                            atomicAdd(dst, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
@@ -188,7 +193,7 @@ bool wgrad_tc_supported(int dtype, int Ca, int Cb, int OW, int OH) {
 
 // g: geometry of the forward-form conv whose output grid carries `gmat` (channels Ca = g.Nc) and whose input view
 // carries `x` (channels Cb = g.K);  dw torch layout [(a*Cb + b)*KK + tap]
-int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int KK, cudaStream_t st) {
+int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, int KK, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
@@ -199,6 +204,7 @@ int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw
     memset(&p, 0, sizeof(p));
     if (!pick_box(g.OW, g.OH, p.BW, p.BH, p.BNI)) { set_error("wgrad_tc: unsupported spatial dims"); return SVRS_E_UNSUPPORTED; }
     p.dw = dw;
+    p.packed = packed;
     p.N = g.N; p.OH = g.OH; p.OW = g.OW;
     p.tiles_x = g.OW / p.BW; p.tiles_y = g.OH / p.BH; p.tiles_n = (g.N + p.BNI - 1) / p.BNI;
     p.Ca = g.Nc; p.Cb = g.K; p.KK = KK;

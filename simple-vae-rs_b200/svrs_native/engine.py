@@ -67,6 +67,7 @@ class ParamStore:
         self.total = off
         self.flat: Optional[torch.Tensor] = None
         self.grad: Optional[torch.Tensor] = None
+        self.gpack: Optional[torch.Tensor] = None
         self._index = {id(p): i for i, p in enumerate(self.params)}
 
     def valid(self) -> bool:
@@ -92,6 +93,7 @@ class ParamStore:
                 p.data = v
         self.flat = flat
         self.grad = torch.zeros_like(flat)
+        self.gpack = torch.zeros_like(flat)     # per-tap packed scratch for the tensor-core wgrad kernels
         return True
 
     def grad_view(self, p: nn.Parameter) -> torch.Tensor:
@@ -101,6 +103,9 @@ class ParamStore:
 
     def grad_ptr(self, p: nn.Parameter) -> int:
         return self.grad.data_ptr() + 4 * self.offsets[self._index[id(p)]]
+
+    def gpack_ptr(self, p: nn.Parameter) -> int:
+        return self.gpack.data_ptr() + 4 * self.offsets[self._index[id(p)]]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,6 +206,8 @@ class Runtime:
         self._scratch: Optional[torch.Tensor] = None
         self._pack_jobs: Optional[torch.Tensor] = None
         self._pack_key = None
+        self._unpack_jobs: Optional[torch.Tensor] = None
+        self._unpack_key = None
         self.packs_dirty = True
         self.launches = 0          # kernels enqueued (our own), for bench.py's gpu_launches
 
@@ -249,6 +256,29 @@ class Runtime:
 
     def zero_grads(self):
         lib.fill_zero(_p(self.store.grad), self.store.grad.numel() * 4, _st())
+        lib.fill_zero(_p(self.store.gpack), self.store.gpack.numel() * 4, _st())
+        self.launches += 2
+
+    def finish_grads(self):
+        """Add the per-tap packed weight-gradient scratch of every conv layer into the torch-layout flat gradient
+        (one launch).  Must run after the last net_backward of a step and before anything reads store.grad."""
+        if self._unpack_jobs is None or self._unpack_key != (self.store.grad.data_ptr(), self.store.gpack.data_ptr()):
+            import numpy as np
+            convs = [op for net in self.nets for op in net.ops if isinstance(op, ConvOp)]
+            rec = np.dtype([("w", "<u8"), ("p01", "<u8"), ("p10", "<u8"), ("d0", "<i4"), ("d1", "<i4"), ("kk", "<i4"),
+                            ("tile0", "<i4"), ("tiles_b", "<i4"), ("pad", "<i4")])
+            jobs = np.zeros(len(convs), dtype=rec)
+            tile0 = 0
+            for i, op in enumerate(convs):
+                w = op.mod.weight
+                d0, d1 = w.shape[0], w.shape[1]
+                tiles_b = (d1 + 15) // 16
+                jobs[i] = (self.store.grad_ptr(w), self.store.gpack_ptr(w), 0, d0, d1, op.kk, tile0, tiles_b, 0)
+                tile0 += ((d0 + 31) // 32) * tiles_b
+            self._unpack_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).to(self.device)
+            self._unpack_tiles, self._unpack_n = tile0, len(convs)
+            self._unpack_key = (self.store.grad.data_ptr(), self.store.gpack.data_ptr())
+        lib.unpack_grads_multi(_p(self._unpack_jobs), self._unpack_n, self._unpack_tiles, 16, _st())
         self.launches += 1
 
     def pack_weights(self, force: bool = False):
@@ -382,11 +412,12 @@ class Runtime:
                     lib.act_bwd(_p(yact), _p(dy), _p(dy), self.dt, op.act, dy.numel(), st)
                     self.launches += 1
                 dw = store.grad_ptr(op.mod.weight)
+                dwp = store.gpack_ptr(op.mod.weight)
                 db = store.grad_ptr(op.mod.bias) if op.mod.bias is not None else None
                 if op.kind == "ct":
-                    lib.convT2d_wgrad(_p(x), _p(dy), dw, db, self.dt, n, h, w, op.cin, op.cout, 0, st)
+                    lib.convT2d_wgrad(_p(x), _p(dy), dw, dwp, db, self.dt, n, h, w, op.cin, op.cout, 0, st)
                 else:
-                    lib.conv2d_wgrad(_p(x), _p(dy), dw, db, self.dt, n, h, w, op.cin, op.cout,
+                    lib.conv2d_wgrad(_p(x), _p(dy), dw, dwp, db, self.dt, n, h, w, op.cin, op.cout,
                                      3 if op.kind == "c3" else 4, 0, st)
                 self.launches += 2
                 if idx > 0 or need_dx:
@@ -632,6 +663,7 @@ class CondEngine:
                 reparam_bwd(rt, ctx["enc_u"], ctx["eps_u"], d_u, Wu, d_enc_u, B, Wu, rng, 0)
             g = rt.to_nhwc(d_enc_u, 2 * Wu, B, 2 * self.cu, h8, h8)
             rt.net_backward(N["encoder_y"], ctx["t_ey"], g, False)
+        rt.finish_grads()
 
     # ---- inference: Cond_SRVAE.sample (cond_vae.py:299-318) ---------------------------------------
     def sample(self, y: torch.Tensor, samples: int, eps_u=None, eps_s=None, training: bool = False):
@@ -750,3 +782,4 @@ class VaeEngine:
                 reparam_bwd(rt, ctx["enc"], ctx["eps"], d_z, Wd, d_enc, B, Wd, ctx["rng"], 0)
             g = rt.to_nhwc(d_enc, 2 * Wd, B, 2 * self.c, P // 4, P // 4)
             rt.net_backward(self.nets["encoder"], ctx["t_e"], g, False)
+        rt.finish_grads()

@@ -176,7 +176,6 @@ class FusedCondTrainer(_FusedBase):
         Wz, Wu = eng.Wz, eng.Wu
         lib.step_increment(_p(self.step_ptr), st)
         rt.zero_grads()
-        rt.launches += 1
         outs, ctx = eng.forward(x, y, eps_u, eps_z, training=True, save=True, repack=False)
         enc_u, enc_z = outs["enc_u"], outs["enc_z"]
         x_hat, y_hat, mu3, lv3 = outs["x_hat"], outs["y_hat"], outs["mu3"], outs["lv3"]
@@ -215,7 +214,6 @@ class FusedVaeTrainer(_FusedBase):
         B, Wd = x.shape[0], eng.Wd
         lib.step_increment(_p(self.step_ptr), st)
         rt.zero_grads()
-        rt.launches += 1
         outs, ctx = eng.forward(x, eps, training=True, save=True, repack=False)
         enc, x_hat = outs["enc"], outs["x_hat"]
         xf = x.contiguous().float()

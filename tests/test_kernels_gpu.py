@@ -64,7 +64,7 @@ def test_conv2d_fprop_dgrad_wgrad(case, ksize, dtype):
 
     dw = torch.zeros_like(wd)
     db = torch.zeros_like(bd)
-    lib.conv2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), db.data_ptr(), dt(dtype), N, H, W, Cin, Cout, ksize, 0, st())
+    lib.conv2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), None, db.data_ptr(), dt(dtype), N, H, W, Cin, Cout, ksize, 0, st())
     report(f"conv{ksize} wgrad {case} {dtype}", dw, wr.grad, 2e-5 if dtype == torch.float32 else 1e-5)
     report(f"conv{ksize} bgrad {case} {dtype}", db, br.grad, 2e-5 if dtype == torch.float32 else 1e-5)
 
@@ -91,7 +91,7 @@ def test_convT2d_fprop_dgrad_wgrad(case, dtype):
     lib.convT2d_dgrad(gyd.data_ptr(), pb.data_ptr(), pf.data_ptr(), dx.data_ptr(), dt(dtype), N, H, W, Cin, Cout, st())
     report(f"convT dgrad {case} {dtype}", nchw(dx), xr.grad, TOL[dtype])
     dw, db = torch.zeros_like(wd), torch.zeros_like(bd)
-    lib.convT2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), db.data_ptr(), dt(dtype), N, H, W, Cin, Cout, 0, st())
+    lib.convT2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), None, db.data_ptr(), dt(dtype), N, H, W, Cin, Cout, 0, st())
     report(f"convT wgrad {case} {dtype}", dw, wr.grad, 2e-5 if dtype == torch.float32 else 1e-5)
     report(f"convT bgrad {case} {dtype}", db, br.grad, 2e-5 if dtype == torch.float32 else 1e-5)
 
@@ -464,7 +464,8 @@ def test_conv_tc_all_forms(case):
 
 @pytest.mark.parametrize("case", [(2, 8, 8, 64, 64), (3, 16, 16, 128, 64), (2, 4, 4, 256, 512), (2, 32, 32, 128, 128),
                                   (5, 8, 8, 64, 192), (2, 16, 16, 16, 16), (2, 32, 32, 64, 16), (2, 8, 8, 32, 128),
-                                  (3, 8, 8, 48, 32), (2, 16, 16, 16, 64)])
+                                  (3, 8, 8, 48, 32), (2, 16, 16, 16, 64), (1, 64, 64, 64, 64), (3, 16, 8, 128, 64),
+                                  (2, 32, 16, 64, 256)])
 def test_wgrad_tc_all_forms(case):
     """tcgen05 weight-gradient kernel (MN-major operands, split-K over pixels) vs float64 torch autograd."""
     N, H, W, Cin, Cout = case
@@ -491,9 +492,9 @@ def test_wgrad_tc_all_forms(case):
             dw = torch.zeros(w.shape, device=DEV)
             db = torch.zeros(Cout, device=DEV)
             if form == "ct":
-                lib.convT2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), db.data_ptr(), BF16, N, H, W, Cin, Cout, 0, st())
+                lib.convT2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), None, db.data_ptr(), BF16, N, H, W, Cin, Cout, 0, st())
             else:
-                lib.conv2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), db.data_ptr(), BF16, N, H, W, Cin, Cout, ks, 0, st())
+                lib.conv2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), None, db.data_ptr(), BF16, N, H, W, Cin, Cout, ks, 0, st())
             torch.cuda.synchronize()
             res[tc] = dw
         lib.set_tc_enabled(1)
@@ -561,3 +562,40 @@ def test_conv3_halo_kernel(case):
     assert max(errs[1]) < 1e-2, f"halo kernel: {errs}"
     # mode 2 (descriptor base-offset field = (start >> 7) & 7) is a hardware experiment: on B200 it is WRONG, i.e. the UMMA
     # swizzle depends on absolute shared-memory address bits; reported, not asserted.
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 64, "c3"), (2, 8, 8, 64, 128, "c4"), (3, 8, 8, 128, 64, "ct"), (2, 16, 16, 16, 32, "c3")])
+def test_wgrad_packed_scratch_and_unpack(case):
+    """tcgen05 wgrad into the per-tap packed scratch + one-launch unpack == wgrad straight into the torch layout."""
+    import numpy as np
+    N, H, W, Cin, Cout, form = case
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(sum(case[:5]))
+    x = nhwc(_rand((N, Cin, H, W), g, dtype).to(DEV), dtype)
+    ks = 3 if form == "c3" else 4
+    if form == "ct":
+        wshape, gyshape = (Cin, Cout, 4, 4), (N, 2 * H, 2 * W, Cout)
+    else:
+        s = 1 if form == "c3" else 2
+        wshape, gyshape = (Cout, Cin, ks, ks), (N, H // s, W // s, Cout)
+    gy = torch.randn(gyshape, generator=g).to(DEV).to(dtype)
+    ref = torch.zeros(wshape, device=DEV)
+    out = torch.zeros(wshape, device=DEV)
+    scratch = torch.zeros(wshape, device=DEV)
+    if form == "ct":
+        lib.convT2d_wgrad(x.data_ptr(), gy.data_ptr(), ref.data_ptr(), None, None, BF16, N, H, W, Cin, Cout, 0, st())
+        lib.convT2d_wgrad(x.data_ptr(), gy.data_ptr(), out.data_ptr(), scratch.data_ptr(), None, BF16, N, H, W, Cin, Cout, 0, st())
+    else:
+        lib.conv2d_wgrad(x.data_ptr(), gy.data_ptr(), ref.data_ptr(), None, None, BF16, N, H, W, Cin, Cout, ks, 0, st())
+        lib.conv2d_wgrad(x.data_ptr(), gy.data_ptr(), out.data_ptr(), scratch.data_ptr(), None, BF16, N, H, W, Cin, Cout, ks, 0, st())
+    rec = np.dtype([("w", "<u8"), ("p01", "<u8"), ("p10", "<u8"), ("d0", "<i4"), ("d1", "<i4"), ("kk", "<i4"),
+                    ("tile0", "<i4"), ("tiles_b", "<i4"), ("pad", "<i4")])
+    assert rec.itemsize == lib.pack_job_bytes()
+    d0, d1, kk = wshape[0], wshape[1], wshape[2] * wshape[3]
+    jobs = np.zeros(1, dtype=rec)
+    jobs[0] = (out.data_ptr(), scratch.data_ptr(), 0, d0, d1, kk, 0, (d1 + 15) // 16, 0)
+    jd = torch.from_numpy(jobs.view(np.uint8).copy()).to(DEV)
+    lib.unpack_grads_multi(jd.data_ptr(), 1, ((d0 + 31) // 32) * ((d1 + 15) // 16), 16, st())
+    torch.cuda.synchronize()
+    assert float(scratch.abs().max()) > 0, "tensor-core wgrad did not use the packed scratch"
+    report(f"packed wgrad + unpack {case}", out, ref, 2e-5)

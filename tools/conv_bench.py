@@ -25,6 +25,7 @@ pf, pb = pack(w, torch.bfloat16)
 y = torch.empty_like(gy)
 dx = torch.empty_like(x)
 dw = torch.zeros_like(w)
+dwp = dw.data_ptr() if os.environ.get('PACKED', '1') == '1' else None   # packed scratch (timing only)
 flops = 2.0 * N * (H // s) * (W // s) * Cin * Cout * ks * ks
 
 
@@ -49,5 +50,8 @@ for halo in ((1, 0) if ks == 3 else (1,)):
         timeit(lambda: lib.conv2d_fprop(x.data_ptr(), pf.data_ptr(), pb.data_ptr(), b.data_ptr(), y.data_ptr(), BF16, N, H, W, Cin, Cout, ks, 0, st()), f"fprop {tag}")
     if only in ("", "dgrad"):
         timeit(lambda: lib.conv2d_dgrad(gy.data_ptr(), pb.data_ptr(), pf.data_ptr(), dx.data_ptr(), BF16, N, H, W, Cin, Cout, ks, st()), f"dgrad {tag}")
-if only in ("", "wgrad"):
-    timeit(lambda: lib.conv2d_wgrad(x.data_ptr(), gy.data_ptr(), dw.data_ptr(), None, BF16, N, H, W, Cin, Cout, ks, 0, st()), "wgrad")
+for halo in ((1, 0) if ks == 3 else (1,)):
+    lib.set_halo_mode(halo)
+    if only in ("", "wgrad"):
+        timeit(lambda: lib.conv2d_wgrad(x.data_ptr(), gy.data_ptr(), dw.data_ptr(), dwp, None, BF16, N, H, W, Cin, Cout, ks, 0, st()), f"wgrad halo={halo}")
+lib.set_halo_mode(1)
