@@ -166,10 +166,80 @@ __global__ void __launch_bounds__(256) conv_taps_kernel(const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Narrow layers (reduction and output channels both in {4, 16}: the first and last convs of every sub-network at full
+// resolution).  They are HBM-bound streaming ops (a few hundred FLOP per pixel), so the GEMM tiling above only adds
+// barriers: here one thread owns one output pixel, the per-tap weights sit in shared memory (broadcast float4 reads) and
+// the taps are a register loop.  No barriers after the weight stage-in.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CR, int CW>
+__global__ void __launch_bounds__(256) conv_pixel_kernel(const __grid_constant__ ConvArgs a) {
+    __shared__ __align__(16) float ws[16 * CR * CW];
+    const TapGeom& g = a.g;
+    const Prob& pb = g.prob[blockIdx.z];
+    const T* __restrict__ in = reinterpret_cast<const T*>(a.in);
+    const T* __restrict__ w = reinterpret_cast<const T*>(a.w);
+    T* __restrict__ out = reinterpret_cast<T*>(a.out) + pb.out_off;
+    for (int i = threadIdx.x; i < pb.ntaps * CR * CW; i += 256)
+        ws[i] = Cvt<T>::to_f(w[pb.taps[i / (CR * CW)].w_off + i % (CR * CW)]);
+    __syncthreads();
+    const long long M = (long long)g.N * g.OH * g.OW;
+    const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (m >= M) return;
+    const int n = (int)(m / ((long long)g.OH * g.OW));
+    const int r = (int)(m % ((long long)g.OH * g.OW));
+    const int oy = r / g.OW, ox = r % g.OW;
+    float acc[CW];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) acc[c] = a.bias ? a.bias[c] : 0.f;
+    const T* base = in + (long long)n * g.i_sn;
+    for (int t = 0; t < pb.ntaps; ++t) {
+        const Tap tp = pb.taps[t];
+        const int iy = oy + tp.dy, ix = ox + tp.dx;
+        if (iy < 0 || iy >= g.IH || ix < 0 || ix >= g.IW) continue;
+        const T* px = base + tp.in_off + (long long)iy * g.i_sy + (long long)ix * g.i_sx;
+        float xv[CR];
+#pragma unroll
+        for (int k = 0; k < CR; k += 4) {
+            float4 v = ld4(px + k);
+            xv[k] = v.x; xv[k + 1] = v.y; xv[k + 2] = v.z; xv[k + 3] = v.w;
+        }
+        const float* wt = ws + t * CR * CW;
+#pragma unroll
+        for (int k = 0; k < CR; ++k)
+#pragma unroll
+            for (int c = 0; c < CW; c += 4) {
+                float4 wv = *reinterpret_cast<const float4*>(wt + k * CW + c);
+                acc[c] = fmaf(xv[k], wv.x, acc[c]); acc[c + 1] = fmaf(xv[k], wv.y, acc[c + 1]);
+                acc[c + 2] = fmaf(xv[k], wv.z, acc[c + 2]); acc[c + 3] = fmaf(xv[k], wv.w, acc[c + 3]);
+            }
+    }
+    T* po = out + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx;
+#pragma unroll
+    for (int c = 0; c < CW; c += 4)
+        st4(po + c, make_float4(apply_act(acc[c], a.act), apply_act(acc[c + 1], a.act), apply_act(acc[c + 2], a.act),
+                                apply_act(acc[c + 3], a.act)));
+}
+
+template <typename T>
+static void launch_pixel(const ConvArgs& a, dim3 grid, cudaStream_t st) {
+    const int K = a.g.K, Nc = a.g.Nc;
+    if (K == 4 && Nc == 4) conv_pixel_kernel<T, 4, 4><<<grid, 256, 0, st>>>(a);
+    else if (K == 4 && Nc == 16) conv_pixel_kernel<T, 4, 16><<<grid, 256, 0, st>>>(a);
+    else if (K == 16 && Nc == 4) conv_pixel_kernel<T, 16, 4><<<grid, 256, 0, st>>>(a);
+    else conv_pixel_kernel<T, 16, 16><<<grid, 256, 0, st>>>(a);
+}
+
 static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
     const TapGeom& g = a.g;
     long long M = (long long)g.N * g.OH * g.OW;
     if (M == 0) return 0;
+    if ((g.K == 4 || g.K == 16) && (g.Nc == 4 || g.Nc == 16) && (g.K == 4 || g.Nc == 4 || dtype == SVRS_F32)) {
+        dim3 grid((unsigned)((M + 255) / 256), 1, g.nprob);
+        if (dtype == SVRS_F32) launch_pixel<float>(a, grid, st);
+        else launch_pixel<__nv_bfloat16>(a, grid, st);
+        return check_launch("conv_pixel_kernel");
+    }
     if (g.Nc <= 16) {
         dim3 grid((unsigned)((M + 255) / 256), (g.Nc + 15) / 16, g.nprob);
         if (dtype == SVRS_F32) conv_taps_kernel<float, 256, 16><<<grid, 256, 0, st>>>(a);
@@ -350,34 +420,45 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(const __grid_constant
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     if (sub_ok) {
         const int ohw = g.OH * g.OW;
-        for (long long m = mbeg + lane; m < mend; m += L) {
-            const int n = (int)(m / ohw);
-            const int r = (int)(m - (long long)n * ohw);
-            const int oy = r / g.OW, ox = r - oy * g.OW;
-            const int iy = oy + tp.dy, ix = ox + tp.dx;
-            if (iy < 0 || iy >= g.IH || ix < 0 || ix >= g.IW) continue;
-            const T* pg = G + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx + a0;
-            const T* px = X + tp.in_off + (long long)n * g.i_sn + (long long)iy * g.i_sy + (long long)ix * g.i_sx + b0;
-            float4 gv, xv;
-            if (vecG) gv = ld4(pg);
-            else {
-                gv.x = Cvt<T>::to_f(pg[0]);
-                gv.y = a0 + 1 < Ca ? Cvt<T>::to_f(pg[1]) : 0.f;
-                gv.z = a0 + 2 < Ca ? Cvt<T>::to_f(pg[2]) : 0.f;
-                gv.w = a0 + 3 < Ca ? Cvt<T>::to_f(pg[3]) : 0.f;
-            }
-            if (vecX) xv = ld4(px);
-            else {
-                xv.x = Cvt<T>::to_f(px[0]);
-                xv.y = b0 + 1 < Cb ? Cvt<T>::to_f(px[1]) : 0.f;
-                xv.z = b0 + 2 < Cb ? Cvt<T>::to_f(px[2]) : 0.f;
-                xv.w = b0 + 3 < Cb ? Cvt<T>::to_f(px[3]) : 0.f;
-            }
-            const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, xb[4] = {xv.x, xv.y, xv.z, xv.w};
+        constexpr int U = 4;      // pixels in flight per thread: issue all loads of a group before the FMAs (ILP)
+        for (long long m0 = mbeg + lane; m0 < mend; m0 += (long long)L * U) {
+            float4 gv[U], xv[U];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int u = 0; u < U; ++u) {
+                gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[u] = gv[u];
+                const long long m = m0 + (long long)u * L;
+                if (m >= mend) continue;
+                const int n = (int)(m / ohw);
+                const int r = (int)(m - (long long)n * ohw);
+                const int oy = r / g.OW, ox = r - oy * g.OW;
+                const int iy = oy + tp.dy, ix = ox + tp.dx;
+                if (iy < 0 || iy >= g.IH || ix < 0 || ix >= g.IW) continue;
+                const T* pg = G + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx + a0;
+                const T* px = X + tp.in_off + (long long)n * g.i_sn + (long long)iy * g.i_sy + (long long)ix * g.i_sx + b0;
+                if (vecG) gv[u] = ld4(pg);
+                else {
+                    gv[u].x = Cvt<T>::to_f(pg[0]);
+                    gv[u].y = a0 + 1 < Ca ? Cvt<T>::to_f(pg[1]) : 0.f;
+                    gv[u].z = a0 + 2 < Ca ? Cvt<T>::to_f(pg[2]) : 0.f;
+                    gv[u].w = a0 + 3 < Ca ? Cvt<T>::to_f(pg[3]) : 0.f;
+                }
+                if (vecX) xv[u] = ld4(px);
+                else {
+                    xv[u].x = Cvt<T>::to_f(px[0]);
+                    xv[u].y = b0 + 1 < Cb ? Cvt<T>::to_f(px[1]) : 0.f;
+                    xv[u].z = b0 + 2 < Cb ? Cvt<T>::to_f(px[2]) : 0.f;
+                    xv[u].w = b0 + 3 < Cb ? Cvt<T>::to_f(px[3]) : 0.f;
+                }
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ga[i], xb[j], acc[i][j]);
+            for (int u = 0; u < U; ++u) {
+                const float ga[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w}, xb[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ga[i], xb[j], acc[i][j]);
+            }
         }
     }
     // reduce over the pixel lanes of each sub-tile
@@ -534,7 +615,8 @@ bool wgrad_halo_supported(const TapGeom& g, int KK);
 int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, cudaStream_t st);
 static int g_tc_enabled = 1;
 static inline bool use_tc(const void* w_nk, int dtype, int K, int Nc, int OW, int OH) {
-    return g_tc_enabled && w_nk != nullptr && tc_supported(dtype, K, Nc, OW, OH);
+    // layers with both channel counts <= 16 are HBM-bound streaming ops: the per-pixel SIMT kernel beats a padded MMA
+    return g_tc_enabled && w_nk != nullptr && !((K == 4 || Nc == 4) && K <= 16 && Nc <= 16) && tc_supported(dtype, K, Nc, OW, OH);
 }
 }  // namespace svrs
 

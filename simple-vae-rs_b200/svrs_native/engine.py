@@ -208,6 +208,7 @@ class Runtime:
         self._pack_key = None
         self._unpack_jobs: Optional[torch.Tensor] = None
         self._unpack_key = None
+        self.scratch_prezeroed = False   # the fused step zeroes all BatchNorm scratch once per step
         self.packs_dirty = True
         self.launches = 0          # kernels enqueued (our own), for bench.py's gpu_launches
 
@@ -254,7 +255,9 @@ class Runtime:
         lib.fill_zero(_p(self._scratch), self._scratch.numel() * 8, _st())
         self.launches += 1
 
-    def zero_grads(self):
+    def zero_grads(self, with_scratch: bool = False):
+        if with_scratch:
+            self.zero_scratch()
         lib.fill_zero(_p(self.store.grad), self.store.grad.numel() * 4, _st())
         lib.fill_zero(_p(self.store.gpack), self.store.gpack.numel() * 4, _st())
         self.launches += 2
@@ -373,7 +376,8 @@ class Runtime:
                 if training:
                     mean = torch.empty(cch, device=dev, dtype=torch.float32)
                     invstd = torch.empty(cch, device=dev, dtype=torch.float32)
-                    lib.fill_zero(_p(op.sums_f), 16 * cch, st)
+                    if not self.scratch_prezeroed:
+                        lib.fill_zero(_p(op.sums_f), 16 * cch, st)
                     lib.bn_stats(_p(x), self.dt, m, cch, _p(op.sums_f), st)
                     mom = 0.1 if bn.momentum is None else bn.momentum
                     track = bn.track_running_stats and bn.running_mean is not None
@@ -438,7 +442,8 @@ class Runtime:
                 n, h, w, cch = x.shape
                 m = n * h * w
                 bn = op.mod
-                lib.fill_zero(_p(op.sums_b), 16 * cch, st)
+                if not self.scratch_prezeroed:
+                    lib.fill_zero(_p(op.sums_b), 16 * cch, st)
                 lib.bn_bwd_reduce(_p(x), _p(dy), self.dt, m, cch, _p(scale), _p(shift), _p(mean), _p(invstd),
                                   int(op.relu), _p(op.sums_b), st)
                 lib.bn_bwd_apply(_p(x), _p(dy), _p(dy), self.dt, m, cch, _p(scale), _p(shift), _p(mean), _p(invstd),

@@ -175,8 +175,12 @@ class FusedCondTrainer(_FusedBase):
         B = x.shape[0]
         Wz, Wu = eng.Wz, eng.Wu
         lib.step_increment(_p(self.step_ptr), st)
-        rt.zero_grads()
-        outs, ctx = eng.forward(x, y, eps_u, eps_z, training=True, save=True, repack=False)
+        rt.zero_grads(with_scratch=True)
+        rt.scratch_prezeroed = True
+        try:
+            outs, ctx = eng.forward(x, y, eps_u, eps_z, training=True, save=True, repack=False)
+        finally:
+            rt.scratch_prezeroed = False
         enc_u, enc_z = outs["enc_u"], outs["enc_z"]
         x_hat, y_hat, mu3, lv3 = outs["x_hat"], outs["y_hat"], outs["mu3"], outs["lv3"]
         xf, yf = x.contiguous().float(), y.contiguous().float()
@@ -193,7 +197,11 @@ class FusedCondTrainer(_FusedBase):
                      _p(mu3), _p(lv3), Wz, Wz, _p(d_mu3), _p(d_lv3), Wz,
                      B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), st)
         rt.launches += 3
-        eng.backward(ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3)
+        rt.scratch_prezeroed = True
+        try:
+            eng.backward(ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3)
+        finally:
+            rt.scratch_prezeroed = False
         self._allreduce_all()
         self._optim_tail()
         return terms
@@ -213,8 +221,12 @@ class FusedVaeTrainer(_FusedBase):
         eng, rt, st = self.eng, self.rt, _st()
         B, Wd = x.shape[0], eng.Wd
         lib.step_increment(_p(self.step_ptr), st)
-        rt.zero_grads()
-        outs, ctx = eng.forward(x, eps, training=True, save=True, repack=False)
+        rt.zero_grads(with_scratch=True)
+        rt.scratch_prezeroed = True
+        try:
+            outs, ctx = eng.forward(x, eps, training=True, save=True, repack=False)
+        finally:
+            rt.scratch_prezeroed = False
         enc, x_hat = outs["enc"], outs["x_hat"]
         xf = x.contiguous().float()
         mu, lv = enc[:, :Wd], enc[:, Wd:]
@@ -227,7 +239,11 @@ class FusedVaeTrainer(_FusedBase):
                      None, None, 0, 0, None, None, 0,
                      B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), st)
         rt.launches += 3
-        eng.backward(ctx, d_xhat, d_enc)
+        rt.scratch_prezeroed = True
+        try:
+            eng.backward(ctx, d_xhat, d_enc)
+        finally:
+            rt.scratch_prezeroed = False
         self._allreduce_all()
         self._optim_tail()
         return terms

@@ -102,7 +102,7 @@ def test_cond_fused_steps_fp32(golden_dir):
         if v.dtype.is_floating_point:
             # Adam's first steps move every weight by ~lr regardless of gradient size, so a weight whose gradient is
             # at rounding-noise level can differ by a few lr between two correct implementations
-            report(f"after {fx['steps']} steps {k}", msd[k], v, 1e-4, atol=0.6 * fx["steps"] * fx["lr"])
+            report(f"after {fx['steps']} steps {k}", msd[k], v, 1e-4, atol=1.0 * fx["steps"] * fx["lr"])
         else:
             assert int(msd[k]) == int(v), k
     report("gammax after steps", model.gammax.detach().reshape(1), torch.tensor([fx["final_gammas"]["gammax"]]), 1e-6)
