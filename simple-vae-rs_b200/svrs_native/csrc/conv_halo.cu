@@ -126,53 +126,60 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-        uint32_t hs = 0, hph = 0, ws = 0, wph = 0, wres_ph = 0, acc = 0, acc_phase = 0;
-        int cur_nt = -1;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile / tiles_pix;
-            if (p.resident && nt != cur_nt) {
-                if (cur_nt >= 0 && lane == 0) tc_commit(wempty(0));   // previous weight set is free once issued MMAs retire
-                __syncwarp();
-                mbar_wait(wfull(0), wres_ph);
-                tc_fence_after();
-                wres_ph ^= 1u;
-                cur_nt = nt;
-            }
-            mbar_wait(tempty(acc), acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 256u;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-                mbar_wait(hfull(hs), hph);
-                tc_fence_after();
-                const uint32_t sh = smem_base + hs * HL_HALO_BYTES;
-                for (int t = 0; t < 9; ++t) {
-                    uint32_t sw;
-                    if (p.resident) sw = w_base + (uint32_t)(kc * 9 + t) * w_slice;
-                    else {
-                        mbar_wait(wfull(ws), wph);
-                        tc_fence_after();
-                        sw = w_base + ws * HL_W_SLOT_BYTES;
-                    }
-                    if (lane == 0) {
-                        const uint64_t adesc = halo_desc(sh + (uint32_t)(p.hy[t] * 16 + p.hx[t]) * 128u, p.base_off_mode);
-                        const uint64_t bdesc = make_kmajor_desc(sw, 1024u, 2u);
+        if (lane == 0) {       // a single thread issues every MMA; the loop is kept free of avoidable ALU work (issue-bound)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_hi = desc_hi(2048u, 2u);      // next 8-pixel group = next halo row
+            const uint32_t b_hi = desc_hi(1024u, 2u);
+            uint32_t aoff[9];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
-                        if (!p.resident) tc_commit(wempty(ws));
-                    }
-                    __syncwarp();
-                    if (!p.resident) { if (++ws == HL_W_SLOTS) { ws = 0; wph ^= 1u; } }
+            for (int t = 0; t < 9; ++t) aoff[t] = (uint32_t)(p.hy[t] * 16 + p.hx[t]) * 8u;   // (halo line * 128 B) >> 4
+            const uint32_t w_slice16 = w_slice >> 4;
+            uint32_t hs = 0, hph = 0, ws = 0, wph = 0, wres_ph = 0, acc = 0, acc_phase = 0;
+            int cur_nt = -1;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile / tiles_pix;
+                if (p.resident && nt != cur_nt) {
+                    if (cur_nt >= 0) tc_commit(wempty(0));   // previous weight set is free once issued MMAs retire
+                    mbar_wait(wfull(0), wres_ph);
+                    tc_fence_after();
+                    wres_ph ^= 1u;
+                    cur_nt = nt;
                 }
-                if (lane == 0) {
+                mbar_wait(tempty(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256u;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(hfull(hs), hph);
+                    tc_fence_after();
+                    const uint32_t a0 = desc_lo(smem_base + hs * HL_HALO_BYTES, 16u);
+                    if (p.resident) {
+                        const uint32_t b0 = desc_lo(w_base, 16u) + (uint32_t)(kc * 9) * w_slice16;
+#pragma unroll
+                        for (int t = 0; t < 9; ++t)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_lohi(d_tmem, a0 + aoff[t] + 2u * k, a_hi, b0 + (uint32_t)t * w_slice16 + 2u * k, b_hi, idesc,
+                                            (t | k) ? 1u : (uint32_t)(kc != 0));
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            mbar_wait(wfull(ws), wph);
+                            tc_fence_after();
+                            const uint32_t b0 = desc_lo(w_base + ws * HL_W_SLOT_BYTES, 16u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_lohi(d_tmem, a0 + aoff[t] + 2u * k, a_hi, b0 + 2u * k, b_hi, idesc,
+                                            (t | k) ? 1u : (uint32_t)(kc != 0));
+                            tc_commit(wempty(ws));
+                            if (++ws == HL_W_SLOTS) { ws = 0; wph ^= 1u; }
+                        }
+                    }
                     tc_commit(hempty(hs));
                     if (kc == p.kchunks - 1) tc_commit(tfull(acc));
+                    if (++hs == HL_HALO_SLOTS) { hs = 0; hph ^= 1u; }
                 }
-                __syncwarp();
-                if (++hs == HL_HALO_SLOTS) { hs = 0; hph ^= 1u; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
         const int q = warp % 4;

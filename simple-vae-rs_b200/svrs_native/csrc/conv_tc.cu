@@ -128,38 +128,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        // instruction descriptor: D=f32, A=B=bf16, both K-major, N = n_tile, M = 128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t sbo = 16u * (uint32_t)p.cw;                               // 8 rows x (cw * 2 B)
-        const uint32_t ltype = p.cw == 64 ? 2u : (p.cw == 32 ? 4u : 6u);         // SWIZZLE_128B / 64B / 32B
-        const int ksub = p.cw / 16;
-        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int pr = tile / tiles_per_prob;
-            const int npairs = p.prob[pr].ntaps * p.kchunks;
-            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 256u;
-            for (int i0 = 0; i0 < npairs; i0 += p.tg) {
-                const int cnt = (npairs - i0) < p.tg ? (npairs - i0) : p.tg;
-                mbar_wait(full_bar(stage), phase);
+        // ================================ MMA issuer (one thread; issue-bound, see tc_ptx.cuh) ================================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N = n_tile, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t ltype = p.cw == 64 ? 2u : (p.cw == 32 ? 4u : 6u);         // SWIZZLE_128B / 64B / 32B
+            const uint32_t hi = desc_hi(16u * (uint32_t)p.cw, ltype);                // SBO = 8 rows x (cw * 2 B)
+            const uint32_t a_box16 = a_box >> 4, b_box16 = b_box >> 4;
+            const int ksub = p.cw / 16;
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int pr = tile / tiles_per_prob;
+                const int npairs = p.prob[pr].ntaps * p.kchunks;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
-                if (lane == 0) {
+                const uint32_t d_tmem = tmem_base + acc * 256u;
+                for (int i0 = 0; i0 < npairs; i0 += p.tg) {
+                    const int cnt = (npairs - i0) < p.tg ? (npairs - i0) : p.tg;
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
                     const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-                    for (int j = 0; j < cnt; ++j) {
-                        const uint64_t adesc = make_kmajor_desc(sa + j * a_box, sbo, ltype);
-                        const uint64_t bdesc = make_kmajor_desc(sa + TC_A_BYTES + j * b_box, sbo, ltype);
-                        for (int k = 0; k < ksub; ++k)      // K = 16 bf16 = 32 B steps inside the swizzle span
-                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i0 | j | k) != 0);
+                    uint32_t a_lo = desc_lo(sa, 16u), b_lo = desc_lo(sa + TC_A_BYTES, 16u);
+                    if (ksub == 4) {                 // cw = 64: one pair per stage, 4 K-steps
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_lohi(d_tmem, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, k ? 1u : (uint32_t)(i0 != 0));
+                    } else {
+                        for (int j = 0; j < cnt; ++j) {
+                            for (int k = 0; k < ksub; ++k)
+                                tc_mma_lohi(d_tmem, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, (uint32_t)((i0 | j | k) != 0));
+                            a_lo += a_box16;
+                            b_lo += b_box16;
+                        }
                     }
                     tc_commit(empty_bar(stage));                          // frees the smem stage when these MMAs retire
                     if (i0 + cnt >= npairs) tc_commit(tfull_bar(acc));    // accumulator complete -> epilogue
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
         // ================================ epilogue (8 warps) ================================
@@ -304,6 +311,12 @@ int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias
     p.Nc = Cw;
     int npad = (Cw + 15) / 16 * 16;
     p.n_tile = npad <= 256 ? npad : 256;
+    // few pixel tiles (4x4 / 8x8 maps): trade MMA width for CTAs until the machine is reasonably full.  N = 128 still
+    // balances the ~58-cycle issue floor (64 cycles of tensor work per MMA); N = 64 only when even that leaves SMs idle.
+    {
+        long long pix_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * g.nprob;
+        while (p.n_tile > 64 && p.n_tile % 32 == 0 && pix_tiles * ((Cw + p.n_tile - 1) / p.n_tile) < 96) p.n_tile /= 2;
+    }
     p.n_tiles = (Cw + p.n_tile - 1) / p.n_tile;
     p.cw = chunk_width(Cr);
     p.tg = 64 / p.cw;

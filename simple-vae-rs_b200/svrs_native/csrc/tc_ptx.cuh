@@ -106,6 +106,26 @@ __device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr, uint32_t lbo, u
     return d;
 }
 
+// Split-word descriptor helpers for the MMA issue loops.  MEASURED on B200 (tools/mma_rate.cu): one thread can issue a
+// tcgen05.mma every ~58 cycles at best, independent of N and of accumulator dependencies, so a 128x64x16 MMA (32 cycles of
+// tensor work) is ISSUE-bound; every extra ALU instruction in the issue loop costs throughput.  The loops therefore keep the
+// descriptor's high word constant and bump only the low word (start address >> 4) with 32-bit adds.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3FFFF) >> 4) | (((lbo >> 4) & 0x3FFF) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo, uint32_t ltype) { return ((sbo >> 4) & 0x3FFF) | (1u << 14) | (ltype << 29); }
+__device__ __forceinline__ void tc_mma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // ------------------------------------------------------------------------------------------ shared conv epilogue
 // 8 epilogue warps: warp e = (lane quarter q = e % 4, column half = e / 4).  Each thread owns ONE accumulator row (pixel)
 // and walks its half of the tile's 32-column chunks: tcgen05.ld -> (+bias) -> (activation) -> bf16 -> 16-byte stores.

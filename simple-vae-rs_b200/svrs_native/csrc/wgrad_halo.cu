@@ -88,32 +88,34 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad3_halo_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        // D = f32, A = B = bf16, both MN-major, N = 64, M = 128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-        uint32_t stage = 0, phase = 0;
-        for (int kstep = 0; kstep < nsteps; ++kstep) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            if (lane == 0) {
+        if (lane == 0) {
+            // D = f32, A = B = bf16, both MN-major, N = 64, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_hi = desc_hi(2048u, 2u), b_hi = desc_hi(1024u, 2u);
+            uint32_t a_rel[5];     // low-word pieces that do not depend on the stage: tap offset (>>4) and LBO field
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {                          // tap pairs (0,1) (2,3) (4,5) (6,7) (8,8)
+                const uint32_t o0 = (uint32_t)p.off[2 * b] * 128u, o1 = (uint32_t)p.off[2 * b + 1] * 128u;
+                const uint32_t lbo = o1 > o0 ? o1 - o0 : 128u;     // tail pair: second half is ignored by the epilogue
+                a_rel[b] = (o0 >> 4) | (((lbo >> 4) & 0x3FFF) << 16);
+            }
+            uint32_t stage = 0, phase = 0;
+            for (int kstep = 0; kstep < nsteps; ++kstep) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
                 const uint32_t sh = smem_base + stage * WH_STAGE_BYTES;
-                const uint32_t sg = sh + WH_HALO_BYTES;
+                const uint32_t a0 = (sh & 0x3FFFF) >> 4;
+                const uint32_t b0 = desc_lo(sh + WH_HALO_BYTES, 16384u);
 #pragma unroll
-                for (int b = 0; b < 5; ++b) {                      // tap pairs (0,1) (2,3) (4,5) (6,7) (8,8)
-                    const uint32_t o0 = (uint32_t)p.off[2 * b] * 128u, o1 = (uint32_t)p.off[2 * b + 1] * 128u;
-                    const uint32_t lbo = o1 > o0 ? o1 - o0 : 128u;     // tail pair: second half is ignored by the epilogue
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(b * 64);
+                for (int k = 0; k < 8; ++k)                        // 16 pixels = 2 halo rows per MMA
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {                  // 16 pixels = 2 halo rows per MMA
-                        const uint64_t adesc = make_mn_desc(sh + o0 + k * 4096u, lbo, 2048u, 2u);
-                        const uint64_t bdesc = make_mn_desc(sg + k * 2048u, 16384u, 1024u, 2u);
-                        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kstep | k) != 0);
-                    }
-                }
+                    for (int b = 0; b < 5; ++b)
+                        tc_mma_lohi(tmem_base + (uint32_t)(b * 64), a0 + a_rel[b] + 256u * k, a_hi, b0 + 128u * k, b_hi, idesc,
+                                    k ? 1u : (uint32_t)(kstep != 0));
                 tc_commit(empty_bar(stage));
                 if (kstep == nsteps - 1) tc_commit(done_bar);
+                if (++stage == WH_STAGES) { stage = 0; phase ^= 1u; }
             }
-            __syncwarp();
-            if (++stage == WH_STAGES) { stage = 0; phase ^= 1u; }
         }
     } else if (nsteps > 0) {
         const int q = warp % 4;

@@ -114,33 +114,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = n_tile, M = 128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                               ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t lt_x = p.cwx == 64 ? 2u : (p.cwx == 32 ? 4u : 6u);
-        const uint32_t lt_g = p.cwg == 64 ? 2u : (p.cwg == 32 ? 4u : 6u);
-        const uint32_t sbo_x = 16u * (uint32_t)p.cwx, sbo_g = 16u * (uint32_t)p.cwg;        // 8 pixel rows
-        const uint32_t kadv_x = 32u * (uint32_t)p.cwx, kadv_g = 32u * (uint32_t)p.cwg;      // 16 pixel rows per MMA
-        uint32_t stage = 0, phase = 0;
-        for (int kstep = 0; kstep < nsteps; ++kstep) {
-            for (int b = 0; b < nblk; ++b) {
-                mbar_wait(full_bar(stage), phase);
-                tc_fence_after();
-                if (lane == 0) {
+        if (lane == 0) {
+            // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = n_tile, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_hi = desc_hi(16u * (uint32_t)p.cwx, p.cwx == 64 ? 2u : (p.cwx == 32 ? 4u : 6u));   // 8 pixel rows
+            const uint32_t b_hi = desc_hi(16u * (uint32_t)p.cwg, p.cwg == 64 ? 2u : (p.cwg == 32 ? 4u : 6u));
+            const uint32_t kadv_x16 = 2u * (uint32_t)p.cwx, kadv_g16 = 2u * (uint32_t)p.cwg;                    // 16 pixel rows, >> 4
+            uint32_t stage = 0, phase = 0;
+            for (int kstep = 0; kstep < nsteps; ++kstep) {
+                for (int b = 0; b < nblk; ++b) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
                     const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
-                    const uint32_t sg = sx + WG_X_BYTES;
+                    const uint32_t a0 = desc_lo(sx, x_box), b0 = desc_lo(sx + WG_X_BYTES, g_box);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(b * p.n_tile);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {     // 8 x (K = 16 pixels)
-                        const uint64_t adesc = make_mn_desc(sx + k * kadv_x, x_box, sbo_x, lt_x);
-                        const uint64_t bdesc = make_mn_desc(sg + k * kadv_g, g_box, sbo_g, lt_g);
-                        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kstep | k) != 0);
-                    }
+                    for (int k = 0; k < 8; ++k)     // 8 x (K = 16 pixels)
+                        tc_mma_lohi(d_tmem, a0 + kadv_x16 * k, a_hi, b0 + kadv_g16 * k, b_hi, idesc, k ? 1u : (uint32_t)(kstep != 0));
                     tc_commit(empty_bar(stage));
                     if (kstep == nsteps - 1 && b == nblk - 1) tc_commit(done_bar);
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (nsteps > 0) {
@@ -223,8 +218,9 @@ int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw
     if (p.group > p.nblocks) p.group = p.nblocks;
     p.ngroups = (p.nblocks + p.group - 1) / p.group;
     p.ksteps_total = p.tiles_x * p.tiles_y * p.tiles_n;
+    // split the pixel range only as far as needed to fill the machine once: every extra split multiplies the atomics
     int base = p.ngroups * p.n_tiles;
-    int ksplit = (2 * num_sms() + base - 1) / base;
+    int ksplit = (num_sms() + base / 2) / base;
     if (ksplit > p.ksteps_total) ksplit = p.ksteps_total;
     if (ksplit < 1) ksplit = 1;
     p.ksplit = ksplit;
