@@ -38,6 +38,13 @@ extern "C" {
 
 const char* svrs_last_error(void);
 int svrs_abi_version(void);
+/* Number of CUDA kernels this library has launched in the process so far (every launch site counts itself); the
+ * difference across a step is bench.py's `gpu_launches`. */
+int64_t svrs_launch_count(void);
+/* Kernel-name trace for profile attribution: svrs_trace_reset(1) starts recording the names of the kernels launched by
+ * the calling thread, svrs_trace() returns them comma-separated, svrs_trace_reset(0) switches recording off. */
+void svrs_trace_reset(int enable);
+const char* svrs_trace(void);
 /* compute capability major*10+minor of device `dev`, or <0 */
 int svrs_device_cc(int dev);
 
@@ -63,7 +70,8 @@ int svrs_pack_weights(const float* w, int d0, int d1, int kk, void* p01, void* p
  * the tile counts of the preceding jobs; total_tiles = sum of all tile counts; max_kk = largest kk (<= 16). */
 int svrs_pack_job_bytes(void);
 int svrs_pack_weights_multi(const void* jobs, int njobs, int total_tiles, int max_kk, int dtype, void* stream);
-/* inverse direction for gradients: same job records with w = torch-layout fp32 gradient (+=) and p01 = packed fp32 scratch */
+/* inverse direction for gradients: same job records with w = torch-layout fp32 gradient (+=) and p01 = the packed
+ * fp32 scratch [kk][d1][d0] the tensor-core wgrad kernels accumulated into (see svrs_conv2d_wgrad) */
 int svrs_unpack_grads_multi(const void* jobs, int njobs, int total_tiles, int max_kk, void* stream);
 
 /* Two kernels sit behind each fprop/dgrad entry point:
@@ -92,13 +100,17 @@ int svrs_conv2d_fprop(const void* x, const void* w_kn, const void* w_nk, const f
 int svrs_conv2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
                       int N, int H, int W, int Cin, int Cout, int ksize, void* stream);
 /* dw_packed (may be NULL): a zeroed fp32 scratch of the weight's size.  When given, the tcgen05 kernels accumulate
- * there in the per-tap layout [tap][d0][d1] (d0, d1 = the weight's first two torch dims), which turns their atomics into
- * fully coalesced 128-byte reductions; svrs_unpack_grads_multi() later adds every layer's scratch into the torch-layout
- * gradient in one launch.  The SIMT kernels always accumulate into dw directly.
+ * there in the per-tap layout [tap][d1][d0] (d0, d1 = the weight's first two torch dims; d0 fastest): each CTA stages
+ * its TMEM accumulators in shared memory and adds them with a handful of TMA tensor reductions
+ * (cp.reduce.async.bulk.tensor .add.f32) instead of thousands of per-thread atomics - measured: a warp sustains only
+ * ~1 global store/atomic per ~100 cycles, which made the epilogue 4-8x longer than the MMA phase on small maps.
+ * svrs_unpack_grads_multi() later adds every layer's scratch into the torch-layout gradient in one launch.  The SIMT
+ * kernels always accumulate into dw directly.
  * wgrad: dw[Cout][Cin][k][k] += sum x (*) dy  (fp32, torch layout, ATOMIC accumulate - zero it first);
  * db[Cout] += column sums of dy when db != NULL.  `ksplit` <= 0 picks a split automatically. */
 int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float* dw_packed, float* db, int dtype,
                       int N, int H, int W, int Cin, int Cout, int ksize, int ksplit, void* stream);
+
 
 /* ---- nn.ConvTranspose2d k4 s2 p1 (layers.py:275-277): x [N,H,W,Cin] -> y [N,2H,2W,Cout].
  *      four output-parity sub-convolutions of 2x2 taps.  w_kn = p01 pack [tap][Cin][Cout]. */

@@ -19,7 +19,10 @@ void set_error(const char* fmt, ...);
         }                                         \
     } while (0)
 
+void note_kernel(const char* what);   // launch counter + optional name trace (layout.cu)
+
 static inline int check_launch(const char* what) {
+    note_kernel(what);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));

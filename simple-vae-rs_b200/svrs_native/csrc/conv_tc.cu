@@ -244,6 +244,20 @@ int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, l
     return 0;
 }
 
+int make_f32_2d_map(CUtensorMap* m, const void* base, long long inner, long long rows, int box_inner, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SVRS_E_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)inner * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUtensorMapSwizzle sw = box_inner * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(f32 2d) failed: %d (inner=%lld rows=%lld box %dx%d)", (int)r, inner, rows, box_inner, box_rows); return SVRS_E_CUDA; }
+    return 0;
+}
+
 // weights in NK pack [tap][Nc][K] (K contiguous): dims (K, Nc, taps), box (cw, n_tile, 1)
 static int make_w_map(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile, int cw) {
     PFN_encodeTiled enc = get_encode();

@@ -13,6 +13,23 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// Every kernel launch of this library passes through check_launch() -> note_kernel(): a process-wide launch counter
+// (bench.py's gpu_launches) and, between svrs_trace_reset() and svrs_trace(), the names of the kernels launched by the
+// calling thread (profile attribution: which kernel a C-ABI entry point actually dispatched to).
+static long long g_launches = 0;
+static thread_local char g_trace[2048] = "";
+static thread_local int g_trace_len = -1;   // -1 = tracing off
+
+void note_kernel(const char* what) {
+    __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED);
+    if (g_trace_len < 0) return;
+    int n = (int)strlen(what);
+    if (g_trace_len + n + 2 >= (int)sizeof(g_trace)) return;
+    if (g_trace_len > 0) g_trace[g_trace_len++] = ',';
+    memcpy(g_trace + g_trace_len, what, n + 1);
+    g_trace_len += n;
+}
+
 // One image: src is [C][HW] (row stride HW), dst is [HW][C].  32x32 smem tile transpose.
 template <typename TS, typename TD>
 __global__ void nchw_to_nhwc_kernel(const TS* __restrict__ src, long long src_ld, TD* __restrict__ dst,
@@ -295,9 +312,9 @@ __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackJob* __rest
     const float* src = reinterpret_cast<const float*>(jb.p01);
     float* dst = const_cast<float*>(jb.w);
     const int total = kk * na * nb;
-    for (int idx = threadIdx.x; idx < total; idx += 256) {       // read packed: b fastest (contiguous runs of nb)
-        int b = idx % nb, a = (idx / nb) % na, t = idx / (nb * na);
-        tile[a * ROW + b * (kk + 1) + t] = src[((long long)t * d0 + a0 + a) * d1 + b0 + b];
+    for (int idx = threadIdx.x; idx < total; idx += 256) {       // read packed [kk][d1][d0]: a fastest (runs of na)
+        int a = idx % na, b = (idx / na) % nb, t = idx / (nb * na);
+        tile[a * ROW + b * (kk + 1) + t] = src[((long long)t * d1 + b0 + b) * d0 + a0 + a];
     }
     __syncthreads();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -327,3 +344,10 @@ extern "C" int svrs_pack_weights_multi(const void* jobs, int njobs, int total_ti
     else { set_error("pack_weights_multi: bad dtype"); return SVRS_E_ARG; }
     return check_launch("pack_weights_multi");
 }
+
+extern "C" int64_t svrs_launch_count(void) { return __atomic_load_n(&svrs::g_launches, __ATOMIC_RELAXED); }
+extern "C" void svrs_trace_reset(int enable) {
+    svrs::g_trace[0] = 0;
+    svrs::g_trace_len = enable ? 0 : -1;
+}
+extern "C" const char* svrs_trace(void) { return svrs::g_trace; }

@@ -42,6 +42,35 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// ---- TMA tensor reduction (shared -> global, element-wise add done by L2) and bulk-group bookkeeping --------------
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Stage one accumulator row for a TMA tensor store/reduce: `row_bytes` (128 or 64) of fp32 per row, rows packed, the
+// tensor map's SWIZZLE_128B / SWIZZLE_64B pattern applied (16-byte chunk index ^= row bits; `box` is 1024-byte aligned).
+template <int NV4>
+__device__ __forceinline__ void stage_row_swizzled(uint32_t box, int r, uint32_t row_bytes, const uint32_t* v) {
+    const uint32_t mask = row_bytes == 128u ? 7u : 3u;
+#pragma unroll
+    for (int j = 0; j < NV4; ++j) {
+        uint32_t off = (uint32_t)r * row_bytes + 16u * j;
+        off ^= ((off >> 7) & mask) << 4;
+        st_shared_v4(box + off, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -195,6 +224,8 @@ __device__ __forceinline__ void epi_dispatch(int act, uint32_t taddr, int n_tile
 int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sx, long long sy, long long sn,
                  int BW, int BH, int BNI, int cw);
 bool pick_box(int OW, int OH, int& BW, int& BH, int& BNI);
+// fp32 matrix [rows][inner] (inner contiguous), box (box_inner = 32 or 16 columns, box_rows), swizzle matching the box width
+int make_f32_2d_map(CUtensorMap* m, const void* base, long long inner, long long rows, int box_inner, int box_rows);
 int chunk_width(int C);   // 64 / 32 / 16 / 0 (unsupported)
 
 }  // namespace svrs

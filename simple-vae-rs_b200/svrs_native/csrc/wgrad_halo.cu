@@ -28,6 +28,7 @@ constexpr int WH_THREADS = 192;
 struct alignas(64) WhParams {
     CUtensorMap x_map;   // (Cb, W, H, N) box (64, 16, 18, 1)
     CUtensorMap g_map;   // (Ca, W, H, N) box (64, 8, 16, 1)
+    CUtensorMap dw_map;  // packed mode: fp32 scratch [9*Cb rows][Ca], box (32 columns, 64 rows), 128B swizzle
     float* dw;
     int N, OH, OW, tiles_x, tiles_y;
     int Ca, Cb, KK;
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad3_halo_kernel(const __grid
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.x_map);
         prefetch_tmap(&p.g_map);
+        if (p.packed) prefetch_tmap(&p.dw_map);
         for (int s = 0; s < WH_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -122,22 +124,54 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad3_halo_kernel(const __grid
         const int m = q * 32 + lane;
         mbar_wait(done_bar, 0);
         tc_fence_after();
-        for (int b = 0; b < 5; ++b) {
-            const int tap = 2 * b + (m >= 64 ? 1 : 0);
-            const bool row_ok = tap < 9;
-            const int cb = bj * 64 + (m & 63);
-            const uint32_t taddr = tmem_base + (uint32_t)(b * 64) + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld_wait();
-                if (row_ok) {
+        if (p.packed) {
+            // packed scratch [tap][b][a]: stage each 128 x 64 accumulator (two taps x 64 b-rows) in shared memory in the
+            // tensor map's 128B-swizzled box layout, then ONE thread adds it with TMA tensor reductions (see wgrad_tc.cu)
+            const int h = m >> 6, r = m & 63;            // h: which tap of the pair
+            const bool issuer = threadIdx.x == 64;
+            for (int b = 0; b < 5; ++b) {
+                const uint32_t buf = smem_base + (uint32_t)(b & 1) * 32768u;
+                if (b >= 2) {
+                    if (issuer) bulk_wait_read_1();
+                    named_bar_sync(1, 128);
+                }
+                const uint32_t taddr = tmem_base + (uint32_t)(b * 64) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int ca = at * 64 + c0 + j;
-                        float* dst = p.packed ? p.dw + ((long long)tap * p.Ca + ca) * p.Cb + cb
-                                              : p.dw + ((long long)ca * p.Cb + cb) * p.KK + tap;
-                        atomicAdd(dst, __uint_as_float(v[j]));
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    stage_row_swizzled<8>(buf + (uint32_t)(h * 2 + c0 / 32) * 8192u, r, 128u, v);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (issuer) {
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int tap = 2 * b + hh;
+                        if (tap >= 9) break;
+                        for (int cc = 0; cc < 2; ++cc)
+                            tma_reduce_add_2d(&p.dw_map, buf + (uint32_t)(hh * 2 + cc) * 8192u, at * 64 + cc * 32, tap * p.Cb + bj * 64);
+                    }
+                    bulk_commit();
+                }
+            }
+            if (issuer) bulk_wait_all();
+        } else {
+            for (int b = 0; b < 5; ++b) {
+                const int tap = 2 * b + (m >= 64 ? 1 : 0);
+                const bool row_ok = tap < 9;
+                const int cb = bj * 64 + (m & 63);
+                const uint32_t taddr = tmem_base + (uint32_t)(b * 64) + ((uint32_t)(q * 32) << 16);
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int ca = at * 64 + c0 + j;
+                            atomicAdd(p.dw + ((long long)ca * p.Cb + cb) * p.KK + tap, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
@@ -159,17 +193,8 @@ bool wgrad_halo_supported(const TapGeom& g, int KK) {
            g.OW % 8 == 0 && g.OH % 16 == 0 && g.IH == g.OH && g.IW == g.OW;
 }
 
-int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("wgrad3_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
-        attr_set = true;
-    }
-    WhParams p;
+static void wh_plan(const TapGeom& g, WhParams& p) {
     memset(&p, 0, sizeof(p));
-    p.dw = dw;
-    p.packed = packed;
     p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.tiles_x = g.OW / 8; p.tiles_y = g.OH / 16;
     p.Ca = g.Nc; p.Cb = g.K; p.KK = 9;
     p.a_tiles = p.Ca / 64; p.b_chunks = p.Cb / 64;
@@ -180,7 +205,28 @@ int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float*
     int ksplit = (ctas_target + base - 1) / base;
     if (ksplit > p.ksteps_total) ksplit = p.ksteps_total;
     if (ksplit < 1) ksplit = 1;
-    p.ksplit = ksplit;
+    const int steps_per = (p.ksteps_total + ksplit - 1) / ksplit;      // exact: every split owns >= 1 k-step (slab mode)
+    p.ksplit = (p.ksteps_total + steps_per - 1) / steps_per;
+}
+
+int wgrad_halo_splits(const TapGeom& g) {
+    WhParams p;
+    wh_plan(g, p);
+    return p.ksplit;
+}
+
+int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("wgrad3_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
+        attr_set = true;
+    }
+    WhParams p;
+    wh_plan(g, p);
+    p.dw = dw;
+    p.packed = packed;
+    const int base = p.a_tiles * p.b_chunks;
     const Prob& pb = g.prob[0];
     for (int t = 0; t < 9; ++t) p.off[t] = (pb.taps[t].dy + 1) * 16 + (pb.taps[t].dx + 1);
     p.off[9] = p.off[8];
@@ -188,6 +234,10 @@ int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float*
     if (rc) return rc;
     rc = make_act_map(&p.g_map, gmat, p.Ca, g.OW, g.OH, g.N, g.o_sx, g.o_sy, g.o_sn, 8, 16, 1, 64);
     if (rc) return rc;
+    if (packed) {
+        rc = make_f32_2d_map(&p.dw_map, dw, p.Ca, 9ll * p.Cb, 32, 64);
+        if (rc) return rc;
+    }
     int grid = base * p.ksplit;
     wgrad3_halo_kernel<<<grid, WH_THREADS, WH_SMEM_BYTES, st>>>(p);
     return check_launch("wgrad3_halo_kernel");

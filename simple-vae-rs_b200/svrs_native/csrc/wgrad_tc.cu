@@ -15,6 +15,7 @@
 #include "taps.cuh"
 #include "tc_ptx.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace svrs {
 
@@ -30,6 +31,7 @@ struct WgTap { int map, dy, dx, tapid; };
 struct alignas(64) WgParams {
     CUtensorMap x_maps[4];    // input views (parity classes)
     CUtensorMap g_map;        // output-grid operand
+    CUtensorMap dw_map;       // packed mode: fp32 scratch [KK*Cb rows][Ca], box (min(32, n_tile) columns, cwx rows)
     float* dw;
     int N, OH, OW, BW, BH, BNI;
     int tiles_x, tiles_y, tiles_n;     // pixel tiling of the output grid
@@ -41,6 +43,7 @@ struct alignas(64) WgParams {
     int nboxes, nblocks, group, ngroups;
     int ksplit, ksteps_total;
     int ntaps, packed;
+    long long* prof;                   // debug (SVRS_WG_PROF=1): per-CTA clock64 stamps, 8 per CTA
     WgTap taps[16];
 };
 
@@ -54,10 +57,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t tmem_slot = bar_base + 8u * (2 * WG_STAGES + 1);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    long long* prof = p.prof ? p.prof + 8ll * blockIdx.x : nullptr;
+    if (prof && threadIdx.x == 0) prof[0] = clock64();
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) prefetch_tmap(&p.x_maps[i]);
         prefetch_tmap(&p.g_map);
+        if (p.packed) prefetch_tmap(&p.dw_map);
         for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -70,6 +76,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (prof && threadIdx.x == 0) prof[1] = clock64();
 
     // work item: (pixel split ks, column tile nt, M-block group grp)
     int w = blockIdx.x;
@@ -126,6 +133,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 for (int b = 0; b < nblk; ++b) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
+                    if (prof && kstep == 0 && b == 0) prof[2] = clock64();
                     const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
                     const uint32_t a0 = desc_lo(sx, x_box), b0 = desc_lo(sx + WG_X_BYTES, g_box);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(b * p.n_tile);
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                     for (int k = 0; k < 8; ++k)     // 8 x (K = 16 pixels)
                         tc_mma_lohi(d_tmem, a0 + kadv_x16 * k, a_hi, b0 + kadv_g16 * k, b_hi, idesc, k ? 1u : (uint32_t)(kstep != 0));
                     tc_commit(empty_bar(stage));
-                    if (kstep == nsteps - 1 && b == nblk - 1) tc_commit(done_bar);
+                    if (kstep == nsteps - 1 && b == nblk - 1) { tc_commit(done_bar); if (prof) prof[3] = clock64(); }
                     if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -143,27 +151,65 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         const int m = q * 32 + lane;
         mbar_wait(done_bar, 0);
         tc_fence_after();
-        for (int b = 0; b < nblk; ++b) {
-            const int box = p.bpb * (blk0 + b) + m / p.cwx;
-            const bool row_ok = box < p.nboxes;
-            const int bx = row_ok ? box : 0;
-            const int tapid = p.taps[bx / p.cb_chunks].tapid;
-            const int cb = (bx % p.cb_chunks) * p.cwx + (m % p.cwx);
-            const uint32_t taddr = tmem_base + (uint32_t)(b * p.n_tile) + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-                uint32_t v[32];
-                const int cols = (p.n_tile - c0 >= 32) ? 32 : 16;
-                if (cols == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
-                tmem_ld_wait();
-                if (row_ok) {
+        if (prof && threadIdx.x == 64) prof[4] = clock64();
+        if (p.packed) {
+            // Packed scratch [tap][b][a] (a fastest): stage each 128 x n_tile accumulator block in shared memory (the
+            // pipeline stages are idle by now) in the tensor map's swizzled box layout and let ONE thread add it to the
+            // scratch with a few TMA tensor reductions - boxes of (32 | 16 columns) x (cwx rows), i.e. one X box each.
+            // Two staging buffers: block b+1 is read out of TMEM while the reductions of block b are still in flight.
+            const int cwd = p.n_tile < 32 ? p.n_tile : 32;
+            const int nch = p.n_tile / cwd;
+            const uint32_t row_bytes = 4u * (uint32_t)cwd;
+            const uint32_t box_bytes = (uint32_t)p.cwx * row_bytes;
+            const uint32_t blk_bytes = 128u * 4u * (uint32_t)p.n_tile;
+            const int h = m / p.cwx, r = m % p.cwx;
+            const bool issuer = threadIdx.x == 64;
+            for (int b = 0; b < nblk; ++b) {
+                const uint32_t buf = smem_base + (uint32_t)(b & 1) * blk_bytes;
+                if (b >= 2) {
+                    if (issuer) bulk_wait_read_1();      // the reductions that last read this buffer are done with it
+                    named_bar_sync(1, 128);
+                }
+                const uint32_t taddr = tmem_base + (uint32_t)(b * p.n_tile) + ((uint32_t)(q * 32) << 16);
+                for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                    uint32_t v[32];
+                    const uint32_t box = buf + (uint32_t)(h * nch + c0 / 32) * box_bytes;
+                    if (cwd == 32) { tmem_ld32(taddr + c0, v); tmem_ld_wait(); stage_row_swizzled<8>(box, r, row_bytes, v); }
+                    else { tmem_ld16(taddr + c0, v); tmem_ld_wait(); stage_row_swizzled<4>(box, r, row_bytes, v); }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (issuer) {
+                    for (int hh = 0; hh < p.bpb; ++hh) {
+                        const int box = p.bpb * (blk0 + b) + hh;
+                        if (box >= p.nboxes) break;                       // tail rows of the last M-block
+                        const int row0 = p.taps[box / p.cb_chunks].tapid * p.Cb + (box % p.cb_chunks) * p.cwx;
+                        for (int cc = 0; cc < nch; ++cc)
+                            tma_reduce_add_2d(&p.dw_map, buf + (uint32_t)(hh * nch + cc) * box_bytes, nt * p.n_tile + cc * cwd, row0);
+                    }
+                    bulk_commit();
+                }
+            }
+            if (issuer) bulk_wait_all();
+        } else {
+            for (int b = 0; b < nblk; ++b) {
+                const int box = p.bpb * (blk0 + b) + m / p.cwx;
+                const bool row_ok = box < p.nboxes;
+                const int bx = row_ok ? box : 0;
+                const int tapid = p.taps[bx / p.cb_chunks].tapid;
+                const int cb = (bx % p.cb_chunks) * p.cwx + (m % p.cwx);
+                const uint32_t taddr = tmem_base + (uint32_t)(b * p.n_tile) + ((uint32_t)(q * 32) << 16);
+                for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                    uint32_t v[32];
+                    const int cols = (p.n_tile - c0 >= 32) ? 32 : 16;
+                    if (cols == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int ca = nt * p.n_tile + c0 + j;
-                        if (j < cols && ca < p.Ca) {
-                            // packed scratch [tap][a][b]: a warp's 32 lanes (consecutive b) hit one 128-byte line
-                            float* dst = p.packed ? p.dw + ((long long)tapid * p.Ca + ca) * p.Cb + cb
-                                                  : p.dw + ((long long)ca * p.Cb + cb) * p.KK + tapid;
-                            atomicAdd(dst, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; ++j) {
+                            const int ca = nt * p.n_tile + c0 + j;
+                            if (j < cols && ca < p.Ca)
+                                atomicAdd(p.dw + ((long long)ca * p.Cb + cb) * p.KK + tapid, __uint_as_float(v[j]));
                         }
                     }
                 }
@@ -171,12 +217,37 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         }
     }
 
+    if (prof && threadIdx.x == 64) { prof[5] = clock64(); prof[7] = nsteps; }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
+}
+
+// Debug aid: SVRS_WG_PROF=1 makes every launch synchronous and prints the mean / max per-CTA phase times (cycles).
+static void wg_prof_report(const WgParams& p, int grid, long long* dprof) {
+    cudaDeviceSynchronize();
+    long long* h = (long long*)malloc(sizeof(long long) * 8 * grid);
+    cudaMemcpy(h, dprof, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+    double sum[5] = {0, 0, 0, 0, 0}, mx[5] = {0, 0, 0, 0, 0};
+    int live = 0;
+    double ldsum = 0;
+    for (int c = 0; c < grid; ++c) {
+        const long long* t = h + 8 * c;
+        if (t[7] <= 0) continue;
+        ldsum += (double)t[6];
+        ++live;
+        double d[5] = {(double)(t[1] - t[0]), (double)(t[2] - t[1]), (double)(t[3] - t[2]), (double)(t[4] - t[3]), (double)(t[5] - t[4])};
+        for (int i = 0; i < 5; ++i) { sum[i] += d[i]; if (d[i] > mx[i]) mx[i] = d[i]; }
+    }
+    fprintf(stderr, "[wgrad_tc] grid %d live %d ksplit %d ksteps %d group %d n_tile %d cwx %d cwg %d | cycles mean(max): setup %.0f(%.0f) "
+            "first-load %.0f(%.0f) mma-issue %.0f(%.0f) mma-drain %.0f(%.0f) epilogue %.0f(%.0f) of which tmem-ld %.0f\n", grid, live, p.ksplit,
+            p.ksteps_total, p.group, p.n_tile, p.cwx, p.cwg, sum[0] / live, mx[0], sum[1] / live, mx[1], sum[2] / live, mx[2],
+            sum[3] / live, mx[3], sum[4] / live, mx[4], ldsum / live);
+    free(h);
+    cudaFree(dprof);
 }
 
 bool wgrad_tc_supported(int dtype, int Ca, int Cb, int OW, int OH) {
@@ -186,20 +257,11 @@ bool wgrad_tc_supported(int dtype, int Ca, int Cb, int OW, int OH) {
     return dtype == SVRS_BF16 && ca_ok && chunk_width(Cb) != 0 && pick_box(OW, OH, bw, bh, bn);
 }
 
-// g: geometry of the forward-form conv whose output grid carries `gmat` (channels Ca = g.Nc) and whose input view
-// carries `x` (channels Cb = g.K);  dw torch layout [(a*Cb + b)*KK + tap]
-int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, int KK, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
-        attr_set = true;
-    }
-    WgParams p;
+// Tiling / split plan of one launch (everything except the tensor maps).  The pixel split is exact - every split owns at
+// least one k-step - because in packed mode each split writes a whole slab that the reduction later reads.
+static int wg_plan(const TapGeom& g, int KK, WgParams& p) {
     memset(&p, 0, sizeof(p));
     if (!pick_box(g.OW, g.OH, p.BW, p.BH, p.BNI)) { set_error("wgrad_tc: unsupported spatial dims"); return SVRS_E_UNSUPPORTED; }
-    p.dw = dw;
-    p.packed = packed;
     p.N = g.N; p.OH = g.OH; p.OW = g.OW;
     p.tiles_x = g.OW / p.BW; p.tiles_y = g.OH / p.BH; p.tiles_n = (g.N + p.BNI - 1) / p.BNI;
     p.Ca = g.Nc; p.Cb = g.K; p.KK = KK;
@@ -218,13 +280,34 @@ int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw
     if (p.group > p.nblocks) p.group = p.nblocks;
     p.ngroups = (p.nblocks + p.group - 1) / p.group;
     p.ksteps_total = p.tiles_x * p.tiles_y * p.tiles_n;
-    // split the pixel range only as far as needed to fill the machine once: every extra split multiplies the atomics
     int base = p.ngroups * p.n_tiles;
     int ksplit = (num_sms() + base / 2) / base;
     if (ksplit > p.ksteps_total) ksplit = p.ksteps_total;
     if (ksplit < 1) ksplit = 1;
-    p.ksplit = ksplit;
+    const int steps_per = (p.ksteps_total + ksplit - 1) / ksplit;
+    p.ksplit = (p.ksteps_total + steps_per - 1) / steps_per;
+    return 0;
+}
 
+int wgrad_tc_splits(const TapGeom& g, int KK) {
+    WgParams p;
+    return wg_plan(g, KK, p) ? 0 : p.ksplit;
+}
+
+// g: geometry of the forward-form conv whose output grid carries `gmat` (channels Ca = g.Nc) and whose input view
+// carries `x` (channels Cb = g.K);  dw torch layout [(a*Cb + b)*KK + tap]
+int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, int KK, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
+        attr_set = true;
+    }
+    WgParams p;
+    if (int rc = wg_plan(g, KK, p)) return rc;
+    p.dw = dw;
+    p.packed = packed;
+    const Prob& pb = g.prob[0];
     long long offs[4]; int nmaps = 0;
     for (int t = 0; t < pb.ntaps; ++t) {
         const Tap& tp = pb.taps[t];
@@ -243,8 +326,19 @@ int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw
     int rc = make_act_map(&p.g_map, gb, p.Ca, g.OW, g.OH, g.N, g.o_sx, g.o_sy, g.o_sn, p.BW, p.BH, p.BNI, p.cwg);
     if (rc) return rc;
 
+    if (packed) {
+        rc = make_f32_2d_map(&p.dw_map, dw, p.Ca, (long long)KK * p.Cb, p.n_tile < 32 ? p.n_tile : 32, p.cwx);
+        if (rc) return rc;
+    }
+
     int grid = p.ngroups * p.n_tiles * p.ksplit;
+    static const bool prof_on = getenv("SVRS_WG_PROF") != nullptr;
+    if (prof_on) {
+        cudaMalloc(&p.prof, sizeof(long long) * 8 * grid);
+        cudaMemset(p.prof, 0, sizeof(long long) * 8 * grid);
+    }
     wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(p);
+    if (prof_on) wg_prof_report(p, grid, p.prof);
     return check_launch("wgrad_tc_kernel");
 }
 

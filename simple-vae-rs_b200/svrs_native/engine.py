@@ -210,7 +210,21 @@ class Runtime:
         self._unpack_key = None
         self.scratch_prezeroed = False   # the fused step zeroes all BatchNorm scratch once per step
         self.packs_dirty = True
-        self.launches = 0          # kernels enqueued (our own), for bench.py's gpu_launches
+        self._replayed = 0         # kernels re-issued by CUDA-graph replays (not seen by the library's own counter)
+
+    # kernels of libsvrs_b200.so enqueued so far (bench.py's gpu_launches): the library counts every launch site itself
+    # (svrs_launch_count); graph replays add the number of kernels captured in the graph.  The `+= n` bookkeeping at the
+    # call sites is kept as documentation of what each call enqueues but no longer feeds the number.
+    @property
+    def launches(self) -> int:
+        return int(lib.launch_count()) + self._replayed
+
+    @launches.setter
+    def launches(self, _v):
+        pass
+
+    def add_replayed(self, n: int):
+        self._replayed += int(n)
 
     # -------------------------------------------------------------------------------------- setup
     @property

@@ -37,7 +37,7 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     src = re.sub(r"//[^\n]*", " ", src)
     protos = {}
-    for m in re.finditer(r"(const\s+char\s*\*|int|void)\s+(svrs_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(const\s+char\s*\*|int64_t|int|void)\s+(svrs_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         arglist = []
         args = " ".join(args.split())
@@ -76,7 +76,7 @@ class _Lib:
         for name, (ret, args) in self.protos.items():
             fn = getattr(dll, name)  # AttributeError => header/library mismatch, fail loudly
             fn.argtypes = [_ctype(t) for t, _ in args]
-            fn.restype = ctypes.c_char_p if ret == "char*" else (None if ret == "void" else ctypes.c_int)
+            fn.restype = {"char*": ctypes.c_char_p, "void": None, "int64_t": ctypes.c_int64}.get(ret, ctypes.c_int)
         self._dll = dll
         return dll
 
@@ -89,7 +89,7 @@ class _Lib:
         if full not in self.protos:
             raise AttributeError(name)
         fn = getattr(self.load(), full)
-        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run", "svrs_pack_job_bytes"):
+        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run", "svrs_pack_job_bytes", "svrs_launch_count"):
             setattr(self, name, fn)
             return fn
 
@@ -101,10 +101,14 @@ class _Lib:
                     # a short device-side spin ahead of the bracket hides the host launch latency of the timed kernel,
                     # so e0 -> e1 is pure device time even for microsecond kernels
                     torch.cuda._sleep(self.timing_pad_cycles)
+                dll = self.load()
+                dll.svrs_trace_reset(1)
                 e0.record()
                 rc = _fn(*a)
                 e1.record()
-                self.timing.append((_n, a, e0, e1))
+                kernels = dll.svrs_trace().decode()
+                dll.svrs_trace_reset(0)
+                self.timing.append((_n, a, e0, e1, kernels))
             else:
                 rc = _fn(*a)
             if rc != 0:

@@ -40,11 +40,16 @@ torch.cuda.synchronize()
 rec, lib.timing = lib.timing, None
 names = {n: [an for _, an in args] for n, (_, args) in lib.protos.items()}
 agg = defaultdict(lambda: [0.0, 0, 0.0])
-for name, args, e0, e1 in rec:
+bykern = defaultdict(lambda: [0.0, 0, 0.0])
+for name, args, e0, e1, kernels in rec:
+    kk = bykern[kernels or name]
+    kk[0] += e0.elapsed_time(e1) / steps
+    kk[1] += 1
+    kk[2] += prof._flops(name, args) / steps
     d = dict(zip(names[name], args))
     key = name.replace("svrs_", "")
     if "conv" in name:
-        key += f" N{d['N']} {d['H']}x{d['W']} {d['Cin']}->{d['Cout']}" + (f" k{d['ksize']}" if "ksize" in d else "")
+        key += f" N{d['N']} {d['H']}x{d['W']} {d['Cin']}->{d['Cout']}" + (f" k{d['ksize']}" if "ksize" in d else "") + f" [{kernels}]"
     elif "M" in d and "C" in d:
         key += f" M{d['M']} C{d['C']}"
     r = agg[key]
@@ -57,9 +62,13 @@ for k, (ms, n, fl) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:a.top]:
     tf = fl / (ms * 1e-3) / 1e12 if ms > 0 and fl > 0 else 0
     print(f"{ms:8.3f} ms {100 * ms / tot:5.1f}%  x{n // steps:<3d} {tf:7.1f} TF/s  {k}")
 byfn = defaultdict(lambda: [0.0, 0])
-for name, args, e0, e1 in rec:
+for name, args, e0, e1, _k in rec:
     byfn[name.replace("svrs_", "")][0] += e0.elapsed_time(e1) / steps
     byfn[name.replace("svrs_", "")][1] += 1
+print("---- by kernel (library launch trace)")
+for k, (ms, n, fl) in sorted(bykern.items(), key=lambda kv: -kv[1][0]):
+    tf = fl / (ms * 1e-3) / 1e12 if ms > 0 and fl > 0 else 0
+    print(f"{ms:8.3f} ms {100 * ms / tot:5.1f}%  x{n // steps:<3d} {tf:7.1f} TF/s  {k}")
 print("---- by C-ABI function")
 for k, (ms, n) in sorted(byfn.items(), key=lambda kv: -kv[1][0]):
     print(f"{ms:8.3f} ms {100 * ms / tot:5.1f}%  x{n // steps:<3d} {k}")
@@ -71,7 +80,7 @@ if os.environ.get("SVRS_REPLAY", "0") == "1":
     reps = 8
     table = []
     side = torch.cuda.Stream()
-    for name, args, _, _ in first:
+    for name, args, _, _, _k in first:
         fn = getattr(lib, name.replace("svrs_", ""))
         args = list(args)
         with torch.cuda.stream(side):
@@ -92,7 +101,7 @@ if os.environ.get("SVRS_REPLAY", "0") == "1":
         d = dict(zip(names[name], args))
         key = name.replace("svrs_", "")
         if "conv" in name:
-            key += f" N{d['N']} {d['H']}x{d['W']} {d['Cin']}->{d['Cout']}" + (f" k{d['ksize']}" if "ksize" in d else "")
+            key += f" N{d['N']} {d['H']}x{d['W']} {d['Cin']}->{d['Cout']}" + (f" k{d['ksize']}" if "ksize" in d else "") + f" [{kernels}]"
         elif "M" in d and "C" in d:
             key += f" M{d['M']} C{d['C']}"
         table.append((e0.elapsed_time(e1) / reps, key, prof._flops(name, tuple(args))))
