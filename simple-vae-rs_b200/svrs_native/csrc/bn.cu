@@ -5,37 +5,70 @@
 
 namespace svrs {
 
-// thread t owns channel quad (t % cg) and row lane (t / cg); cg = C/4 divides 256.
-template <typename T, bool BWD>
+// 16-byte vector access: V = 4 floats or 8 bf16 (V = 4 bf16 = 8 bytes only when C is not a multiple of 8).
+template <int V> __device__ __forceinline__ void ldv(const float* p, float* o) {
+    static_assert(V == 4, "fp32 vectors are 4 wide");
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <int V> __device__ __forceinline__ void ldv(const __nv_bfloat16* p, float* o) {
+    if (V == 8) {
+        uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { o[2 * j] = __uint_as_float(w[j] << 16); o[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+    } else {
+        uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+        const uint32_t w[2] = {r.x, r.y};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { o[2 * j] = __uint_as_float(w[j] << 16); o[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+    }
+}
+template <int V> __device__ __forceinline__ void stv(float* p, const float* o) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+}
+template <int V> __device__ __forceinline__ void stv(__nv_bfloat16* p, const float* o) {
+    uint32_t w[V / 2];
+#pragma unroll
+    for (int j = 0; j < V / 2; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    if (V == 8) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[V / 2 - 2], w[V / 2 - 1]);
+    else *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+}
+
+// thread t owns channel group (t % cg) of V channels and row lane (t / cg); cg = C/V divides 256.  Four rows are loaded
+// per trip so every thread keeps 4 (forward) or 8 (backward) 16-byte loads in flight - these kernels are pure streaming.
+template <typename T, int V, bool BWD>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                          long long M, int C, long long rows_per_block,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
                                                          int relu, double* __restrict__ sums) {
-    __shared__ double red[256][8];
-    const int cg = C / 4;
+    constexpr int U = 4;
+    __shared__ double red[256 * 8];
+    const int cg = C / V;
     const int q = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = 256 / cg;
-    const int c = q * 4;
+    const int c = q * V;
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     long long r1 = r0 + rows_per_block;
     if (r1 > M) r1 = M;
-    double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
-    float sc[4], sh[4], mu[4], is[4];
+    double s0[V], s1[V];
+    float sc[V], sh[V], mu[V], is[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { s0[j] = 0; s1[j] = 0; }
     if (BWD) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j]; }
+        for (int j = 0; j < V; ++j) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j]; }
     }
-    for (long long r = r0 + lane; r < r1; r += lanes) {
-        float4 xv = ld4(x + r * C + c);
-        float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    auto accumulate = [&](const float* xs, const float* gs) {
         if (!BWD) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { s0[j] += (double)xs[j]; s1[j] += (double)xs[j] * (double)xs[j]; }
+            for (int j = 0; j < V; ++j) { s0[j] += (double)xs[j]; s1[j] += (double)xs[j] * (double)xs[j]; }
         } else {
-            float4 gv = ld4(dy + r * C + c);
-            float gs[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < V; ++j) {
                 float g = gs[j];
                 if (relu && !(fmaf(xs[j], sc[j], sh[j]) > 0.f)) g = 0.f;
                 float xh = (xs[j] - mu[j]) * is[j];
@@ -43,18 +76,38 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x,
                 s1[j] += (double)g * (double)xh;
             }
         }
+    };
+    long long r = r0 + lane;
+    for (; r + (long long)(U - 1) * lanes < r1; r += (long long)U * lanes) {
+        float xs[U][V], gs[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ldv<V>(x + (r + (long long)u * lanes) * C + c, xs[u]);
+            if (BWD) ldv<V>(dy + (r + (long long)u * lanes) * C + c, gs[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) accumulate(xs[u], gs[u]);
     }
+    for (; r < r1; r += lanes) {
+        float xs[V], gs[V];
+        ldv<V>(x + r * C + c, xs);
+        if (BWD) ldv<V>(dy + r * C + c, gs);
+        accumulate(xs, gs);
+    }
+    // cross-lane reduction, one statistic at a time (256 x 8 doubles of shared memory)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { red[threadIdx.x][j] = s0[j]; red[threadIdx.x][4 + j] = s1[j]; }
-    __syncthreads();
-    if (lane == 0) {
-        for (int l = 1; l < lanes; ++l)
+    for (int half = 0; half < 2; ++half) {
+        __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { s0[j] += red[l * cg + q][j]; s1[j] += red[l * cg + q][4 + j]; }
+        for (int j = 0; j < V; ++j) red[threadIdx.x * V + j] = half ? s1[j] : s0[j];
+        __syncthreads();
+        if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            atomicAdd(&sums[c + j], s0[j]);
-            atomicAdd(&sums[C + c + j], s1[j]);
+            for (int j = 0; j < V; ++j) {
+                double acc = 0;
+                for (int l = 0; l < lanes; ++l) acc += red[(l * cg + q) * V + j];
+                atomicAdd(&sums[half * C + c + j], acc);
+            }
         }
     }
 }
@@ -103,21 +156,38 @@ __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, 
     shift[c] = (beta ? beta[c] : 0.f) - rmean[c] * sc;
 }
 
-template <typename T>
+// The grid stride (gridDim * 256 vectors) is a multiple of cg, so a thread's channel group never changes: its per-channel
+// coefficients are loaded once.  Two vectors per trip for memory-level parallelism.
+template <typename T, int V>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec, int cg,
                                                         const float* __restrict__ scale, const float* __restrict__ shift, int relu) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % cg) * 4;
-        float4 v = ld4(x + i * 4);
-        float4 sc = *reinterpret_cast<const float4*>(scale + c);
-        float4 sh = *reinterpret_cast<const float4*>(shift + c);
-        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        st4(y + i * 4, v);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(i % cg) * V;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; }
+    auto apply = [&](float* v) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { v[j] = fmaf(v[j], sc[j], sh[j]); if (relu) v[j] = fmaxf(v[j], 0.f); }
+    };
+    for (; i + stride < nvec; i += 2 * stride) {
+        float a[V], b[V];
+        ldv<V>(x + i * V, a);
+        ldv<V>(x + (i + stride) * V, b);
+        apply(a); apply(b);
+        stv<V>(y + i * V, a);
+        stv<V>(y + (i + stride) * V, b);
+    }
+    if (i < nvec) {
+        float a[V];
+        ldv<V>(x + i * V, a);
+        apply(a);
+        stv<V>(y + i * V, a);
     }
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
                                                             long long nvec, int cg, long long M, int C,
                                                             const float* __restrict__ scale, const float* __restrict__ shift,
@@ -132,33 +202,53 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
         }
     }
     const float invM = 1.0f / (float)M;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % cg) * 4;
-        float4 xv = ld4(x + i * 4);
-        float4 gv = ld4(dy + i * 4);
-        float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-        float gs[4] = {gv.x, gv.y, gv.z, gv.w};
-        float o[4];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(i % cg) * V;
+    float sc[V], sh[V], mu[V], is[V], mg[V], mgx[V], gi[V];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V; ++j) {
+        sc[j] = scale[c + j]; sh[j] = shift[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j];
+        mg[j] = (float)sums[c + j] * invM;
+        mgx[j] = (float)sums[C + c + j] * invM;
+        gi[j] = (gamma ? gamma[c + j] : 1.f) * is[j];
+    }
+    auto apply = [&](const float* xs, float* gs) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
             float g = gs[j];
-            if (relu && !(fmaf(xs[j], scale[c + j], shift[c + j]) > 0.f)) g = 0.f;
-            float xh = (xs[j] - mean[c + j]) * invstd[c + j];
-            float mg = (float)sums[c + j] * invM;
-            float mgx = (float)sums[C + c + j] * invM;
-            float gam = gamma ? gamma[c + j] : 1.f;
-            o[j] = gam * invstd[c + j] * (g - mg - xh * mgx);
+            if (relu && !(fmaf(xs[j], sc[j], sh[j]) > 0.f)) g = 0.f;
+            float xh = (xs[j] - mu[j]) * is[j];
+            gs[j] = gi[j] * (g - mg[j] - xh * mgx[j]);
         }
-        st4(dx + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+    };
+    for (; i + stride < nvec; i += 2 * stride) {
+        float xa[V], ga[V], xb[V], gb[V];
+        ldv<V>(x + i * V, xa);
+        ldv<V>(dy + i * V, ga);
+        ldv<V>(x + (i + stride) * V, xb);
+        ldv<V>(dy + (i + stride) * V, gb);
+        apply(xa, ga); apply(xb, gb);
+        stv<V>(dx + i * V, ga);
+        stv<V>(dx + (i + stride) * V, gb);
+    }
+    if (i < nvec) {
+        float xa[V], ga[V];
+        ldv<V>(x + i * V, xa);
+        ldv<V>(dy + i * V, ga);
+        apply(xa, ga);
+        stv<V>(dx + i * V, ga);
     }
 }
 
 static bool c_ok(int C) { return C >= 4 && C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0; }
+// bf16 with C % 8 == 0 moves 8 channels (16 bytes) per access
+static bool wide(int dtype, int C) { return dtype == SVRS_BF16 && C % 8 == 0 && 256 % (C / 8) == 0; }
 
-static void reduce_grid(long long M, int C, unsigned& blocks, long long& rpb) {
-    int lanes = 256 / (C / 4);
-    long long b = (M + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
-    long long cap = 4LL * num_sms();
+static void reduce_grid(long long M, int C, int V, unsigned& blocks, long long& rpb) {
+    int lanes = 256 / (C / V);
+    long long b = (M + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
+    long long cap = 8LL * num_sms();
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     rpb = (M + b - 1) / b;
@@ -179,12 +269,15 @@ using namespace svrs;
 extern "C" int svrs_bn_stats(const void* x, int dtype, int64_t M, int C, double* sums, void* stream) {
     SVRS_CHECK_ARG(x && sums && M > 0 && c_ok(C), "bn_stats: bad args (C=%d must be 4*2^k <= 1024)", C);
     unsigned blocks; long long rpb;
-    reduce_grid(M, C, blocks, rpb);
+    const bool w8 = wide(dtype, C);
+    reduce_grid(M, C, w8 ? 8 : 4, blocks, rpb);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        bn_reduce_kernel<float, false><<<blocks, 256, 0, st>>>((const float*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
+        bn_reduce_kernel<float, 4, false><<<blocks, 256, 0, st>>>((const float*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
+    else if (dtype == SVRS_BF16 && w8)
+        bn_reduce_kernel<__nv_bfloat16, 8, false><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
     else if (dtype == SVRS_BF16)
-        bn_reduce_kernel<__nv_bfloat16, false><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
+        bn_reduce_kernel<__nv_bfloat16, 4, false><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
     else { set_error("bn_stats: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_stats");
 }
@@ -210,13 +303,16 @@ extern "C" int svrs_bn_finalize_eval(int C, const float* gamma, const float* bet
 
 extern "C" int svrs_bn_apply(const void* x, void* y, int dtype, int64_t M, int C, const float* scale,
                              const float* shift, int relu, void* stream) {
-    SVRS_CHECK_ARG(x && y && scale && shift && M > 0 && C % 4 == 0, "bn_apply: bad args");
-    long long nvec = M * C / 4;
+    SVRS_CHECK_ARG(x && y && scale && shift && M > 0 && c_ok(C), "bn_apply: bad args (C=%d must be 4*2^k <= 1024)", C);
+    const bool w8 = wide(dtype, C);
+    long long nvec = M * C / (w8 ? 8 : 4);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        bn_apply_kernel<float><<<ew_grid(nvec), 256, 0, st>>>((const float*)x, (float*)y, nvec, C / 4, scale, shift, relu);
+        bn_apply_kernel<float, 4><<<ew_grid(nvec), 256, 0, st>>>((const float*)x, (float*)y, nvec, C / 4, scale, shift, relu);
+    else if (dtype == SVRS_BF16 && w8)
+        bn_apply_kernel<__nv_bfloat16, 8><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 8, scale, shift, relu);
     else if (dtype == SVRS_BF16)
-        bn_apply_kernel<__nv_bfloat16><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 4, scale, shift, relu);
+        bn_apply_kernel<__nv_bfloat16, 4><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 4, scale, shift, relu);
     else { set_error("bn_apply: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_apply");
 }
@@ -226,12 +322,15 @@ extern "C" int svrs_bn_bwd_reduce(const void* x, const void* dy, int dtype, int6
                                   double* sums, void* stream) {
     SVRS_CHECK_ARG(x && dy && sums && scale && shift && mean && invstd && M > 0 && c_ok(C), "bn_bwd_reduce: bad args");
     unsigned blocks; long long rpb;
-    reduce_grid(M, C, blocks, rpb);
+    const bool w8 = wide(dtype, C);
+    reduce_grid(M, C, w8 ? 8 : 4, blocks, rpb);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        bn_reduce_kernel<float, true><<<blocks, 256, 0, st>>>((const float*)x, (const float*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
+        bn_reduce_kernel<float, 4, true><<<blocks, 256, 0, st>>>((const float*)x, (const float*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
+    else if (dtype == SVRS_BF16 && w8)
+        bn_reduce_kernel<__nv_bfloat16, 8, true><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
     else if (dtype == SVRS_BF16)
-        bn_reduce_kernel<__nv_bfloat16, true><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
+        bn_reduce_kernel<__nv_bfloat16, 4, true><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
     else { set_error("bn_bwd_reduce: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_bwd_reduce");
 }
@@ -240,13 +339,16 @@ extern "C" int svrs_bn_bwd_apply(const void* x, const void* dy, void* dx, int dt
                                  const float* scale, const float* shift, const float* mean, const float* invstd,
                                  const float* gamma, int relu, const double* sums, float* dgamma, float* dbeta,
                                  void* stream) {
-    SVRS_CHECK_ARG(x && dy && dx && sums && scale && shift && mean && invstd && M > 0 && C % 4 == 0, "bn_bwd_apply: bad args");
-    long long nvec = M * C / 4;
+    SVRS_CHECK_ARG(x && dy && dx && sums && scale && shift && mean && invstd && M > 0 && c_ok(C), "bn_bwd_apply: bad args");
+    const bool w8 = wide(dtype, C);
+    long long nvec = M * C / (w8 ? 8 : 4);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        bn_bwd_apply_kernel<float><<<ew_grid(nvec), 256, 0, st>>>((const float*)x, (const float*)dy, (float*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
+        bn_bwd_apply_kernel<float, 4><<<ew_grid(nvec), 256, 0, st>>>((const float*)x, (const float*)dy, (float*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
+    else if (dtype == SVRS_BF16 && w8)
+        bn_bwd_apply_kernel<__nv_bfloat16, 8><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 8, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
     else if (dtype == SVRS_BF16)
-        bn_bwd_apply_kernel<__nv_bfloat16><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
+        bn_bwd_apply_kernel<__nv_bfloat16, 4><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
     else { set_error("bn_bwd_apply: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_bwd_apply");
 }

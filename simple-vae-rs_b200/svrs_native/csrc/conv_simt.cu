@@ -505,6 +505,118 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad for the 4 <-> 16 and 4 <-> 4 channel layers (the image-side ends of every sub-network at full resolution).
+// One WARP per tap (TPW taps per warp for the 4x4 case), lanes = 32 consecutive output pixels, so a warp reads its G and
+// X vectors fully coalesced and a thread keeps the whole CA x CB outer-product tile of its tap(s) in registers: per
+// pixel it issues 1-2 vector loads per operand and CA*CB FMAs - no shared memory, no per-pixel 64-bit index math (the
+// image index is uniform per 32-pixel group).  The nine / sixteen warps of a CTA walk the same pixels, so all but the
+// first tap's loads hit L1.  Lanes are folded with shuffles at the end; one atomic per output per CTA.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int C> __device__ __forceinline__ void load_chan(const T* p, float* o);
+template <> __device__ __forceinline__ void load_chan<float, 4>(const float* p, float* o) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void load_chan<float, 16>(const float* p, float* o) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) load_chan<float, 4>(p + 4 * i, o + 4 * i);
+}
+template <> __device__ __forceinline__ void load_chan<__nv_bfloat16, 4>(const __nv_bfloat16* p, float* o) {
+    uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    o[0] = __uint_as_float(r.x << 16); o[1] = __uint_as_float(r.x & 0xffff0000u);
+    o[2] = __uint_as_float(r.y << 16); o[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void load_chan<__nv_bfloat16, 16>(const __nv_bfloat16* p, float* o) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint4 r = __ldg(reinterpret_cast<const uint4*>(p) + h);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { o[8 * h + 2 * j] = __uint_as_float(w[j] << 16); o[8 * h + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+    }
+}
+
+template <typename T, int CA, int CB, int TPW>
+__global__ void __launch_bounds__(512, 1) wgrad_narrow_kernel(const __grid_constant__ WgradArgs a) {
+    __shared__ float red[16][TPW * CA * CB];
+    const TapGeom& g = a.g;
+    const Prob& pb = g.prob[0];
+    const T* __restrict__ G = reinterpret_cast<const T*>(a.gmat) + pb.out_off;
+    const T* __restrict__ X = reinterpret_cast<const T*>(a.x);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = warp * TPW;
+    Tap tp[TPW];
+    bool tap_ok[TPW];
+#pragma unroll
+    for (int j = 0; j < TPW; ++j) { tap_ok[j] = t0 + j < pb.ntaps; tp[j] = pb.taps[tap_ok[j] ? t0 + j : 0]; }
+    float acc[TPW][CA][CB];
+#pragma unroll
+    for (int j = 0; j < TPW; ++j)
+#pragma unroll
+        for (int ia = 0; ia < CA; ++ia)
+#pragma unroll
+            for (int ib = 0; ib < CB; ++ib) acc[j][ia][ib] = 0.f;
+    const int ohw = g.OH * g.OW;
+    const int groups = g.N * (ohw / 32);          // 32-pixel groups; ohw % 32 == 0 (checked by the launcher)
+    for (int gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+        const int m0 = gi * 32;
+        const int n = m0 / ohw;
+        const int r = m0 - n * ohw + lane;
+        const int oy = r / g.OW, ox = r - oy * g.OW;
+        float gv[CA];
+        load_chan<T, CA>(G + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx, gv);
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) {
+            const int iy = oy + tp[j].dy, ix = ox + tp[j].dx;
+            float xv[CB];
+#pragma unroll
+            for (int ib = 0; ib < CB; ++ib) xv[ib] = 0.f;
+            if (tap_ok[j] && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW)
+                load_chan<T, CB>(X + tp[j].in_off + (long long)n * g.i_sn + (long long)iy * g.i_sy + (long long)ix * g.i_sx, xv);
+#pragma unroll
+            for (int ia = 0; ia < CA; ++ia)
+#pragma unroll
+                for (int ib = 0; ib < CB; ++ib) acc[j][ia][ib] = fmaf(gv[ia], xv[ib], acc[j][ia][ib]);
+        }
+    }
+    // fold the 32 lanes; lane 0 parks the warp's tile in shared memory, then the warp issues its atomics in parallel
+#pragma unroll
+    for (int j = 0; j < TPW; ++j)
+#pragma unroll
+        for (int ia = 0; ia < CA; ++ia)
+#pragma unroll
+            for (int ib = 0; ib < CB; ++ib) {
+                float v = acc[j][ia][ib];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[warp][(j * CA + ia) * CB + ib] = v;
+            }
+    __syncwarp();
+    for (int e = lane; e < TPW * CA * CB; e += 32) {
+        const int ib = e % CB, ia = (e / CB) % CA, j = e / (CA * CB);
+        if (t0 + j < pb.ntaps) atomicAdd(&a.dw[((long long)ia * CB + ib) * a.KK + t0 + j], red[warp][e]);
+    }
+}
+
+// true (and launched) when the shape is one of the narrow forms
+template <typename T>
+static bool try_launch_wgrad_narrow(const WgradArgs& a, cudaStream_t st, int& rc) {
+    const TapGeom& g = a.g;
+    const int Ca = g.Nc, Cb = g.K, ntaps = g.prob[0].ntaps;
+    const long long ohw = (long long)g.OH * g.OW;
+    if (g.nprob != 1 || ohw % 32 != 0 || (long long)g.N * ohw >= (1ll << 31) || ntaps > 16) return false;
+    const int groups = (int)((long long)g.N * ohw / 32);
+    const int warps = (Ca == 4 && Cb == 4) ? (ntaps + 3) / 4 : ntaps;
+    int grid = num_sms() * (warps >= 8 ? 1 : 16 / warps);          // ~16 resident warps per SM (100-120 registers each)
+    if (grid > groups) grid = groups;
+    if (Ca == 4 && Cb == 16) wgrad_narrow_kernel<T, 4, 16, 1><<<grid, 32 * ntaps, 0, st>>>(a);
+    else if (Ca == 16 && Cb == 4) wgrad_narrow_kernel<T, 16, 4, 1><<<grid, 32 * ntaps, 0, st>>>(a);
+    else if (Ca == 4 && Cb == 4) wgrad_narrow_kernel<T, 4, 4, 4><<<grid, 32 * ((ntaps + 3) / 4), 0, st>>>(a);
+    else return false;
+    rc = check_launch("wgrad_narrow_kernel");
+    return true;
+}
+
 template <typename T>
 static int launch_wgrad_direct(const WgradArgs& a, cudaStream_t st) {
     const TapGeom& g = a.g;
@@ -534,6 +646,8 @@ static int launch_wgrad(WgradArgs& a, int dtype, int ksplit, cudaStream_t st) {
     if (M == 0) return 0;
     if ((g.Nc <= 16 || g.K <= 16) && ksplit <= 0) {
         a.ksplit = 1;
+        int rc = 0;
+        if (dtype == SVRS_F32 ? try_launch_wgrad_narrow<float>(a, st, rc) : try_launch_wgrad_narrow<__nv_bfloat16>(a, st, rc)) return rc;
         return dtype == SVRS_F32 ? launch_wgrad_direct<float>(a, st) : launch_wgrad_direct<__nv_bfloat16>(a, st);
     }
     int tiles = ((g.Nc + 63) / 64) * ((g.K + 63) / 64);

@@ -22,6 +22,8 @@ CONV_CASES = [
     (3, 6, 10, 5, 7),        # odd channel counts + non-square: scalar load paths
     (1, 4, 4, 128, 64),
     (2, 16, 16, 4, 4),       # first layers of every encoder
+    (3, 16, 16, 16, 4),      # image-side ends: narrow wgrad kernel (one warp per tap)
+    (2, 16, 32, 4, 16),
     (2, 8, 8, 64, 16),
     (1, 4, 4, 42, 84),       # cr = 1.5 channel counts
     (5, 2, 2, 8, 130),
