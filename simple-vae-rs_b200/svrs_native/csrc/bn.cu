@@ -62,6 +62,12 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x,
 #pragma unroll
         for (int j = 0; j < V; ++j) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j]; }
     }
+    // Backward sums (sum g, sum g*xhat): fp32 partials over at most 16 rows folded into the double accumulators.  The
+    // forward statistics stay in double per element: var = E[x^2] - E[x]^2 amplifies any rounding of E[x^2] by
+    // mean^2/var, and fp32 partial sums measurably broke fp32 gradient parity (1e-3) on channels with |mean| >> std.
+    float p0[V], p1[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { p0[j] = 0.f; p1[j] = 0.f; }
     auto accumulate = [&](const float* xs, const float* gs) {
         if (!BWD) {
 #pragma unroll
@@ -72,12 +78,17 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x,
                 float g = gs[j];
                 if (relu && !(fmaf(xs[j], sc[j], sh[j]) > 0.f)) g = 0.f;
                 float xh = (xs[j] - mu[j]) * is[j];
-                s0[j] += (double)g;
-                s1[j] += (double)g * (double)xh;
+                p0[j] += g;
+                p1[j] = fmaf(g, xh, p1[j]);
             }
         }
     };
+    auto fold = [&]() {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { s0[j] += (double)p0[j]; s1[j] += (double)p1[j]; p0[j] = 0.f; p1[j] = 0.f; }
+    };
     long long r = r0 + lane;
+    int trips = 0;
     for (; r + (long long)(U - 1) * lanes < r1; r += (long long)U * lanes) {
         float xs[U][V], gs[U][V];
 #pragma unroll
@@ -87,6 +98,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x,
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) accumulate(xs[u], gs[u]);
+        if ((++trips & 3) == 0) fold();
     }
     for (; r < r1; r += lanes) {
         float xs[V], gs[V];
@@ -94,6 +106,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x,
         if (BWD) ldv<V>(dy + r * C + c, gs);
         accumulate(xs, gs);
     }
+    fold();
     // cross-lane reduction, one statistic at a time (256 x 8 doubles of shared memory)
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -248,7 +261,9 @@ static bool wide(int dtype, int C) { return dtype == SVRS_BF16 && C % 8 == 0 && 
 static void reduce_grid(long long M, int C, int V, unsigned& blocks, long long& rpb) {
     int lanes = 256 / (C / V);
     long long b = (M + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
-    long long cap = 8LL * num_sms();
+    // every block ends with 2C double atomics on the same few cache lines: keep the block count low (measured: with
+    // 8 blocks per SM the same-line atomics, not the streaming loop, set the kernel time)
+    long long cap = 2LL * num_sms();
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     rpb = (M + b - 1) / b;

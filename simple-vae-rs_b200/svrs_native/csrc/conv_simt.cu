@@ -3,6 +3,7 @@
 // whose channel counts are too small / odd for the tcgen05 kernel (Cin or Cout in {4, 16}, cr != 2).
 // Accumulation is always fp32; T is the storage type of activations and packed weights.
 #include "common.cuh"
+#include <stdlib.h>
 #include "taps.cuh"
 
 namespace svrs {
@@ -513,28 +514,30 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(const __grid_constant
 // image index is uniform per 32-pixel group).  The nine / sixteen warps of a CTA walk the same pixels, so all but the
 // first tap's loads hit L1.  Lanes are folded with shuffles at the end; one atomic per output per CTA.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int C> __device__ __forceinline__ void load_chan(const T* p, float* o);
-template <> __device__ __forceinline__ void load_chan<float, 4>(const float* p, float* o) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-}
-template <> __device__ __forceinline__ void load_chan<float, 16>(const float* p, float* o) {
+// raw (unconverted) channel vectors: NW 32-bit words, loaded with the widest access that fits
+template <int NW> __device__ __forceinline__ void load_raw(const void* p, uint32_t* w) {
+    if (NW == 2) { uint2 r = __ldg(reinterpret_cast<const uint2*>(p)); w[0] = r.x; w[1] = r.y; }
+    else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) load_chan<float, 4>(p + 4 * i, o + 4 * i);
-}
-template <> __device__ __forceinline__ void load_chan<__nv_bfloat16, 4>(const __nv_bfloat16* p, float* o) {
-    uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
-    o[0] = __uint_as_float(r.x << 16); o[1] = __uint_as_float(r.x & 0xffff0000u);
-    o[2] = __uint_as_float(r.y << 16); o[3] = __uint_as_float(r.y & 0xffff0000u);
-}
-template <> __device__ __forceinline__ void load_chan<__nv_bfloat16, 16>(const __nv_bfloat16* p, float* o) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        uint4 r = __ldg(reinterpret_cast<const uint4*>(p) + h);
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { o[8 * h + 2 * j] = __uint_as_float(w[j] << 16); o[8 * h + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+        for (int i = 0; i < NW / 4; ++i) {
+            uint4 r = __ldg(reinterpret_cast<const uint4*>(p) + i);
+            w[4 * i] = r.x; w[4 * i + 1] = r.y; w[4 * i + 2] = r.z; w[4 * i + 3] = r.w;
+        }
     }
 }
+template <typename T, int C> __device__ __forceinline__ void raw_to_float(const uint32_t* w, float* o);
+template <int C> __device__ __forceinline__ void raw_to_float_f32(const uint32_t* w, float* o) {
+#pragma unroll
+    for (int i = 0; i < C; ++i) o[i] = __uint_as_float(w[i]);
+}
+template <> __device__ __forceinline__ void raw_to_float<float, 4>(const uint32_t* w, float* o) { raw_to_float_f32<4>(w, o); }
+template <> __device__ __forceinline__ void raw_to_float<float, 16>(const uint32_t* w, float* o) { raw_to_float_f32<16>(w, o); }
+template <int C> __device__ __forceinline__ void raw_to_float_bf16(const uint32_t* w, float* o) {
+#pragma unroll
+    for (int i = 0; i < C / 2; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <> __device__ __forceinline__ void raw_to_float<__nv_bfloat16, 4>(const uint32_t* w, float* o) { raw_to_float_bf16<4>(w, o); }
+template <> __device__ __forceinline__ void raw_to_float<__nv_bfloat16, 16>(const uint32_t* w, float* o) { raw_to_float_bf16<16>(w, o); }
 
 template <typename T, int CA, int CB, int TPW>
 __global__ void __launch_bounds__(512, 1) wgrad_narrow_kernel(const __grid_constant__ WgradArgs a) {
@@ -558,26 +561,51 @@ __global__ void __launch_bounds__(512, 1) wgrad_narrow_kernel(const __grid_const
             for (int ib = 0; ib < CB; ++ib) acc[j][ia][ib] = 0.f;
     const int ohw = g.OH * g.OW;
     const int groups = g.N * (ohw / 32);          // 32-pixel groups; ohw % 32 == 0 (checked by the launcher)
-    for (int gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+    // Three pixel groups in flight per thread (raw, unconverted vectors: 10 registers per group for 4 x 16 bf16): with
+    // one 9..16-warp CTA per SM the loop would otherwise be exposed to the full L2 latency once per group.
+    constexpr int GW = CA * (int)sizeof(T) / 4, XW = CB * (int)sizeof(T) / 4;
+    struct Slot { uint32_t g[GW]; uint32_t x[TPW][XW]; };
+    auto issue = [&](int gi, Slot& sl) {
+#pragma unroll
+        for (int i = 0; i < GW; ++i) sl.g[i] = 0u;
+#pragma unroll
+        for (int j = 0; j < TPW; ++j)
+#pragma unroll
+            for (int i = 0; i < XW; ++i) sl.x[j][i] = 0u;
+        if (gi >= groups) return;
         const int m0 = gi * 32;
         const int n = m0 / ohw;
         const int r = m0 - n * ohw + lane;
         const int oy = r / g.OW, ox = r - oy * g.OW;
-        float gv[CA];
-        load_chan<T, CA>(G + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx, gv);
+        load_raw<GW>(G + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx, sl.g);
 #pragma unroll
         for (int j = 0; j < TPW; ++j) {
             const int iy = oy + tp[j].dy, ix = ox + tp[j].dx;
-            float xv[CB];
-#pragma unroll
-            for (int ib = 0; ib < CB; ++ib) xv[ib] = 0.f;
             if (tap_ok[j] && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW)
-                load_chan<T, CB>(X + tp[j].in_off + (long long)n * g.i_sn + (long long)iy * g.i_sy + (long long)ix * g.i_sx, xv);
+                load_raw<XW>(X + tp[j].in_off + (long long)n * g.i_sn + (long long)iy * g.i_sy + (long long)ix * g.i_sx, sl.x[j]);
+        }
+    };
+    auto compute = [&](const Slot& sl) {
+        float gv[CA];
+        raw_to_float<T, CA>(sl.g, gv);
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) {
+            float xv[CB];
+            raw_to_float<T, CB>(sl.x[j], xv);
 #pragma unroll
             for (int ia = 0; ia < CA; ++ia)
 #pragma unroll
                 for (int ib = 0; ib < CB; ++ib) acc[j][ia][ib] = fmaf(gv[ia], xv[ib], acc[j][ia][ib]);
         }
+    };
+    const int st = gridDim.x;
+    Slot s0, s1, s2;
+    issue(blockIdx.x, s0);
+    issue(blockIdx.x + st, s1);
+    for (int gi = blockIdx.x; gi < groups; gi += 3 * st) {
+        issue(gi + 2 * st, s2); compute(s0);
+        issue(gi + 3 * st, s0); compute(s1);
+        issue(gi + 4 * st, s1); compute(s2);
     }
     // fold the 32 lanes; lane 0 parks the warp's tile in shared memory, then the warp issues its atomics in parallel
 #pragma unroll
@@ -604,6 +632,8 @@ static bool try_launch_wgrad_narrow(const WgradArgs& a, cudaStream_t st, int& rc
     const TapGeom& g = a.g;
     const int Ca = g.Nc, Cb = g.K, ntaps = g.prob[0].ntaps;
     const long long ohw = (long long)g.OH * g.OW;
+    static const bool disabled = getenv("SVRS_NO_NARROW") != nullptr;
+    if (disabled) return false;
     if (g.nprob != 1 || ohw % 32 != 0 || (long long)g.N * ohw >= (1ll << 31) || ntaps > 16) return false;
     const int groups = (int)((long long)g.N * ohw / 32);
     const int warps = (Ca == 4 && Cb == 4) ? (ntaps + 3) / 4 : ntaps;
