@@ -24,6 +24,22 @@ template <int V> __device__ __forceinline__ void ldv(const __nv_bfloat16* p, flo
         for (int j = 0; j < 2; ++j) { o[2 * j] = __uint_as_float(w[j] << 16); o[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
     }
 }
+// raw 16-byte (or 8-byte) row fragments: kept unconverted while several loads are in flight (half the registers of floats)
+template <typename T, int V> struct RawVec { uint32_t w[V * sizeof(T) / 4]; };
+template <typename T, int V> __device__ __forceinline__ void ld_raw(const T* p, RawVec<T, V>& r) {
+    constexpr int NW = V * sizeof(T) / 4;
+    if (NW == 4) { uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[NW - 1] = v.w; }
+    else { uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); r.w[0] = v.x; r.w[1] = v.y; }
+}
+template <int V> __device__ __forceinline__ void raw_cvt(const RawVec<float, V>& r, float* o) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) o[j] = __uint_as_float(r.w[j]);
+}
+template <int V> __device__ __forceinline__ void raw_cvt(const RawVec<__nv_bfloat16, V>& r, float* o) {
+#pragma unroll
+    for (int j = 0; j < V / 2; ++j) { o[2 * j] = __uint_as_float(r.w[j] << 16); o[2 * j + 1] = __uint_as_float(r.w[j] & 0xffff0000u); }
+}
+
 template <int V> __device__ __forceinline__ void stv(float* p, const float* o) {
     *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
 }
@@ -41,7 +57,7 @@ template <int V> __device__ __forceinline__ void stv(__nv_bfloat16* p, const flo
 // thread t owns channel group (t % cg) of V channels and row lane (t / cg); cg = C/V divides 256.  Four rows are loaded
 // per trip so every thread keeps 4 (forward) or 8 (backward) 16-byte loads in flight - these kernels are pure streaming.
 template <typename T, int V, bool BWD>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                          long long M, int C, long long rows_per_block,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -90,14 +106,19 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ x,
     long long r = r0 + lane;
     int trips = 0;
     for (; r + (long long)(U - 1) * lanes < r1; r += (long long)U * lanes) {
-        float xs[U][V], gs[U][V];
+        RawVec<T, V> xr[U], gr[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            ldv<V>(x + (r + (long long)u * lanes) * C + c, xs[u]);
-            if (BWD) ldv<V>(dy + (r + (long long)u * lanes) * C + c, gs[u]);
+            ld_raw<T, V>(x + (r + (long long)u * lanes) * C + c, xr[u]);
+            if (BWD) ld_raw<T, V>(dy + (r + (long long)u * lanes) * C + c, gr[u]);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) accumulate(xs[u], gs[u]);
+        for (int u = 0; u < U; ++u) {
+            float xs[V], gs[V];
+            raw_cvt<V>(xr[u], xs);
+            if (BWD) raw_cvt<V>(gr[u], gs);
+            accumulate(xs, gs);
+        }
         if ((++trips & 3) == 0) fold();
     }
     for (; r < r1; r += lanes) {
@@ -260,7 +281,7 @@ static bool wide(int dtype, int C) { return dtype == SVRS_BF16 && C % 8 == 0 && 
 
 static void reduce_grid(long long M, int C, int V, unsigned& blocks, long long& rpb) {
     int lanes = 256 / (C / V);
-    long long b = (M + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
+    long long b = (M + (long long)lanes * 8 - 1) / ((long long)lanes * 8);       // >= 8 rows per thread
     // every block ends with 2C double atomics on the same few cache lines: keep the block count low (measured: with
     // 8 blocks per SM the same-line atomics, not the streaming loop, set the kernel time)
     long long cap = 2LL * num_sms();
@@ -270,8 +291,11 @@ static void reduce_grid(long long M, int C, int V, unsigned& blocks, long long& 
     blocks = (unsigned)((M + rpb - 1) / rpb);
 }
 
+// element-wise BN kernels: every thread first loads its V channels' coefficients (up to 56 scalar loads), so give each
+// thread >= 8 vectors of work where the tensor allows and cap the grid at 4 blocks per SM (measured: with 16 blocks per
+// SM the coefficient prologue, not the streaming loop, dominated the small layers)
 static unsigned ew_grid(long long n) {
-    long long b = (n + 255) / 256, cap = 16LL * num_sms();
+    long long b = (n + 256 * 8 - 1) / (256 * 8), cap = 4LL * num_sms();
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (unsigned)b;
