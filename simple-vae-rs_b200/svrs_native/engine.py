@@ -10,6 +10,7 @@ the reference's NCHW-flat fp32 order, which is also what the Python 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -211,6 +212,13 @@ class Runtime:
         self.scratch_prezeroed = False   # the fused step zeroes all BatchNorm scratch once per step
         self.packs_dirty = True
         self._replayed = 0         # kernels re-issued by CUDA-graph replays (not seen by the library's own counter)
+        # Weight gradients are leaves of the backward pass: they run on a side stream, concurrently with the
+        # dgrad -> BatchNorm chain of the main stream (most of them are small, latency-bound launches that leave SMs
+        # idle).  SVRS_WGRAD_STREAM=0 keeps everything on one stream.
+        self.wgrad_side = os.environ.get("SVRS_WGRAD_STREAM", "1") != "0"
+        self._side: Optional[torch.cuda.Stream] = None
+        self._side_busy = False
+        self._wg_keep: list = []   # operands of in-flight side-stream wgrads (kept alive until the join)
 
     # kernels of libsvrs_b200.so enqueued so far (bench.py's gpu_launches): the library counts every launch site itself
     # (svrs_launch_count); graph replays add the number of kernels captured in the graph.  The `+= n` bookkeeping at the
@@ -276,9 +284,29 @@ class Runtime:
         lib.fill_zero(_p(self.store.gpack), self.store.gpack.numel() * 4, _st())
         self.launches += 2
 
+    def _wgrad_stream(self, *operands) -> int:
+        """Stream handle for a weight-gradient launch whose operands were produced by work already enqueued on the
+        current stream.  The operands are kept alive until join_wgrads(): the caching allocator must not hand their
+        memory to a later main-stream allocation while the side stream still reads them."""
+        if not self.wgrad_side:
+            return _st()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(torch.cuda.current_stream())
+        self._side_busy = True
+        self._wg_keep.append(operands)
+        return self._side.cuda_stream
+
+    def join_wgrads(self):
+        if self._side_busy:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_busy = False
+        self._wg_keep.clear()
+
     def finish_grads(self):
         """Add the per-tap packed weight-gradient scratch of every conv layer into the torch-layout flat gradient
         (one launch).  Must run after the last net_backward of a step and before anything reads store.grad."""
+        self.join_wgrads()
         if self._unpack_jobs is None or self._unpack_key != (self.store.grad.data_ptr(), self.store.gpack.data_ptr()):
             import numpy as np
             convs = [op for net in self.nets for op in net.ops if isinstance(op, ConvOp)]
@@ -432,11 +460,12 @@ class Runtime:
                 dw = store.grad_ptr(op.mod.weight)
                 dwp = store.gpack_ptr(op.mod.weight)
                 db = store.grad_ptr(op.mod.bias) if op.mod.bias is not None else None
+                wst = self._wgrad_stream(x, dy)
                 if op.kind == "ct":
-                    lib.convT2d_wgrad(_p(x), _p(dy), dw, dwp, db, self.dt, n, h, w, op.cin, op.cout, 0, st)
+                    lib.convT2d_wgrad(_p(x), _p(dy), dw, dwp, db, self.dt, n, h, w, op.cin, op.cout, 0, wst)
                 else:
                     lib.conv2d_wgrad(_p(x), _p(dy), dw, dwp, db, self.dt, n, h, w, op.cin, op.cout,
-                                     3 if op.kind == "c3" else 4, 0, st)
+                                     3 if op.kind == "c3" else 4, 0, wst)
                 self.launches += 2
                 if idx > 0 or need_dx:
                     dx = torch.empty_like(x)

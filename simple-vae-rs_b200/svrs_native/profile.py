@@ -58,7 +58,11 @@ def dominant_kernel_roofline(tr, step_from_device, inputs, pk, steps: int = 2):
         else:
             tr.step(dataset.grid_patch_normalize(hr, P), use_graph=False)
 
-    per = time_step(eager, steps)
+    side, tr.rt.wgrad_side = tr.rt.wgrad_side, False      # per-call event brackets only see the current stream
+    try:
+        per = time_step(eager, steps)
+    finally:
+        tr.rt.wgrad_side = side
     fam = defaultdict(lambda: [0.0, 0.0, 0.0])
     total_ms = sum(v[0] for v in per.values())
     for (name, kernels), (ms, n, fl) in per.items():

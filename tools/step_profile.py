@@ -3,6 +3,7 @@
 """
 import argparse
 import os
+os.environ.setdefault("SVRS_WGRAD_STREAM", "0")   # per-call event brackets only see the current stream
 import sys
 from collections import defaultdict
 
