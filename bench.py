@@ -259,6 +259,13 @@ def main():
     try:
         from svrs_native import profile as prof
         roof = prof.dominant_kernel_roofline(tr, step_from_device, dev_sets[0], pk, steps=2)
+        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (tools/ncu_traffic.py)
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("kernel") and tj["kernel"] in roof.get("kernel", ""):
+                roof["traffic"] = tj["dram_bytes_per_launch"]
+                roof["traffic_source"] = "profiles/traffic_r01.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
     except Exception as ex:  # keep the headline number even if the profiling pass fails
         roof = {"error": repr(ex)}
 
