@@ -38,6 +38,7 @@ struct alignas(64) HaloParams {
     int N, OH, OW, tiles_x, tiles_y;
     int Nc, n_tile, n_tiles, kchunks;
     int act, resident, base_off_mode;
+    int cw;                         // channels per chunk: 64 / 32 / 16 (SWIZZLE_128B / 64B / 32B rows of 2*cw bytes)
     int hy[9], hx[9], wtap[9];      // tap -> halo offset (dy+1, dx+1) and packed-weight tap index
 };
 
@@ -52,7 +53,12 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t saddr, int mode) {
     return d;
 }
 
+// KSUB = cw / 16 = MMAs (K = 16) per tap and chunk
+template <int KSUB>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_constant__ HaloParams p) {
+    constexpr uint32_t ROWB = 32u * KSUB;                 // bytes of one pixel's channel chunk
+    constexpr uint32_t HALO_BYTES = 18u * 16u * ROWB;     // 36864 / 18432 / 9216 (all multiples of 1024)
+    constexpr uint32_t LTYPE = KSUB == 4 ? 2u : (KSUB == 2 ? 4u : 6u);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w_base = smem_base + HL_HALO_SLOTS * HL_HALO_BYTES;
@@ -86,7 +92,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
 
     const int tiles_pix = p.tiles_x * p.tiles_y * p.N;
     const int total_tiles = tiles_pix * p.n_tiles;
-    const uint32_t w_slice = (uint32_t)p.n_tile * 128u;      // bytes of one (chunk, tap) weight slice
+    const uint32_t w_slice = (uint32_t)p.n_tile * ROWB;      // bytes of one (chunk, tap) weight slice
 
     // tile order: n-tile outermost so that resident weights are loaded once per n-tile change
     if (warp == 0) {
@@ -106,19 +112,19 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
                     mbar_expect_tx(wfull(0), (uint32_t)(9 * p.kchunks) * w_slice);
                     for (int kc = 0; kc < p.kchunks; ++kc)
                         for (int t = 0; t < 9; ++t)
-                            tma_load_3d(w_base + (uint32_t)(kc * 9 + t) * w_slice, &p.w_map, wfull(0), kc * 64, nt * p.n_tile, p.wtap[t]);
+                            tma_load_3d(w_base + (uint32_t)(kc * 9 + t) * w_slice, &p.w_map, wfull(0), kc * p.cw, nt * p.n_tile, p.wtap[t]);
                     cur_nt = nt;
                 }
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(hempty(hs), hph ^ 1u);
-                    mbar_expect_tx(hfull(hs), (uint32_t)HL_HALO_BYTES);
-                    tma_load_4d(smem_base + hs * HL_HALO_BYTES, &p.in_map, hfull(hs), kc * 64, tx * 8 - 1, ty * 16 - 1, n);
+                    mbar_expect_tx(hfull(hs), HALO_BYTES);
+                    tma_load_4d(smem_base + hs * HL_HALO_BYTES, &p.in_map, hfull(hs), kc * p.cw, tx * 8 - 1, ty * 16 - 1, n);
                     if (++hs == HL_HALO_SLOTS) { hs = 0; hph ^= 1u; }
                     if (!p.resident) {
                         for (int t = 0; t < 9; ++t) {
                             mbar_wait(wempty(ws), wph ^ 1u);
                             mbar_expect_tx(wfull(ws), w_slice);
-                            tma_load_3d(w_base + ws * HL_W_SLOT_BYTES, &p.w_map, wfull(ws), kc * 64, nt * p.n_tile, p.wtap[t]);
+                            tma_load_3d(w_base + ws * HL_W_SLOT_BYTES, &p.w_map, wfull(ws), kc * p.cw, nt * p.n_tile, p.wtap[t]);
                             if (++ws == HL_W_SLOTS) { ws = 0; wph ^= 1u; }
                         }
                     }
@@ -128,11 +134,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
     } else if (warp == 1) {
         if (lane == 0) {       // a single thread issues every MMA; the loop is kept free of avoidable ALU work (issue-bound)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t a_hi = desc_hi(2048u, 2u);      // next 8-pixel group = next halo row
-            const uint32_t b_hi = desc_hi(1024u, 2u);
+            const uint32_t a_hi = desc_hi(16u * ROWB, LTYPE);      // next 8-pixel group = next halo line (16 pixels)
+            const uint32_t b_hi = desc_hi(8u * ROWB, LTYPE);
             uint32_t aoff[9];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) aoff[t] = (uint32_t)(p.hy[t] * 16 + p.hx[t]) * 8u;   // (halo line * 128 B) >> 4
+            for (int t = 0; t < 9; ++t) aoff[t] = (uint32_t)(p.hy[t] * 16 + p.hx[t]) * (ROWB >> 4);   // (halo pixel * ROWB) >> 4
             const uint32_t w_slice16 = w_slice >> 4;
             uint32_t hs = 0, hph = 0, ws = 0, wph = 0, wres_ph = 0, acc = 0, acc_phase = 0;
             int cur_nt = -1;
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
 #pragma unroll
                         for (int t = 0; t < 9; ++t)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
+                            for (int k = 0; k < KSUB; ++k)
                                 tc_mma_lohi(d_tmem, a0 + aoff[t] + 2u * k, a_hi, b0 + (uint32_t)t * w_slice16 + 2u * k, b_hi, idesc,
                                             (t | k) ? 1u : (uint32_t)(kc != 0));
                     } else {
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
                             tc_fence_after();
                             const uint32_t b0 = desc_lo(w_base + ws * HL_W_SLOT_BYTES, 16u);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
+                            for (int k = 0; k < KSUB; ++k)
                                 tc_mma_lohi(d_tmem, a0 + aoff[t] + 2u * k, a_hi, b0 + 2u * k, b_hi, idesc,
                                             (t | k) ? 1u : (uint32_t)(kc != 0));
                             tc_commit(wempty(ws));
@@ -220,14 +226,17 @@ int get_halo_mode() { return g_halo_mode; }
 int make_w_map_pub(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile, int cw);
 
 bool halo_supported(int form, int Cr, int Cw, int OW, int OH) {
-    return g_halo_mode != 0 && (form == 0 || form == 1) && Cr % 64 == 0 && Cw % 16 == 0 && Cw >= 16 && OW % 8 == 0 && OH % 16 == 0;
+    const bool cr_ok = Cr % 64 == 0 || Cr == 32 || Cr == 16;      // one 16/32-channel chunk, or 64-channel chunks
+    return g_halo_mode != 0 && (form == 0 || form == 1) && cr_ok && Cw % 16 == 0 && Cw >= 16 && OW % 8 == 0 && OH % 16 == 0;
 }
 
 int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
                       int act, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
         if (e != cudaSuccess) { set_error("conv3_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
         attr_set = true;
     }
@@ -239,9 +248,10 @@ int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* b
     p.Nc = Cw;
     p.n_tile = Cw <= 128 ? Cw : 128;
     p.n_tiles = (Cw + p.n_tile - 1) / p.n_tile;
-    p.kchunks = Cr / 64;
+    p.cw = Cr % 64 == 0 ? 64 : Cr;
+    p.kchunks = Cr / p.cw;
     p.act = act;
-    p.resident = (9 * p.kchunks * p.n_tile * 128 <= HL_W_RESIDENT_MAX) ? 1 : 0;
+    p.resident = (9 * p.kchunks * p.n_tile * 2 * p.cw <= HL_W_RESIDENT_MAX) ? 1 : 0;
     p.base_off_mode = g_halo_mode == 2 ? 1 : 0;
     for (int ky = 0; ky < 3; ++ky)
         for (int kx = 0; kx < 3; ++kx) {
@@ -250,14 +260,16 @@ int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* b
             p.hy[t] = dy + 1; p.hx[t] = dx + 1; p.wtap[t] = t;
         }
     // halo box: 16 pixels wide (x0-1 .. x0+14), 18 rows (y0-1 .. y0+16), one image
-    int rc = make_act_map(&p.in_map, in, Cr, W, H, N, Cr, (long long)W * Cr, (long long)H * W * Cr, 16, 18, 1, 64);
+    int rc = make_act_map(&p.in_map, in, Cr, W, H, N, Cr, (long long)W * Cr, (long long)H * W * Cr, 16, 18, 1, p.cw);
     if (rc) return rc;
-    rc = make_w_map_pub(&p.w_map, w_nk, Cr, Cw, 9, p.n_tile, 64);
+    rc = make_w_map_pub(&p.w_map, w_nk, Cr, Cw, 9, p.n_tile, p.cw);
     if (rc) return rc;
     long long total = (long long)p.tiles_x * p.tiles_y * N * p.n_tiles;
     int grid = (int)(total < num_sms() ? total : num_sms());
     if (grid < 1) return 0;
-    conv3_halo_kernel<<<grid, HL_THREADS, HL_SMEM_BYTES, st>>>(p);
+    if (p.cw == 64) conv3_halo_kernel<4><<<grid, HL_THREADS, HL_SMEM_BYTES, st>>>(p);
+    else if (p.cw == 32) conv3_halo_kernel<2><<<grid, HL_THREADS, HL_SMEM_BYTES, st>>>(p);
+    else conv3_halo_kernel<1><<<grid, HL_THREADS, HL_SMEM_BYTES, st>>>(p);
     return check_launch("conv3_halo_kernel");
 }
 

@@ -527,7 +527,8 @@ def test_pack_weights_multi_matches_single():
 
 
 HALO_CASES = [(2, 16, 16, 64, 64), (1, 32, 32, 128, 128), (2, 16, 8, 64, 256), (1, 64, 64, 64, 16), (3, 16, 16, 128, 64),
-              (2, 32, 16, 256, 64)]
+              (2, 32, 16, 256, 64),
+              (2, 16, 16, 16, 16), (1, 64, 64, 16, 64), (2, 32, 16, 32, 32), (3, 16, 24, 32, 16)]   # 16/32-channel chunks (32B/64B swizzle)
 
 
 @pytest.mark.parametrize("case", HALO_CASES)
