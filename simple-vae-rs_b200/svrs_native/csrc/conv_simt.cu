@@ -754,9 +754,9 @@ bool tc_supported(int dtype, int K, int Nc, int OW, int OH);
 int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
                    int act, cudaStream_t st);
 bool wgrad_tc_supported(int dtype, int Ca, int Cb, int OW, int OH);
-int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, int KK, cudaStream_t st);
+int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, int KK, float* db, cudaStream_t st);
 bool wgrad_halo_supported(const TapGeom& g, int KK);
-int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, cudaStream_t st);
+int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, float* db, cudaStream_t st);
 static int g_tc_enabled = 1;
 static inline bool use_tc(const void* w_nk, int dtype, int K, int Nc, int OW, int OH) {
     // layers with both channel counts <= 16 are HBM-bound streaming ops: the per-pixel SIMT kernel beats a padded MMA
@@ -836,11 +836,15 @@ extern "C" int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float
         a.gmat = dy; a.x = x; a.dw = dw; a.KK = ksize * ksize;
         if (ksize == 3) geom_conv3(a.g, N, H, W, Cin, Cout, false);
         else geom_conv4s2(a.g, N, H, W, Cin, Cout);
-        if (g_tc_enabled && N > 0 && dtype == SVRS_BF16 && wgrad_halo_supported(a.g, a.KK))
-            rc = launch_wgrad3_halo(a.g, dy, x, dw_packed ? dw_packed : dw, dw_packed != nullptr, (cudaStream_t)stream);
-        else if (g_tc_enabled && N > 0 && wgrad_tc_supported(dtype, Cout, Cin, a.g.OW, a.g.OH))
-            rc = launch_wgrad_tc(a.g, dy, x, dw_packed ? dw_packed : dw, dw_packed != nullptr, a.KK, (cudaStream_t)stream);
-        else
+        // the tensor-core kernels fold the bias gradient (column sums of dy) into their idle epilogue warps
+        const bool fold_db = db != nullptr && Cout % 8 == 0;
+        if (g_tc_enabled && N > 0 && dtype == SVRS_BF16 && wgrad_halo_supported(a.g, a.KK)) {
+            rc = launch_wgrad3_halo(a.g, dy, x, dw_packed ? dw_packed : dw, dw_packed != nullptr, fold_db ? db : nullptr, (cudaStream_t)stream);
+            if (fold_db) db = nullptr;
+        } else if (g_tc_enabled && N > 0 && wgrad_tc_supported(dtype, Cout, Cin, a.g.OW, a.g.OH)) {
+            rc = launch_wgrad_tc(a.g, dy, x, dw_packed ? dw_packed : dw, dw_packed != nullptr, a.KK, fold_db ? db : nullptr, (cudaStream_t)stream);
+            if (fold_db) db = nullptr;
+        } else
             rc = launch_wgrad(a, dtype, ksplit, (cudaStream_t)stream);
         if (rc) return rc;
     }
@@ -861,7 +865,7 @@ extern "C" int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, floa
         a.gmat = x; a.x = dy; a.dw = dw; a.KK = 16;
         geom_conv4s2(a.g, N, 2 * H, 2 * W, Cout, Cin);
         if (g_tc_enabled && N > 0 && wgrad_tc_supported(dtype, Cin, Cout, a.g.OW, a.g.OH))
-            rc = launch_wgrad_tc(a.g, x, dy, dw_packed ? dw_packed : dw, dw_packed != nullptr, 16, (cudaStream_t)stream);
+            rc = launch_wgrad_tc(a.g, x, dy, dw_packed ? dw_packed : dw, dw_packed != nullptr, 16, nullptr, (cudaStream_t)stream);
         else
             rc = launch_wgrad(a, dtype, ksplit, (cudaStream_t)stream);
         if (rc) return rc;

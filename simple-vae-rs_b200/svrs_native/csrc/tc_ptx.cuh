@@ -58,6 +58,40 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// ---- bias gradient folded into the wgrad kernels ---------------------------------------------------------------------
+// The four epilogue warps are idle while the MMA warp runs the pixel loop; they use that time to sum the CTA's G (= dy)
+// tiles over pixels straight from global memory (the same lines TMA is pulling through L2): thread = (8-channel group q,
+// pixel lane), 16-byte loads.  `acc` holds the thread's 8 partial channel sums.
+__device__ __forceinline__ void colsum_tile8(const __nv_bfloat16* __restrict__ g, long long sn, long long sy, long long sx,
+                                             int n0, int y0, int x0, int BW, int BH, int BNI, int N, int c0,
+                                             int lane, int lanes, float* acc) {
+    const int npix = BW * BH * BNI;
+    for (int i = lane; i < npix; i += lanes) {
+        const int bx = i % BW, by = (i / BW) % BH, n = n0 + i / (BW * BH);
+        if (n >= N) break;
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(g + (long long)n * sn + (long long)(y0 + by) * sy + (long long)(x0 + bx) * sx + c0));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[2 * j] += __uint_as_float(w[j] << 16); acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u); }
+    }
+}
+// fold the pixel lanes through shared memory (csum: 128 x 8 floats) and add the CTA's sums to db; t = thread 0..127
+__device__ __forceinline__ void colsum_finish(float (*csum)[8], const float* acc, int t, int q, int lane, int cg, int lanes,
+                                              float* db, int c_base, int C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csum[t][j] = acc[j];
+    named_bar_sync(2, 128);
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = 0.f;
+            for (int l = 0; l < lanes; ++l) v += csum[l * cg + q][j];
+            const int c = c_base + q * 8 + j;
+            if (c < C) atomicAdd(db + c, v);
+        }
+    }
+}
+
 // Stage one accumulator row for a TMA tensor store/reduce: `row_bytes` (128 or 64) of fp32 per row, rows packed, the
 // tensor map's SWIZZLE_128B / SWIZZLE_64B pattern applied (16-byte chunk index ^= row bits; `box` is 1024-byte aligned).
 template <int NV4>

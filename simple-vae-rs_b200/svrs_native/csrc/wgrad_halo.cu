@@ -30,6 +30,8 @@ struct alignas(64) WhParams {
     CUtensorMap g_map;   // (Ca, W, H, N) box (64, 8, 16, 1)
     CUtensorMap dw_map;  // packed mode: fp32 scratch [9*Cb rows][Ca], box (32 columns, 64 rows), 128B swizzle
     float* dw;
+    float* db;                      // != NULL: bias gradient folded in (column sums of G by the idle epilogue warps)
+    const __nv_bfloat16* gptr;
     int N, OH, OW, tiles_x, tiles_y;
     int Ca, Cb, KK;
     int a_tiles, b_chunks, ksplit, ksteps_total, packed;
@@ -122,6 +124,20 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad3_halo_kernel(const __grid
     } else if (nsteps > 0) {
         const int q = warp % 4;
         const int m = q * 32 + lane;
+        if (p.db && bj == 0) {           // one CTA per (pixel split, 64-channel tile of G)
+            __shared__ float csum[128][8];
+            const int t = threadIdx.x - 64, cq = t % 8, cl = t / 8;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const long long sx = p.Ca, sy = (long long)p.OW * p.Ca, sn = (long long)p.OH * p.OW * p.Ca;
+            for (int kstep = k_begin; kstep < k_end; ++kstep) {
+                int pt = kstep;
+                const int tx = pt % p.tiles_x; pt /= p.tiles_x;
+                const int ty = pt % p.tiles_y;
+                const int n = pt / p.tiles_y;
+                colsum_tile8(p.gptr, sn, sy, sx, n, ty * 16, tx * 8, 8, 16, 1, p.N, at * 64 + cq * 8, cl, 16, acc);
+            }
+            colsum_finish(csum, acc, t, cq, cl, 8, 16, p.db, at * 64, p.Ca);
+        }
         mbar_wait(done_bar, 0);
         tc_fence_after();
         if (p.packed) {
@@ -215,7 +231,7 @@ int wgrad_halo_splits(const TapGeom& g) {
     return p.ksplit;
 }
 
-int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, cudaStream_t st) {
+int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, float* db, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(wgrad3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM_BYTES);
@@ -226,6 +242,8 @@ int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float*
     wh_plan(g, p);
     p.dw = dw;
     p.packed = packed;
+    p.db = db;
+    p.gptr = reinterpret_cast<const __nv_bfloat16*>(gmat);
     const int base = p.a_tiles * p.b_chunks;
     const Prob& pb = g.prob[0];
     for (int t = 0; t < 9; ++t) p.off[t] = (pb.taps[t].dy + 1) * 16 + (pb.taps[t].dx + 1);

@@ -33,6 +33,9 @@ struct alignas(64) WgParams {
     CUtensorMap g_map;        // output-grid operand
     CUtensorMap dw_map;       // packed mode: fp32 scratch [KK*Cb rows][Ca], box (min(32, n_tile) columns, cwx rows)
     float* dw;
+    float* db;                         // != NULL: bias gradient (column sums of G) folded in, see colsum_tile8
+    const __nv_bfloat16* gptr;         // G base (output view) and its element strides, for the folded column sums
+    long long g_sn, g_sy, g_sx;
     int N, OH, OW, BW, BH, BNI;
     int tiles_x, tiles_y, tiles_n;     // pixel tiling of the output grid
     int Ca, Cb, KK;
@@ -149,6 +152,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     } else if (nsteps > 0) {
         const int q = warp % 4;
         const int m = q * 32 + lane;
+        if (p.db && grp == 0) {          // one CTA per (pixel split, column tile) sums its G tiles while the MMAs run
+            __shared__ float csum[128][8];
+            const int cg = p.n_tile / 8, lanes = 128 / cg;
+            const int t = threadIdx.x - 64, cq = t % cg, cl = t / cg;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int kstep = k_begin; kstep < k_end; ++kstep) {
+                int pt = kstep;
+                const int tx = pt % p.tiles_x; pt /= p.tiles_x;
+                const int ty = pt % p.tiles_y;
+                const int tn = pt / p.tiles_y;
+                colsum_tile8(p.gptr, p.g_sn, p.g_sy, p.g_sx, tn * p.BNI, ty * p.BH, tx * p.BW, p.BW, p.BH, p.BNI, p.N,
+                             nt * p.n_tile + cq * 8, cl, lanes, acc);
+            }
+            colsum_finish(csum, acc, t, cq, cl, cg, lanes, p.db, nt * p.n_tile, p.Ca);
+        }
         mbar_wait(done_bar, 0);
         tc_fence_after();
         if (prof && threadIdx.x == 64) prof[4] = clock64();
@@ -296,7 +314,7 @@ int wgrad_tc_splits(const TapGeom& g, int KK) {
 
 // g: geometry of the forward-form conv whose output grid carries `gmat` (channels Ca = g.Nc) and whose input view
 // carries `x` (channels Cb = g.K);  dw torch layout [(a*Cb + b)*KK + tap]
-int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, int KK, cudaStream_t st) {
+int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, int KK, float* db, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
@@ -308,6 +326,9 @@ int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw
     p.dw = dw;
     p.packed = packed;
     const Prob& pb = g.prob[0];
+    p.db = db;
+    p.gptr = reinterpret_cast<const __nv_bfloat16*>(gmat) + pb.out_off;
+    p.g_sn = g.o_sn; p.g_sy = g.o_sy; p.g_sx = g.o_sx;
     long long offs[4]; int nmaps = 0;
     for (int t = 0; t < pb.ntaps; ++t) {
         const Tap& tp = pb.taps[t];

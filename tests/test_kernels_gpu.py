@@ -499,6 +499,8 @@ def test_wgrad_tc_all_forms(case):
                 lib.conv2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), None, db.data_ptr(), BF16, N, H, W, Cin, Cout, ks, 0, st())
             torch.cuda.synchronize()
             res[tc] = dw
+            # bias gradient = column sums of dy (folded into the tensor-core kernels' idle epilogue warps for conv forms)
+            report(f"wgrad_tc {form} {case} db (tc={tc})", db, gy.double().sum(dim=(0, 2, 3)), 2e-5)
         lib.set_tc_enabled(1)
         report(f"wgrad_tc {form} {case} vs fp64", res[1], wr.grad, 2e-5)
         report(f"wgrad_tc {form} {case} vs simt", res[1], res[0], 2e-5)
