@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const T* __restrict__
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
                                                          int relu, double* __restrict__ sums) {
+    pdl_entry();
     constexpr int U = 4;
     __shared__ double red[256 * 8];
     const int cg = C / V;
@@ -152,6 +153,7 @@ __global__ void bn_finalize_train_kernel(const double* __restrict__ sums, long l
                                          long long* __restrict__ nbt, int n_updates,
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+    pdl_entry();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt) *nbt += n_updates;
     if (c >= C) return;
@@ -182,6 +184,7 @@ __global__ void bn_finalize_train_kernel(const double* __restrict__ sums, long l
 __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                         const float* __restrict__ rmean, const float* __restrict__ rvar,
                                         float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_entry();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float is = 1.0f / sqrtf(rvar[c] + eps);
@@ -195,6 +198,7 @@ __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec, int cg,
                                                         const float* __restrict__ scale, const float* __restrict__ shift, int relu) {
+    pdl_entry();
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c = (int)(i % cg) * V;
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                             const float* __restrict__ gamma, int relu,
                                                             const double* __restrict__ sums,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_entry();
     if (blockIdx.x == 0) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             if (dbeta) dbeta[c] += (float)sums[c];
@@ -312,11 +317,11 @@ extern "C" int svrs_bn_stats(const void* x, int dtype, int64_t M, int C, double*
     reduce_grid(M, C, w8 ? 8 : 4, blocks, rpb);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        bn_reduce_kernel<float, 4, false><<<blocks, 256, 0, st>>>((const float*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
+        SVRS_LAUNCH((bn_reduce_kernel<float, 4, false>), blocks, 256, 0, st, (const float*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
     else if (dtype == SVRS_BF16 && w8)
-        bn_reduce_kernel<__nv_bfloat16, 8, false><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
+        SVRS_LAUNCH((bn_reduce_kernel<__nv_bfloat16, 8, false>), blocks, 256, 0, st, (const __nv_bfloat16*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
     else if (dtype == SVRS_BF16)
-        bn_reduce_kernel<__nv_bfloat16, 4, false><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
+        SVRS_LAUNCH((bn_reduce_kernel<__nv_bfloat16, 4, false>), blocks, 256, 0, st, (const __nv_bfloat16*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
     else { set_error("bn_stats: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_stats");
 }
@@ -326,7 +331,7 @@ extern "C" int svrs_bn_finalize_train(const double* sums, int64_t M, int C, cons
                                       int64_t* num_batches_tracked, int n_updates,
                                       float* scale, float* shift, float* mean, float* invstd, void* stream) {
     SVRS_CHECK_ARG(sums && scale && shift && M > 0 && C > 0, "bn_finalize_train: bad args");
-    bn_finalize_train_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    SVRS_LAUNCH((bn_finalize_train_kernel), (C + 127) / 128, 128, 0, (cudaStream_t)stream, 
         sums, M, C, gamma, beta, eps, momentum, running_mean, running_var, (long long*)num_batches_tracked, n_updates,
         scale, shift, mean, invstd);
     return check_launch("bn_finalize_train");
@@ -336,7 +341,7 @@ extern "C" int svrs_bn_finalize_eval(int C, const float* gamma, const float* bet
                                      const float* running_mean, const float* running_var,
                                      float* scale, float* shift, void* stream) {
     SVRS_CHECK_ARG(running_mean && running_var && scale && shift && C > 0, "bn_finalize_eval: bad args");
-    bn_finalize_eval_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, eps, running_mean, running_var, scale, shift);
+    SVRS_LAUNCH((bn_finalize_eval_kernel), (C + 127) / 128, 128, 0, (cudaStream_t)stream, C, gamma, beta, eps, running_mean, running_var, scale, shift);
     return check_launch("bn_finalize_eval");
 }
 
@@ -347,11 +352,11 @@ extern "C" int svrs_bn_apply(const void* x, void* y, int dtype, int64_t M, int C
     long long nvec = M * C / (w8 ? 8 : 4);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        bn_apply_kernel<float, 4><<<ew_grid(nvec), 256, 0, st>>>((const float*)x, (float*)y, nvec, C / 4, scale, shift, relu);
+        SVRS_LAUNCH((bn_apply_kernel<float, 4>), ew_grid(nvec), 256, 0, st, (const float*)x, (float*)y, nvec, C / 4, scale, shift, relu);
     else if (dtype == SVRS_BF16 && w8)
-        bn_apply_kernel<__nv_bfloat16, 8><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 8, scale, shift, relu);
+        SVRS_LAUNCH((bn_apply_kernel<__nv_bfloat16, 8>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 8, scale, shift, relu);
     else if (dtype == SVRS_BF16)
-        bn_apply_kernel<__nv_bfloat16, 4><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 4, scale, shift, relu);
+        SVRS_LAUNCH((bn_apply_kernel<__nv_bfloat16, 4>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 4, scale, shift, relu);
     else { set_error("bn_apply: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_apply");
 }
@@ -365,11 +370,11 @@ extern "C" int svrs_bn_bwd_reduce(const void* x, const void* dy, int dtype, int6
     reduce_grid(M, C, w8 ? 8 : 4, blocks, rpb);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        bn_reduce_kernel<float, 4, true><<<blocks, 256, 0, st>>>((const float*)x, (const float*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
+        SVRS_LAUNCH((bn_reduce_kernel<float, 4, true>), blocks, 256, 0, st, (const float*)x, (const float*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
     else if (dtype == SVRS_BF16 && w8)
-        bn_reduce_kernel<__nv_bfloat16, 8, true><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
+        SVRS_LAUNCH((bn_reduce_kernel<__nv_bfloat16, 8, true>), blocks, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
     else if (dtype == SVRS_BF16)
-        bn_reduce_kernel<__nv_bfloat16, 4, true><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
+        SVRS_LAUNCH((bn_reduce_kernel<__nv_bfloat16, 4, true>), blocks, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
     else { set_error("bn_bwd_reduce: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_bwd_reduce");
 }
@@ -383,11 +388,11 @@ extern "C" int svrs_bn_bwd_apply(const void* x, const void* dy, void* dx, int dt
     long long nvec = M * C / (w8 ? 8 : 4);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        bn_bwd_apply_kernel<float, 4><<<ew_grid(nvec), 256, 0, st>>>((const float*)x, (const float*)dy, (float*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
+        SVRS_LAUNCH((bn_bwd_apply_kernel<float, 4>), ew_grid(nvec), 256, 0, st, (const float*)x, (const float*)dy, (float*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
     else if (dtype == SVRS_BF16 && w8)
-        bn_bwd_apply_kernel<__nv_bfloat16, 8><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 8, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
+        SVRS_LAUNCH((bn_bwd_apply_kernel<__nv_bfloat16, 8>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 8, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
     else if (dtype == SVRS_BF16)
-        bn_bwd_apply_kernel<__nv_bfloat16, 4><<<ew_grid(nvec), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
+        SVRS_LAUNCH((bn_bwd_apply_kernel<__nv_bfloat16, 4>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
     else { set_error("bn_bwd_apply: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_bwd_apply");
 }

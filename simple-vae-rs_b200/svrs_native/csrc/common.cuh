@@ -31,6 +31,34 @@ static inline int check_launch(const char* what) {
     return 0;
 }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// Every kernel of the library can be launched with the programmatic-stream-serialization attribute and starts with
+// pdl_trigger() (let the NEXT kernel of the stream begin launching: its CTAs become resident as ours retire) and
+// pdl_wait() (block until the PREVIOUS kernel of the stream has completed and flushed) before it touches global memory.
+// That hides the kernel-to-kernel launch latency of the ~300 mostly tiny launches of a step; the tensor-core kernels
+// additionally run their barrier / TMEM / tensor-map prologue ahead of pdl_wait().  The attribute is only set with
+// SVRS_PDL=1 (without it the device-side instructions are no-ops): measured neutral under CUDA-graph replay.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
+bool pdl_enabled();   // layout.cu
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define SVRS_LAUNCH(kernel, grid, block, smem, st, ...) svrs::launch_k(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
+
 static inline int num_sms() {
     static int n = 0;
     if (n == 0) {

@@ -56,6 +56,7 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t saddr, int mode) {
 // KSUB = cw / 16 = MMAs (K = 16) per tap and chunk
 template <int KSUB>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_constant__ HaloParams p) {
+    pdl_entry();
     constexpr uint32_t ROWB = 32u * KSUB;                 // bytes of one pixel's channel chunk
     constexpr uint32_t HALO_BYTES = 18u * 16u * ROWB;     // 36864 / 18432 / 9216 (all multiples of 1024)
     constexpr uint32_t LTYPE = KSUB == 4 ? 2u : (KSUB == 2 ? 4u : 6u);
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();     // prologue above overlaps the previous kernel; nothing before this line touches global memory
 
     const int tiles_pix = p.tiles_x * p.tiles_y * p.N;
     const int total_tiles = tiles_pix * p.n_tiles;
@@ -267,9 +269,9 @@ int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* b
     long long total = (long long)p.tiles_x * p.tiles_y * N * p.n_tiles;
     int grid = (int)(total < num_sms() ? total : num_sms());
     if (grid < 1) return 0;
-    if (p.cw == 64) conv3_halo_kernel<4><<<grid, HL_THREADS, HL_SMEM_BYTES, st>>>(p);
-    else if (p.cw == 32) conv3_halo_kernel<2><<<grid, HL_THREADS, HL_SMEM_BYTES, st>>>(p);
-    else conv3_halo_kernel<1><<<grid, HL_THREADS, HL_SMEM_BYTES, st>>>(p);
+    if (p.cw == 64) SVRS_LAUNCH((conv3_halo_kernel<4>), grid, HL_THREADS, HL_SMEM_BYTES, st, p);
+    else if (p.cw == 32) SVRS_LAUNCH((conv3_halo_kernel<2>), grid, HL_THREADS, HL_SMEM_BYTES, st, p);
+    else SVRS_LAUNCH((conv3_halo_kernel<1>), grid, HL_THREADS, HL_SMEM_BYTES, st, p);
     return check_launch("conv3_halo_kernel");
 }
 

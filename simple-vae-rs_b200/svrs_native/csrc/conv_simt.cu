@@ -21,6 +21,7 @@ constexpr int BK = 16;
 
 template <typename T, int BM, int BN>
 __global__ void __launch_bounds__(256) conv_taps_kernel(const __grid_constant__ ConvArgs a) {
+    pdl_entry();
     constexpr int TM = 4, TN = 4;
     constexpr int TX = BN / TN;            // threads along channels
     static_assert((BM / TM) * TX == 256, "256 threads");
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(256) conv_taps_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CR, int CW>
 __global__ void __launch_bounds__(256) conv_pixel_kernel(const __grid_constant__ ConvArgs a) {
+    pdl_entry();
     __shared__ __align__(16) float ws[16 * CR * CW];
     const TapGeom& g = a.g;
     const Prob& pb = g.prob[blockIdx.z];
@@ -225,10 +227,10 @@ __global__ void __launch_bounds__(256) conv_pixel_kernel(const __grid_constant__
 template <typename T>
 static void launch_pixel(const ConvArgs& a, dim3 grid, cudaStream_t st) {
     const int K = a.g.K, Nc = a.g.Nc;
-    if (K == 4 && Nc == 4) conv_pixel_kernel<T, 4, 4><<<grid, 256, 0, st>>>(a);
-    else if (K == 4 && Nc == 16) conv_pixel_kernel<T, 4, 16><<<grid, 256, 0, st>>>(a);
-    else if (K == 16 && Nc == 4) conv_pixel_kernel<T, 16, 4><<<grid, 256, 0, st>>>(a);
-    else conv_pixel_kernel<T, 16, 16><<<grid, 256, 0, st>>>(a);
+    if (K == 4 && Nc == 4) SVRS_LAUNCH((conv_pixel_kernel<T, 4, 4>), grid, 256, 0, st, a);
+    else if (K == 4 && Nc == 16) SVRS_LAUNCH((conv_pixel_kernel<T, 4, 16>), grid, 256, 0, st, a);
+    else if (K == 16 && Nc == 4) SVRS_LAUNCH((conv_pixel_kernel<T, 16, 4>), grid, 256, 0, st, a);
+    else SVRS_LAUNCH((conv_pixel_kernel<T, 16, 16>), grid, 256, 0, st, a);
 }
 
 static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
@@ -243,12 +245,12 @@ static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
     }
     if (g.Nc <= 16) {
         dim3 grid((unsigned)((M + 255) / 256), (g.Nc + 15) / 16, g.nprob);
-        if (dtype == SVRS_F32) conv_taps_kernel<float, 256, 16><<<grid, 256, 0, st>>>(a);
-        else conv_taps_kernel<__nv_bfloat16, 256, 16><<<grid, 256, 0, st>>>(a);
+        if (dtype == SVRS_F32) SVRS_LAUNCH((conv_taps_kernel<float, 256, 16>), grid, 256, 0, st, a);
+        else SVRS_LAUNCH((conv_taps_kernel<__nv_bfloat16, 256, 16>), grid, 256, 0, st, a);
     } else {
         dim3 grid((unsigned)((M + 63) / 64), (g.Nc + 63) / 64, g.nprob);
-        if (dtype == SVRS_F32) conv_taps_kernel<float, 64, 64><<<grid, 256, 0, st>>>(a);
-        else conv_taps_kernel<__nv_bfloat16, 64, 64><<<grid, 256, 0, st>>>(a);
+        if (dtype == SVRS_F32) SVRS_LAUNCH((conv_taps_kernel<float, 64, 64>), grid, 256, 0, st, a);
+        else SVRS_LAUNCH((conv_taps_kernel<__nv_bfloat16, 64, 64>), grid, 256, 0, st, a);
     }
     return check_launch("conv_taps_kernel");
 }
@@ -269,6 +271,7 @@ struct WgradArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_taps_kernel(const __grid_constant__ WgradArgs a) {
+    pdl_entry();
     constexpr int BA = 64, BB = 64, BP = 16;
     __shared__ float Gs[BP][BA];
     __shared__ float Xs[BP][BB];
@@ -363,6 +366,7 @@ __global__ void __launch_bounds__(256) wgrad_taps_kernel(const __grid_constant__
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long M, int C,
                                                       float* __restrict__ out, long long rows_per_block) {
+    pdl_entry();
     __shared__ float red[8][33];
     const int lx = threadIdx.x % 32, ly = threadIdx.x / 32;
     const long long r0 = (long long)blockIdx.x * rows_per_block;
@@ -395,6 +399,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 // ------------------------------------------------------------------------------------------------
 template <typename T, int SUB>
 __global__ void __launch_bounds__(256) wgrad_direct_kernel(const __grid_constant__ WgradArgs a) {
+    pdl_entry();
     constexpr int L = 256 / SUB;   // pixel lanes per sub-tile
     __shared__ float red[(L > 32 ? L / 32 : 1)][SUB][16];
     const TapGeom& g = a.g;
@@ -541,6 +546,7 @@ template <> __device__ __forceinline__ void raw_to_float<__nv_bfloat16, 16>(cons
 
 template <typename T, int CA, int CB, int TPW>
 __global__ void __launch_bounds__(512, 1) wgrad_narrow_kernel(const __grid_constant__ WgradArgs a) {
+    pdl_entry();
     __shared__ float red[16][TPW * CA * CB];
     const TapGeom& g = a.g;
     const Prob& pb = g.prob[0];
@@ -639,9 +645,9 @@ static bool try_launch_wgrad_narrow(const WgradArgs& a, cudaStream_t st, int& rc
     const int warps = (Ca == 4 && Cb == 4) ? (ntaps + 3) / 4 : ntaps;
     int grid = num_sms() * (warps >= 8 ? 1 : 16 / warps);          // ~16 resident warps per SM (100-120 registers each)
     if (grid > groups) grid = groups;
-    if (Ca == 4 && Cb == 16) wgrad_narrow_kernel<T, 4, 16, 1><<<grid, 32 * ntaps, 0, st>>>(a);
-    else if (Ca == 16 && Cb == 4) wgrad_narrow_kernel<T, 16, 4, 1><<<grid, 32 * ntaps, 0, st>>>(a);
-    else if (Ca == 4 && Cb == 4) wgrad_narrow_kernel<T, 4, 4, 4><<<grid, 32 * ((ntaps + 3) / 4), 0, st>>>(a);
+    if (Ca == 4 && Cb == 16) SVRS_LAUNCH((wgrad_narrow_kernel<T, 4, 16, 1>), grid, 32 * ntaps, 0, st, a);
+    else if (Ca == 16 && Cb == 4) SVRS_LAUNCH((wgrad_narrow_kernel<T, 16, 4, 1>), grid, 32 * ntaps, 0, st, a);
+    else if (Ca == 4 && Cb == 4) SVRS_LAUNCH((wgrad_narrow_kernel<T, 4, 4, 4>), grid, 32 * ((ntaps + 3) / 4), 0, st, a);
     else return false;
     rc = check_launch("wgrad_narrow_kernel");
     return true;
@@ -663,10 +669,10 @@ static int launch_wgrad_direct(const WgradArgs& a, cudaStream_t st) {
     if (split < 1) split = 1;
     if (split > 65535) split = 65535;
     dim3 grid(ntaps, (unsigned)split, groups);
-    if (SUB == 1) wgrad_direct_kernel<T, 1><<<grid, 256, 0, st>>>(a);
-    else if (SUB == 4) wgrad_direct_kernel<T, 4><<<grid, 256, 0, st>>>(a);
-    else if (SUB == 16) wgrad_direct_kernel<T, 16><<<grid, 256, 0, st>>>(a);
-    else wgrad_direct_kernel<T, 64><<<grid, 256, 0, st>>>(a);
+    if (SUB == 1) SVRS_LAUNCH((wgrad_direct_kernel<T, 1>), grid, 256, 0, st, a);
+    else if (SUB == 4) SVRS_LAUNCH((wgrad_direct_kernel<T, 4>), grid, 256, 0, st, a);
+    else if (SUB == 16) SVRS_LAUNCH((wgrad_direct_kernel<T, 16>), grid, 256, 0, st, a);
+    else SVRS_LAUNCH((wgrad_direct_kernel<T, 64>), grid, 256, 0, st, a);
     return check_launch("wgrad_direct_kernel");
 }
 
@@ -692,8 +698,8 @@ static int launch_wgrad(WgradArgs& a, int dtype, int ksplit, cudaStream_t st) {
     }
     a.ksplit = ksplit;
     dim3 grid(tiles, ntaps, ksplit);
-    if (dtype == SVRS_F32) wgrad_taps_kernel<float><<<grid, 256, 0, st>>>(a);
-    else wgrad_taps_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a);
+    if (dtype == SVRS_F32) SVRS_LAUNCH((wgrad_taps_kernel<float>), grid, 256, 0, st, a);
+    else SVRS_LAUNCH((wgrad_taps_kernel<__nv_bfloat16>), grid, 256, 0, st, a);
     return check_launch("wgrad_taps_kernel");
 }
 
@@ -701,6 +707,7 @@ static int launch_wgrad(WgradArgs& a, int dtype, int ksplit, cudaStream_t st) {
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, long long M, int C,
                                                           float* __restrict__ out, long long rows_per_block) {
+    pdl_entry();
     __shared__ float red[256][4];
     const int cg = C / 4;
     const int q = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = 256 / cg;
@@ -733,8 +740,8 @@ static int launch_colsum(const void* x, int dtype, long long M, int C, float* ou
         if (blocks < 1) blocks = 1;
         long long rpb = (M + blocks - 1) / blocks;
         blocks = (M + rpb - 1) / rpb;
-        if (dtype == SVRS_F32) colsum_vec_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, M, C, out, rpb);
-        else colsum_vec_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, M, C, out, rpb);
+        if (dtype == SVRS_F32) SVRS_LAUNCH((colsum_vec_kernel<float>), (unsigned)blocks, 256, 0, st, (const float*)x, M, C, out, rpb);
+        else SVRS_LAUNCH((colsum_vec_kernel<__nv_bfloat16>), (unsigned)blocks, 256, 0, st, (const __nv_bfloat16*)x, M, C, out, rpb);
         return check_launch("colsum_vec_kernel");
     }
     long long blocks = (M + 511) / 512;
@@ -742,8 +749,8 @@ static int launch_colsum(const void* x, int dtype, long long M, int C, float* ou
     if (blocks > cap) blocks = cap;
     long long rpb = (M + blocks - 1) / blocks;
     blocks = (M + rpb - 1) / rpb;
-    if (dtype == SVRS_F32) colsum_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, M, C, out, rpb);
-    else colsum_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, M, C, out, rpb);
+    if (dtype == SVRS_F32) SVRS_LAUNCH((colsum_kernel<float>), (unsigned)blocks, 256, 0, st, (const float*)x, M, C, out, rpb);
+    else SVRS_LAUNCH((colsum_kernel<__nv_bfloat16>), (unsigned)blocks, 256, 0, st, (const __nv_bfloat16*)x, M, C, out, rpb);
     return check_launch("colsum_kernel");
 }
 

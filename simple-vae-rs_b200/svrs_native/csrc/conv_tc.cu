@@ -62,6 +62,7 @@ struct alignas(64) TcParams {
 
 // ------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();     // prologue above overlaps the previous kernel; nothing before this line touches global memory
 
     const int tiles_pix = p.tiles_x * p.tiles_y * p.tiles_n;
     const int tiles_per_prob = tiles_pix * p.n_tiles;
@@ -364,7 +366,7 @@ int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias
     long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * p.nprob;
     int grid = (int)(total < num_sms() ? total : num_sms());
     if (grid < 1) return 0;
-    conv_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
+    SVRS_LAUNCH((conv_tc_kernel), grid, TC_THREADS, TC_SMEM_BYTES, st, p);
     return check_launch("conv_tc_kernel");
 }
 

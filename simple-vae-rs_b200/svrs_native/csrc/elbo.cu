@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) reparam_fwd_kernel(const float* __restric
                                                            float* __restrict__ z, long long z_ld, float* __restrict__ eps_out, int B, int Wd,
                                                            uint64_t seed, uint32_t sid, uint64_t sample_offset,
                                                            const long long* __restrict__ step_ptr) {
+    pdl_entry();
     const long long nvec = (long long)B * Wd / 4;
     const int wq = Wd / 4;
     const uint32_t step = step_ptr ? (uint32_t)(*step_ptr) : 0u;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restric
                                                            const float* __restrict__ dz, long long dz_ld, float* __restrict__ denc, int B, int Wd,
                                                            uint64_t seed, uint32_t sid, uint64_t sample_offset,
                                                            const long long* __restrict__ step_ptr) {
+    pdl_entry();
     const long long nvec = (long long)B * Wd / 4;
     const int wq = Wd / 4;
     const uint32_t step = step_ptr ? (uint32_t)(*step_ptr) : 0u;
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restric
 
 __global__ void philox_normal_kernel(float* __restrict__ out, int B, int Wd, uint64_t seed, uint32_t sid, uint64_t sample_offset,
                                      const long long* __restrict__ step_ptr) {
+    pdl_entry();
     const long long nvec = (long long)B * Wd / 4;
     const uint32_t step = step_ptr ? (uint32_t)(*step_ptr) : 0u;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
@@ -128,6 +131,7 @@ struct ElboArgs {
 };
 
 __global__ void __launch_bounds__(256) elbo_fwd_kernel(const __grid_constant__ ElboArgs a, double* __restrict__ acc) {
+    pdl_entry();
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gsize = (long long)gridDim.x * blockDim.x;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(256) elbo_fwd_kernel(const __grid_constant__ E
 
 __global__ void elbo_finalize_kernel(const double* __restrict__ acc, long long nx, long long ny, int B,
                                      const float* __restrict__ gammas, float* __restrict__ out) {
+    pdl_entry();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float gx = gammas[0], gy = gammas[1];
     // loss/cond_vae_loss.py:43-49: n * (mean((r-x)^2) / (2 g^2) + log g)
@@ -220,6 +225,7 @@ __device__ __forceinline__ void nll_bwd_segment(const T* __restrict__ r, const T
 }
 
 __global__ void __launch_bounds__(256) elbo_bwd_kernel(const __grid_constant__ ElboBwdArgs a) {
+    pdl_entry();
     const ElboArgs& f = a.f;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gsize = (long long)gridDim.x * blockDim.x;
@@ -302,7 +308,7 @@ extern "C" int svrs_reparam_fwd(const float* enc, const float* eps, float* z, in
     SVRS_CHECK_ARG(enc && z && B >= 0 && Wd > 0 && Wd % 4 == 0 && z_ld % 4 == 0 && z_ld >= Wd, "reparam_fwd: bad args (Wd, z_ld %% 4 != 0?)");
     SVRS_CHECK_ARG(al16(enc) && al16(eps) && al16(z) && al16(eps_out), "reparam_fwd: pointers must be 16B aligned");
     if (B == 0) return 0;
-    reparam_fwd_kernel<<<ew_grid2((long long)B * Wd / 4), 256, 0, (cudaStream_t)stream>>>(enc, eps, z, z_ld, eps_out, B, Wd, seed, stream_id, sample_offset, (const long long*)step_ptr);
+    SVRS_LAUNCH((reparam_fwd_kernel), ew_grid2((long long)B * Wd / 4), 256, 0, (cudaStream_t)stream, enc, eps, z, z_ld, eps_out, B, Wd, seed, stream_id, sample_offset, (const long long*)step_ptr);
     return check_launch("reparam_fwd");
 }
 
@@ -311,7 +317,7 @@ extern "C" int svrs_reparam_bwd(const float* enc, const float* eps, const float*
     SVRS_CHECK_ARG(enc && dz && denc && B >= 0 && Wd > 0 && Wd % 4 == 0 && dz_ld % 4 == 0 && dz_ld >= Wd, "reparam_bwd: bad args");
     SVRS_CHECK_ARG(al16(enc) && al16(eps) && al16(dz) && al16(denc), "reparam_bwd: pointers must be 16B aligned");
     if (B == 0) return 0;
-    reparam_bwd_kernel<<<ew_grid2((long long)B * Wd / 4), 256, 0, (cudaStream_t)stream>>>(enc, eps, dz, dz_ld, denc, B, Wd, seed, stream_id, sample_offset, (const long long*)step_ptr);
+    SVRS_LAUNCH((reparam_bwd_kernel), ew_grid2((long long)B * Wd / 4), 256, 0, (cudaStream_t)stream, enc, eps, dz, dz_ld, denc, B, Wd, seed, stream_id, sample_offset, (const long long*)step_ptr);
     return check_launch("reparam_bwd");
 }
 
@@ -319,7 +325,7 @@ extern "C" int svrs_philox_normal(float* out, int B, int Wd, uint64_t seed, uint
                                   uint64_t sample_offset, const int64_t* step_ptr, void* stream) {
     SVRS_CHECK_ARG(out && B >= 0 && Wd > 0 && Wd % 4 == 0 && al16(out), "philox_normal: bad args");
     if (B == 0) return 0;
-    philox_normal_kernel<<<ew_grid2((long long)B * Wd / 4), 256, 0, (cudaStream_t)stream>>>(out, B, Wd, seed, stream_id, sample_offset, (const long long*)step_ptr);
+    SVRS_LAUNCH((philox_normal_kernel), ew_grid2((long long)B * Wd / 4), 256, 0, (cudaStream_t)stream, out, B, Wd, seed, stream_id, sample_offset, (const long long*)step_ptr);
     return check_launch("philox_normal");
 }
 
@@ -355,14 +361,14 @@ extern "C" int svrs_elbo_fwd(const void* recon_x, const void* x, int dt_x, int64
     long long work = (n_x > n_y ? n_x : n_y) / 4;
     long long w2 = (long long)B * (W2 > W1 ? W2 : W1) / 4;
     if (w2 > work) work = w2;
-    elbo_fwd_kernel<<<ew_grid2(work), 256, 0, (cudaStream_t)stream>>>(a, acc);
+    SVRS_LAUNCH((elbo_fwd_kernel), ew_grid2(work), 256, 0, (cudaStream_t)stream, a, acc);
     return check_launch("elbo_fwd");
 }
 
 extern "C" int svrs_elbo_finalize(const double* acc, int64_t n_x, int64_t n_y, int B, const float* gammas,
                                   float* out5, void* stream) {
     SVRS_CHECK_ARG(acc && gammas && out5 && B > 0, "elbo_finalize: bad args");
-    elbo_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, n_x, n_y, B, gammas, out5);
+    SVRS_LAUNCH((elbo_finalize_kernel), 1, 32, 0, (cudaStream_t)stream, acc, n_x, n_y, B, gammas, out5);
     return check_launch("elbo_finalize");
 }
 
@@ -387,6 +393,6 @@ extern "C" int svrs_elbo_bwd(const void* recon_x, const void* x, int dt_x, int64
     long long work = (n_x > n_y ? n_x : n_y) / 4;
     long long w2 = (long long)B * (W2 > W1 ? W2 : W1) / 4;
     if (w2 > work) work = w2;
-    elbo_bwd_kernel<<<ew_grid2(work), 256, 0, (cudaStream_t)stream>>>(a);
+    SVRS_LAUNCH((elbo_bwd_kernel), ew_grid2(work), 256, 0, (cudaStream_t)stream, a);
     return check_launch("elbo_bwd");
 }

@@ -1,6 +1,7 @@
 // layout.cu - layout glue (NCHW-flat <-> NHWC), weight packing, casts, error plumbing.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace svrs {
 
@@ -20,6 +21,12 @@ static long long g_launches = 0;
 static thread_local char g_trace[2048] = "";
 static thread_local int g_trace_len = -1;   // -1 = tracing off
 
+bool pdl_enabled() {
+    // measured on B200: neutral for the graph-replayed step (graph nodes already launch back to back), so off by default
+    static const bool on = [] { const char* e = getenv("SVRS_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+
 void note_kernel(const char* what) {
     __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED);
     if (g_trace_len < 0) return;
@@ -34,6 +41,7 @@ void note_kernel(const char* what) {
 template <typename TS, typename TD>
 __global__ void nchw_to_nhwc_kernel(const TS* __restrict__ src, long long src_ld, TD* __restrict__ dst,
                                     int C, int HW) {
+    pdl_entry();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const TS* s = src + (long long)n * src_ld;
@@ -53,6 +61,7 @@ __global__ void nchw_to_nhwc_kernel(const TS* __restrict__ src, long long src_ld
 template <typename TS, typename TD>
 __global__ void nhwc_to_nchw_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long dst_ld,
                                     int C, int HW, int accumulate) {
+    pdl_entry();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const TS* s = src + (long long)n * C * HW;
@@ -77,6 +86,7 @@ __global__ void nhwc_to_nchw_kernel(const TS* __restrict__ src, TD* __restrict__
 template <typename TD>
 __global__ void pack_weights_kernel(const float* __restrict__ w, int d0, int d1, int kk, TD* __restrict__ p01,
                                     TD* __restrict__ p10) {
+    pdl_entry();
     long long total = (long long)d0 * d1 * kk;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -92,6 +102,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int d0, int d1,
 
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         d[i] = Cvt<TD>::from_f(Cvt<TS>::to_f(s[i]));
 }
@@ -99,6 +110,7 @@ __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long l
 template <typename TS, typename TD>
 __global__ void copy2d_kernel(const TS* __restrict__ s, long long sld, TD* __restrict__ d, long long dld,
                               long long rows, int cols, int accumulate) {
+    pdl_entry();
     long long total = rows * cols;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long r = i / cols;
@@ -111,6 +123,7 @@ __global__ void copy2d_kernel(const TS* __restrict__ s, long long sld, TD* __res
 
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, int act, long long n) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float yv = Cvt<T>::to_f(y[i]), g = Cvt<T>::to_f(dy[i]);
         float o = g;
@@ -121,6 +134,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ y, const T* __restrict__ dy
 }
 
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = fmaf(a, x[i], y[i]);
 }
@@ -163,7 +177,7 @@ extern "C" int svrs_nchw_to_nhwc(const void* src, int src_dtype, int64_t src_ld,
     int HW = H * W;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(TS, TD) nchw_to_nhwc_kernel<TS, TD><<<grid, block, 0, st>>>((const TS*)src, src_ld, (TD*)dst, C, HW)
+#define CALL(TS, TD) SVRS_LAUNCH((nchw_to_nhwc_kernel<TS, TD>), grid, block, 0, st, (const TS*)src, src_ld, (TD*)dst, C, HW)
     DISPATCH2(src_dtype, dst_dtype, CALL);
 #undef CALL
     return check_launch("nchw_to_nhwc");
@@ -177,7 +191,7 @@ extern "C" int svrs_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int 
     int HW = H * W;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(TS, TD) nhwc_to_nchw_kernel<TS, TD><<<grid, block, 0, st>>>((const TS*)src, (TD*)dst, dst_ld, C, HW, accumulate)
+#define CALL(TS, TD) SVRS_LAUNCH((nhwc_to_nchw_kernel<TS, TD>), grid, block, 0, st, (const TS*)src, (TD*)dst, dst_ld, C, HW, accumulate)
     DISPATCH2(src_dtype, dst_dtype, CALL);
 #undef CALL
     return check_launch("nhwc_to_nchw");
@@ -189,9 +203,9 @@ extern "C" int svrs_pack_weights(const float* w, int d0, int d1, int kk, void* p
     long long total = (long long)d0 * d1 * kk;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        pack_weights_kernel<float><<<grid_for(total), 256, 0, st>>>(w, d0, d1, kk, (float*)p01, (float*)p10);
+        SVRS_LAUNCH((pack_weights_kernel<float>), grid_for(total), 256, 0, st, w, d0, d1, kk, (float*)p01, (float*)p10);
     else if (dtype == SVRS_BF16)
-        pack_weights_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>(w, d0, d1, kk, (__nv_bfloat16*)p01,
+        SVRS_LAUNCH((pack_weights_kernel<__nv_bfloat16>), grid_for(total), 256, 0, st, w, d0, d1, kk, (__nv_bfloat16*)p01,
                                                                              (__nv_bfloat16*)p10);
     else { set_error("pack_weights: bad dtype"); return SVRS_E_ARG; }
     return check_launch("pack_weights");
@@ -208,7 +222,7 @@ extern "C" int svrs_fill_zero(void* p, int64_t bytes, void* stream) {
 extern "C" int svrs_axpy_f32(float* y, const float* x, float a, int64_t n, void* stream) {
     if (n <= 0) return 0;
     SVRS_CHECK_ARG(x && y, "axpy: null");
-    axpy_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(y, x, a, n);
+    SVRS_LAUNCH((axpy_kernel), grid_for(n), 256, 0, (cudaStream_t)stream, y, x, a, n);
     return check_launch("axpy");
 }
 
@@ -216,7 +230,7 @@ extern "C" int svrs_cast(const void* src, int src_dtype, void* dst, int dst_dtyp
     if (n <= 0) return 0;
     SVRS_CHECK_ARG(src && dst, "cast: null");
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(TS, TD) cast_kernel<TS, TD><<<grid_for(n), 256, 0, st>>>((const TS*)src, (TD*)dst, n)
+#define CALL(TS, TD) SVRS_LAUNCH((cast_kernel<TS, TD>), grid_for(n), 256, 0, st, (const TS*)src, (TD*)dst, n)
     DISPATCH2(src_dtype, dst_dtype, CALL);
 #undef CALL
     return check_launch("cast");
@@ -228,7 +242,7 @@ extern "C" int svrs_copy2d(const void* src, int src_dtype, int64_t src_ld, void*
     SVRS_CHECK_ARG(src && dst && (src_ld >= cols || src_ld == 0) && dst_ld >= cols, "copy2d: bad args (src_ld 0 = broadcast)");
     cudaStream_t st = (cudaStream_t)stream;
     long long n = rows * cols;
-#define CALL(TS, TD) copy2d_kernel<TS, TD><<<grid_for(n), 256, 0, st>>>((const TS*)src, src_ld, (TD*)dst, dst_ld, rows, cols, accumulate)
+#define CALL(TS, TD) SVRS_LAUNCH((copy2d_kernel<TS, TD>), grid_for(n), 256, 0, st, (const TS*)src, src_ld, (TD*)dst, dst_ld, rows, cols, accumulate)
     DISPATCH2(src_dtype, dst_dtype, CALL);
 #undef CALL
     return check_launch("copy2d");
@@ -238,8 +252,8 @@ extern "C" int svrs_act_bwd(const void* y, const void* dy, void* dx, int dtype, 
     if (n <= 0) return 0;
     SVRS_CHECK_ARG(y && dy && dx, "act_bwd: null");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == SVRS_F32) act_bwd_kernel<float><<<grid_for(n), 256, 0, st>>>((const float*)y, (const float*)dy, (float*)dx, act, n);
-    else if (dtype == SVRS_BF16) act_bwd_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, act, n);
+    if (dtype == SVRS_F32) SVRS_LAUNCH((act_bwd_kernel<float>), grid_for(n), 256, 0, st, (const float*)y, (const float*)dy, (float*)dx, act, n);
+    else if (dtype == SVRS_BF16) SVRS_LAUNCH((act_bwd_kernel<__nv_bfloat16>), grid_for(n), 256, 0, st, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, act, n);
     else { set_error("act_bwd: bad dtype"); return SVRS_E_ARG; }
     return check_launch("act_bwd");
 }
@@ -263,6 +277,7 @@ constexpr int PK_TA = 32, PK_TB = 16;
 
 template <typename TD>
 __global__ void __launch_bounds__(256) pack_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    pdl_entry();
     extern __shared__ float tile[];
     int j = 0;
     while (j + 1 < njobs && jobs[j + 1].tile0 <= (int)blockIdx.x) ++j;
@@ -300,6 +315,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackJob* __restri
 namespace svrs {
 // gradients: packed fp32 scratch [tap][d0][d1] -> torch layout [d0][d1][tap] (+=), same tiling as pack_multi_kernel
 __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    pdl_entry();
     extern __shared__ float tile[];
     int j = 0;
     while (j + 1 < njobs && jobs[j + 1].tile0 <= (int)blockIdx.x) ++j;
@@ -329,7 +345,7 @@ __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackJob* __rest
 extern "C" int svrs_unpack_grads_multi(const void* jobs, int njobs, int total_tiles, int max_kk, void* stream) {
     SVRS_CHECK_ARG(jobs && njobs > 0 && total_tiles > 0 && max_kk > 0 && max_kk <= 16, "unpack_grads_multi: bad args");
     size_t smem = (size_t)svrs::PK_TA * (svrs::PK_TB * (max_kk + 1) + 1) * sizeof(float);
-    svrs::unpack_multi_kernel<<<total_tiles, 256, smem, (cudaStream_t)stream>>>((const svrs::PackJob*)jobs, njobs);
+    SVRS_LAUNCH((svrs::unpack_multi_kernel), total_tiles, 256, smem, (cudaStream_t)stream, (const svrs::PackJob*)jobs, njobs);
     return check_launch("unpack_grads_multi");
 }
 
@@ -339,8 +355,8 @@ extern "C" int svrs_pack_weights_multi(const void* jobs, int njobs, int total_ti
     SVRS_CHECK_ARG(jobs && njobs > 0 && total_tiles > 0 && max_kk > 0 && max_kk <= 16, "pack_weights_multi: bad args");
     size_t smem = (size_t)svrs::PK_TA * (svrs::PK_TB * (max_kk + 1) + 1) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == SVRS_F32) svrs::pack_multi_kernel<float><<<total_tiles, 256, smem, st>>>((const svrs::PackJob*)jobs, njobs);
-    else if (dtype == SVRS_BF16) svrs::pack_multi_kernel<__nv_bfloat16><<<total_tiles, 256, smem, st>>>((const svrs::PackJob*)jobs, njobs);
+    if (dtype == SVRS_F32) SVRS_LAUNCH((svrs::pack_multi_kernel<float>), total_tiles, 256, smem, st, (const svrs::PackJob*)jobs, njobs);
+    else if (dtype == SVRS_BF16) SVRS_LAUNCH((svrs::pack_multi_kernel<__nv_bfloat16>), total_tiles, 256, smem, st, (const svrs::PackJob*)jobs, njobs);
     else { set_error("pack_weights_multi: bad dtype"); return SVRS_E_ARG; }
     return check_launch("pack_weights_multi");
 }

@@ -4,6 +4,7 @@
 namespace svrs {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ acc) {
+    pdl_entry();
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gsize = (long long)gridDim.x * blockDim.x;
     double s = 0.0;
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
                                                          const double* __restrict__ sumsq, float max_norm, float grad_scale,
                                                          float lr, float b1, float b2, float eps,
                                                          const long long* __restrict__ step_ptr) {
+    pdl_entry();
     __shared__ float s_coef, s_step_size, s_bc2_sqrt;
     if (threadIdx.x == 0) {
         float coef = grad_scale;
@@ -60,7 +62,8 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
     }
 }
 
-__global__ void step_increment_kernel(long long* s) { *s += 1; }
+__global__ void step_increment_kernel(long long* s) {
+    pdl_entry(); *s += 1; }
 
 }  // namespace svrs
 
@@ -72,7 +75,7 @@ extern "C" int svrs_sumsq(const float* g, int64_t n, double* acc, void* stream) 
     long long b = (n / 4 + 255) / 256, cap = 8LL * num_sms();
     if (b > cap) b = cap;
     if (b < 1) b = 1;
-    sumsq_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(g, n, acc);
+    SVRS_LAUNCH((sumsq_kernel), (unsigned)b, 256, 0, (cudaStream_t)stream, g, n, acc);
     return check_launch("sumsq");
 }
 
@@ -83,13 +86,13 @@ extern "C" int svrs_clip_adam(float* p, const float* g, float* m, float* v, int6
     if (n == 0) return 0;
     long long b = (n + 255) / 256, cap = 16LL * num_sms();
     if (b > cap) b = cap;
-    clip_adam_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps,
+    SVRS_LAUNCH((clip_adam_kernel), (unsigned)b, 256, 0, (cudaStream_t)stream, p, g, m, v, n, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps,
                                                                      (const long long*)step_ptr);
     return check_launch("clip_adam");
 }
 
 extern "C" int svrs_step_increment(int64_t* step_ptr, void* stream) {
     SVRS_CHECK_ARG(step_ptr, "step_increment: null");
-    step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)step_ptr);
+    SVRS_LAUNCH((step_increment_kernel), 1, 1, 0, (cudaStream_t)stream, (long long*)step_ptr);
     return check_launch("step_increment");
 }

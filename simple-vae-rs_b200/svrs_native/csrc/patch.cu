@@ -13,6 +13,7 @@ __device__ __forceinline__ float load_src(const TS* p) { return (float)(*p); }
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) grid_patch_kernel(const TS* __restrict__ tiles, TD* __restrict__ dst, int nhwc,
                                                           int C, int S, int P) {
+    pdl_entry();
     __shared__ float s_mn[MAXC], s_mx[MAXC];
     __shared__ float red_mn[8], red_mx[8];
     const int per_side = S / P;
@@ -71,12 +72,12 @@ extern "C" int svrs_grid_patch_normalize(const void* tiles, int src_is_i16, void
     unsigned blocks = (unsigned)(T * (S / P) * (S / P));
     cudaStream_t st = (cudaStream_t)stream;
     if (src_is_i16) {
-        if (dst_dtype == SVRS_F32) grid_patch_kernel<short, float><<<blocks, 256, 0, st>>>((const short*)tiles, (float*)dst, nhwc, C, S, P);
-        else if (dst_dtype == SVRS_BF16) grid_patch_kernel<short, __nv_bfloat16><<<blocks, 256, 0, st>>>((const short*)tiles, (__nv_bfloat16*)dst, nhwc, C, S, P);
+        if (dst_dtype == SVRS_F32) SVRS_LAUNCH((grid_patch_kernel<short, float>), blocks, 256, 0, st, (const short*)tiles, (float*)dst, nhwc, C, S, P);
+        else if (dst_dtype == SVRS_BF16) SVRS_LAUNCH((grid_patch_kernel<short, __nv_bfloat16>), blocks, 256, 0, st, (const short*)tiles, (__nv_bfloat16*)dst, nhwc, C, S, P);
         else { set_error("grid_patch_normalize: bad dtype"); return SVRS_E_ARG; }
     } else {
-        if (dst_dtype == SVRS_F32) grid_patch_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)tiles, (float*)dst, nhwc, C, S, P);
-        else if (dst_dtype == SVRS_BF16) grid_patch_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)tiles, (__nv_bfloat16*)dst, nhwc, C, S, P);
+        if (dst_dtype == SVRS_F32) SVRS_LAUNCH((grid_patch_kernel<float, float>), blocks, 256, 0, st, (const float*)tiles, (float*)dst, nhwc, C, S, P);
+        else if (dst_dtype == SVRS_BF16) SVRS_LAUNCH((grid_patch_kernel<float, __nv_bfloat16>), blocks, 256, 0, st, (const float*)tiles, (__nv_bfloat16*)dst, nhwc, C, S, P);
         else { set_error("grid_patch_normalize: bad dtype"); return SVRS_E_ARG; }
     }
     return check_launch("grid_patch_normalize");

@@ -39,6 +39,7 @@ struct alignas(64) WhParams {
 };
 
 __global__ void __launch_bounds__(WH_THREADS, 1) wgrad3_halo_kernel(const __grid_constant__ WhParams p) {
+    pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + WH_STAGES * WH_STAGE_BYTES;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad3_halo_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();     // prologue above overlaps the previous kernel; nothing before this line touches global memory
 
     int w = blockIdx.x;
     const int bj = w % p.b_chunks; w /= p.b_chunks;     // 64-channel chunk of X (b)
@@ -257,7 +259,7 @@ int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float*
         if (rc) return rc;
     }
     int grid = base * p.ksplit;
-    wgrad3_halo_kernel<<<grid, WH_THREADS, WH_SMEM_BYTES, st>>>(p);
+    SVRS_LAUNCH((wgrad3_halo_kernel), grid, WH_THREADS, WH_SMEM_BYTES, st, p);
     return check_launch("wgrad3_halo_kernel");
 }
 

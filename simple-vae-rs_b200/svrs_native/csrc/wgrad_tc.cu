@@ -51,6 +51,7 @@ struct alignas(64) WgParams {
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+    pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + WG_STAGES * WG_STAGE_BYTES;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();     // prologue above overlaps the previous kernel; nothing before this line touches global memory
     if (prof && threadIdx.x == 0) prof[1] = clock64();
 
     // work item: (pixel split ks, column tile nt, M-block group grp)
@@ -358,7 +360,7 @@ int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw
         cudaMalloc(&p.prof, sizeof(long long) * 8 * grid);
         cudaMemset(p.prof, 0, sizeof(long long) * 8 * grid);
     }
-    wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(p);
+    SVRS_LAUNCH((wgrad_tc_kernel), grid, WG_THREADS, WG_SMEM_BYTES, st, p);
     if (prof_on) wg_prof_report(p, grid, p.prof);
     return check_launch("wgrad_tc_kernel");
 }
