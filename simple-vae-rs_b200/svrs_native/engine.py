@@ -219,6 +219,12 @@ class Runtime:
         self._side: Optional[torch.cuda.Stream] = None
         self._side_busy = False
         self._wg_keep: list = []   # operands of in-flight side-stream wgrads (kept alive until the join)
+        # Independent sub-networks (encoder_y | encoder_x | y_to_z, decoder_y | prior heads | decoder_x, and their
+        # backward passes) run on parallel branch streams: their small-map layers are latency-bound and leave most SMs
+        # idle.  SVRS_BRANCH_STREAMS=0 serialises them.
+        self.branch_streams = os.environ.get("SVRS_BRANCH_STREAMS", "1") != "0"
+        self._branches: List[torch.cuda.Stream] = []
+        self._branch_open: List[bool] = []
 
     # kernels of libsvrs_b200.so enqueued so far (bench.py's gpu_launches): the library counts every launch site itself
     # (svrs_launch_count); graph replays add the number of kernels captured in the graph.  The `+= n` bookkeeping at the
@@ -283,6 +289,41 @@ class Runtime:
         lib.fill_zero(_p(self.store.grad), self.store.grad.numel() * 4, _st())
         lib.fill_zero(_p(self.store.gpack), self.store.gpack.numel() * 4, _st())
         self.launches += 2
+
+    def branch(self, i: int):
+        """Context manager: run the enclosed launches on branch stream `i`, forked from the current stream.
+        Memory rules (torch caching allocator): tensors allocated inside belong to the branch stream's pool and may be
+        consumed by the parent after join(); tensors of the parent that the branch reads must stay referenced until
+        join() - every caller keeps them in locals / the tape."""
+        rt = self
+
+        class _Branch:
+            def __enter__(self_b):
+                if not rt.branch_streams:
+                    return self_b
+                while len(rt._branches) <= i:
+                    rt._branches.append(torch.cuda.Stream(device=rt.device))
+                    rt._branch_open.append(False)
+                s_ = rt._branches[i]
+                s_.wait_stream(torch.cuda.current_stream())
+                rt._branch_open[i] = True
+                self_b.cm = torch.cuda.stream(s_)
+                self_b.cm.__enter__()
+                return self_b
+
+            def __exit__(self_b, *exc):
+                if rt.branch_streams:
+                    self_b.cm.__exit__(*exc)
+                return False
+
+        return _Branch()
+
+    def join(self, *idx: int):
+        """The current stream waits for the given branch streams."""
+        for i in idx:
+            if i < len(self._branches) and self._branch_open[i]:
+                torch.cuda.current_stream().wait_stream(self._branches[i])
+                self._branch_open[i] = False
 
     def _wgrad_stream(self, *operands) -> int:
         """Stream handle for a weight-gradient launch whose operands were produced by work already enqueued on the
@@ -575,54 +616,59 @@ class CondEngine:
         y_nhwc = rt.to_nhwc(y, 4 * (P // 2) ** 2, B, 4, P // 2, P // 2)
         x_nhwc = rt.to_nhwc(x, 4 * P * P, B, 4, P, P)
 
-        # q(u|y): encoder_y -> chunk -> reparameterize (RNG draw #1)
-        ey, ctx["t_ey"] = rt.net_forward(N["encoder_y"], y_nhwc, training, save)
         enc_u = torch.empty((B, 2 * Wu), **f32)
-        rt.to_nchw(ey, enc_u, 2 * Wu)
         u = torch.empty((B, Wu), **f32)
-        reparam_fwd(rt, enc_u, eps_u, u, Wu, B, Wu, self.rng, 0)
-
-        # q(z|x): encoder_x -> chunk -> reparameterize (draw #2); z lands in the right half of `stack`
-        ex, ctx["t_ex"] = rt.net_forward(N["encoder_x"], x_nhwc, training, save)
         enc_z = torch.empty((B, 2 * Wz), **f32)
-        rt.to_nchw(ex, enc_z, 2 * Wz)
         stack = torch.empty((B, 2 * Wz), **f32)          # torch.cat((y_enc, z), dim=1)  cond_vae.py:272
-        reparam_fwd(rt, enc_z, eps_z, stack.data_ptr() + 4 * Wz, 2 * Wz, B, Wz, self.rng, 1)
-
-        # y_to_z once (two BN running-stat updates)
-        yz, ctx["t_yz"] = rt.net_forward(N["y_to_z"], y_nhwc, training, save, bn_updates=2)
-        rt.to_nchw(yz, stack, 2 * Wz)                    # left half of stack = y_enc flat
-
-        # u_to_z on u re-viewed as (Lu/16, P/16, P/16)   cond_vae.py:168-175
-        u16 = rt.to_nhwc(u, Wu, B, self.cu16, h16, h16)
-        uz, ctx["t_uz"] = rt.net_forward(N["u_to_z"], u16, training, save)
-
-        # jointure = cat(y_enc, u_enc) viewed (2L/16, P/16, P/16) == channel concat in NHWC
-        c16 = self.c16
-        joint = torch.empty((B, h16, h16, 2 * c16), device=dev, dtype=rt.dtype)
-        rows = B * h16 * h16
-        es = joint.element_size()
-        rt.copy2d(yz, c16, joint, 2 * c16, rows, c16)
-        lib.copy2d(_p(uz), rt.dt, c16, joint.data_ptr() + es * c16, rt.dt, 2 * c16, rows, c16, 0, _st())
-        rt.launches += 1
-        m3, ctx["t_mu"] = rt.net_forward(N["mu_u_y_to_z"], joint, training, save)
-        l3, ctx["t_lv"] = rt.net_forward(N["logvar_u_y_to_z"], joint, training, save)
         mu3 = torch.empty((B, Wz), **f32)
         lv3 = torch.empty((B, Wz), **f32)
-        rt.to_nchw(m3, mu3, Wz)
-        rt.to_nchw(l3, lv3, Wz)
+        x_hat = torch.empty((B, 4, P, P), **f32)
+        y_hat = torch.empty((B, 4, P // 2, P // 2), **f32)
 
+        # ---- phase 1: three independent encoders -------------------------------------------------------------------
+        with rt.branch(0):
+            # q(u|y): encoder_y -> chunk -> reparameterize (RNG draw #1; Philox is counter-based, so the
+            # draw order is a naming convention - stream ids 0 / 1 - not an execution order)
+            ey, ctx["t_ey"] = rt.net_forward(N["encoder_y"], y_nhwc, training, save)
+            rt.to_nchw(ey, enc_u, 2 * Wu)
+            reparam_fwd(rt, enc_u, eps_u, u, Wu, B, Wu, self.rng, 0)
+        with rt.branch(1):
+            # y_to_z once (two BN running-stat updates)
+            yz, ctx["t_yz"] = rt.net_forward(N["y_to_z"], y_nhwc, training, save, bn_updates=2)
+            rt.to_nchw(yz, stack, 2 * Wz)                # left half of stack = y_enc flat
+        # q(z|x): encoder_x -> chunk -> reparameterize (draw #2); z lands in the right half of `stack`
+        ex, ctx["t_ex"] = rt.net_forward(N["encoder_x"], x_nhwc, training, save)
+        rt.to_nchw(ex, enc_z, 2 * Wz)
+        reparam_fwd(rt, enc_z, eps_z, stack.data_ptr() + 4 * Wz, 2 * Wz, B, Wz, self.rng, 1)
+        rt.join(0, 1)
+
+        # ---- phase 2: decoder_y | prior heads | decoder_x -----------------------------------------------------------
+        with rt.branch(0):
+            # decode_y(u): u viewed (Lu/64, P/8, P/8)
+            u8 = rt.to_nhwc(u, Wu, B, self.cu, h8, h8)
+            yh, ctx["t_dy"] = rt.net_forward(N["decoder_y"], u8, training, save)
+            rt.to_nchw(yh, y_hat, 4 * (P // 2) ** 2)
+        with rt.branch(1):
+            # u_to_z on u re-viewed as (Lu/16, P/16, P/16)   cond_vae.py:168-175
+            u16 = rt.to_nhwc(u, Wu, B, self.cu16, h16, h16)
+            uz, ctx["t_uz"] = rt.net_forward(N["u_to_z"], u16, training, save)
+            # jointure = cat(y_enc, u_enc) viewed (2L/16, P/16, P/16) == channel concat in NHWC
+            c16 = self.c16
+            joint = torch.empty((B, h16, h16, 2 * c16), device=dev, dtype=rt.dtype)
+            rows = B * h16 * h16
+            es = joint.element_size()
+            rt.copy2d(yz, c16, joint, 2 * c16, rows, c16)
+            lib.copy2d(_p(uz), rt.dt, c16, joint.data_ptr() + es * c16, rt.dt, 2 * c16, rows, c16, 0, _st())
+            rt.launches += 1
+            m3, ctx["t_mu"] = rt.net_forward(N["mu_u_y_to_z"], joint, training, save)
+            l3, ctx["t_lv"] = rt.net_forward(N["logvar_u_y_to_z"], joint, training, save)
+            rt.to_nchw(m3, mu3, Wz)
+            rt.to_nchw(l3, lv3, Wz)
         # decode_x(z, y): stack viewed (2L/64, P/8, P/8)
         s8 = rt.to_nhwc(stack, 2 * Wz, B, 2 * self.cz, h8, h8)
         xh, ctx["t_dx"] = rt.net_forward(N["decoder_x"], s8, training, save)
-        x_hat = torch.empty((B, 4, P, P), **f32)
         rt.to_nchw(xh, x_hat, 4 * P * P)
-
-        # decode_y(u): u viewed (Lu/64, P/8, P/8)
-        u8 = rt.to_nhwc(u, Wu, B, self.cu, h8, h8)
-        yh, ctx["t_dy"] = rt.net_forward(N["decoder_y"], u8, training, save)
-        y_hat = torch.empty((B, 4, P // 2, P // 2), **f32)
-        rt.to_nchw(yh, y_hat, 4 * (P // 2) ** 2)
+        rt.join(0, 1)
 
         if save:
             ctx.update(B=B, enc_u=enc_u, enc_z=enc_z, eps_u=eps_u, eps_z=eps_z, rng=RngState(**vars(self.rng)))
@@ -649,68 +695,72 @@ class CondEngine:
             rt.launches += 1
             return t
 
-        # decoder_x
-        d_stack = None
+        # ---- phase 1: decoder_y | prior heads + u_to_z | decoder_x (independent until the latents) ------------------
+        d_stack = d_u = d_yz = du16 = None
+        with rt.branch(0):
+            if d_yhat is not None:
+                g_y = rt.to_nhwc(d_yhat.contiguous(), 4 * (P // 2) ** 2, B, 4, P // 2, P // 2)
+                du8 = rt.net_backward(N["decoder_y"], ctx["t_dy"], g_y, True)
+                d_u = torch.empty((B, Wu), **f32)
+                rt.to_nchw(du8, d_u, Wu)
+        with rt.branch(1):
+            d_joint = None
+            for key, tape, net in ((d_mu3, "t_mu", "mu_u_y_to_z"), (d_lv3, "t_lv", "logvar_u_y_to_z")):
+                if key is None:
+                    continue
+                g_h = rt.to_nhwc(key.contiguous(), Wz, B, c16, h16, h16)
+                dj = rt.net_backward(N[net], ctx[tape], g_h, True)
+                if d_joint is None:
+                    d_joint = dj
+                else:
+                    rt.copy2d(dj, 2 * c16, d_joint, 2 * c16, rows, 2 * c16, accumulate=True)
+            # gradient wrt y_to_z output (NHWC) and u_to_z output
+            if d_joint is not None:
+                es = d_joint.element_size()
+                d_yz = torch.empty((B, h16, h16, c16), device=dev, dtype=rt.dtype)
+                d_uz = torch.empty((B, h16, h16, c16), device=dev, dtype=rt.dtype)
+                rt.copy2d(d_joint, 2 * c16, d_yz, c16, rows, c16)
+                lib.copy2d(d_joint.data_ptr() + es * c16, rt.dt, 2 * c16, _p(d_uz), rt.dt, c16, rows, c16, 0, _st())
+                rt.launches += 1
+                du16 = rt.net_backward(N["u_to_z"], ctx["t_uz"], d_uz, True)
         if d_xhat is not None:
-            g = rt.to_nhwc(d_xhat.contiguous(), 4 * P * P, B, 4, P, P)
-            ds8 = rt.net_backward(N["decoder_x"], ctx["t_dx"], g, True)
+            g_x = rt.to_nhwc(d_xhat.contiguous(), 4 * P * P, B, 4, P, P)
+            ds8 = rt.net_backward(N["decoder_x"], ctx["t_dx"], g_x, True)
             d_stack = torch.empty((B, 2 * Wz), **f32)
             rt.to_nchw(ds8, d_stack, 2 * Wz)
-        # decoder_y
-        d_u = None
-        if d_yhat is not None:
-            g = rt.to_nhwc(d_yhat.contiguous(), 4 * (P // 2) ** 2, B, 4, P // 2, P // 2)
-            du8 = rt.net_backward(N["decoder_y"], ctx["t_dy"], g, True)
-            d_u = torch.empty((B, Wu), **f32)
-            rt.to_nchw(du8, d_u, Wu)
-        # prior heads
-        d_joint = None
-        for key, tape, net in ((d_mu3, "t_mu", "mu_u_y_to_z"), (d_lv3, "t_lv", "logvar_u_y_to_z")):
-            if key is None:
-                continue
-            g = rt.to_nhwc(key.contiguous(), Wz, B, c16, h16, h16)
-            dj = rt.net_backward(N[net], ctx[tape], g, True)
-            if d_joint is None:
-                d_joint = dj
-            else:
-                rt.copy2d(dj, 2 * c16, d_joint, 2 * c16, rows, 2 * c16, accumulate=True)
-        # gradient wrt y_to_z output (NHWC) and u_to_z output
-        d_yz = None
-        if d_joint is not None:
-            es = d_joint.element_size()
-            d_yz = torch.empty((B, h16, h16, c16), device=dev, dtype=rt.dtype)
-            d_uz = torch.empty((B, h16, h16, c16), device=dev, dtype=rt.dtype)
-            rt.copy2d(d_joint, 2 * c16, d_yz, c16, rows, c16)
-            lib.copy2d(d_joint.data_ptr() + es * c16, rt.dt, 2 * c16, _p(d_uz), rt.dt, c16, rows, c16, 0, _st())
-            rt.launches += 1
-            du16 = rt.net_backward(N["u_to_z"], ctx["t_uz"], d_uz, True)
+        rt.join(0, 1)
+        if du16 is not None:
             if d_u is None:
                 d_u = zeros(B, Wu)
             rt.to_nchw(du16, d_u, Wu, accumulate=True)
         if d_stack is not None:
-            g = rt.to_nhwc(d_stack, 2 * Wz, B, c16, h16, h16)   # left half rows: y_enc as (L/16, P/16, P/16)
+            g_s = rt.to_nhwc(d_stack, 2 * Wz, B, c16, h16, h16)   # left half rows: y_enc as (L/16, P/16, P/16)
             if d_yz is None:
-                d_yz = g
+                d_yz = g_s
             else:
-                rt.copy2d(g, c16, d_yz, c16, rows, c16, accumulate=True)
-        if d_yz is not None:
-            rt.net_backward(N["y_to_z"], ctx["t_yz"], d_yz, False)
+                rt.copy2d(g_s, c16, d_yz, c16, rows, c16, accumulate=True)
+        # ---- phase 2: y_to_z | encoder_y | encoder_x ------------------------------------------------------------------
+        with rt.branch(0):
+            if d_yz is not None:
+                rt.net_backward(N["y_to_z"], ctx["t_yz"], d_yz, False)
+        with rt.branch(1):
+            # encoder_y through reparameterize(u)
+            if d_enc_u is None and d_u is not None:
+                d_enc_u = zeros(B, 2 * Wu)
+            if d_enc_u is not None:
+                if d_u is not None:
+                    reparam_bwd(rt, ctx["enc_u"], ctx["eps_u"], d_u, Wu, d_enc_u, B, Wu, rng, 0)
+                g_eu = rt.to_nhwc(d_enc_u, 2 * Wu, B, 2 * self.cu, h8, h8)
+                rt.net_backward(N["encoder_y"], ctx["t_ey"], g_eu, False)
         # encoder_x through reparameterize(z)
         if d_enc_z is None and d_stack is not None:
             d_enc_z = zeros(B, 2 * Wz)
         if d_enc_z is not None:
             if d_stack is not None:
                 reparam_bwd(rt, ctx["enc_z"], ctx["eps_z"], d_stack.data_ptr() + 4 * Wz, 2 * Wz, d_enc_z, B, Wz, rng, 1)
-            g = rt.to_nhwc(d_enc_z, 2 * Wz, B, 2 * self.cz, h8, h8)
-            rt.net_backward(N["encoder_x"], ctx["t_ex"], g, False)
-        # encoder_y through reparameterize(u)
-        if d_enc_u is None and d_u is not None:
-            d_enc_u = zeros(B, 2 * Wu)
-        if d_enc_u is not None:
-            if d_u is not None:
-                reparam_bwd(rt, ctx["enc_u"], ctx["eps_u"], d_u, Wu, d_enc_u, B, Wu, rng, 0)
-            g = rt.to_nhwc(d_enc_u, 2 * Wu, B, 2 * self.cu, h8, h8)
-            rt.net_backward(N["encoder_y"], ctx["t_ey"], g, False)
+            g_ez = rt.to_nhwc(d_enc_z, 2 * Wz, B, 2 * self.cz, h8, h8)
+            rt.net_backward(N["encoder_x"], ctx["t_ex"], g_ez, False)
+        rt.join(0, 1)
         rt.finish_grads()
 
     # ---- inference: Cond_SRVAE.sample (cond_vae.py:299-318) ---------------------------------------

@@ -77,11 +77,12 @@ def dominant_kernel_roofline(tr, step_from_device, inputs, pk, steps: int = 2):
         else:
             tr.step(dataset.grid_patch_normalize(hr, P), use_graph=False)
 
-    side, tr.rt.wgrad_side = tr.rt.wgrad_side, False      # per-call event brackets only see the current stream
+    side, tr.rt.wgrad_side = tr.rt.wgrad_side, False      # per-call event brackets only see the current stream,
+    br, tr.rt.branch_streams = tr.rt.branch_streams, False  # and kernels must not overlap while they are being timed
     try:
         per = time_step(eager, steps)
     finally:
-        tr.rt.wgrad_side = side
+        tr.rt.wgrad_side, tr.rt.branch_streams = side, br
     fam = defaultdict(lambda: [0.0, 0.0, 0.0, 0.0])
     total_ms = sum(v[0] for v in per.values())
     for (name, kernels), (ms, n, fl, by) in per.items():

@@ -4,6 +4,7 @@
 import argparse
 import os
 os.environ.setdefault("SVRS_WGRAD_STREAM", "0")   # per-call event brackets only see the current stream
+os.environ.setdefault("SVRS_BRANCH_STREAMS", "0")
 import sys
 from collections import defaultdict
 
