@@ -132,6 +132,12 @@ int svrs_bn_finalize_train(const double* sums, int64_t M, int C, const float* ga
                            float eps, float momentum, float* running_mean, float* running_var,
                            int64_t* num_batches_tracked, int n_updates,
                            float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* train, fused: svrs_bn_finalize_train + svrs_bn_apply in one launch (same coefficients bit for bit; every block derives
+ * them from `sums`, block 0 publishes scale/shift/mean/invstd and advances the running statistics).  C <= 1024. */
+int svrs_bn_apply_train(const void* x, void* y, int dtype, int64_t M, int C, const double* sums,
+                        const float* gamma, const float* beta, float eps, float momentum,
+                        float* running_mean, float* running_var, int64_t* num_batches_tracked, int n_updates,
+                        int relu, float* scale, float* shift, float* mean, float* invstd, void* stream);
 /* eval: scale/shift from the running statistics */
 int svrs_bn_finalize_eval(int C, const float* gamma, const float* beta, float eps,
                           const float* running_mean, const float* running_var,

@@ -147,6 +147,34 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const T* __restrict__
     }
 }
 
+// scale/shift (+ mean, invstd, unbiased variance) of one channel from its batch sums: the single definition used by the
+// stand-alone finalize kernel and by the fused statistics->apply kernel, so both give bit-identical coefficients
+__device__ __forceinline__ void bn_channel_coeffs(const double* __restrict__ sums, long long M, int C, int c,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                  float& sc, float& sh, float& meanf, float& is, float& unb) {
+    double m = sums[c] / (double)M;
+    double var = sums[C + c] / (double)M - m * m;
+    if (var < 0) var = 0;
+    meanf = (float)m;
+    float varf = (float)var;
+    is = 1.0f / sqrtf(varf + eps);
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    sc = g * is;
+    sh = b - meanf * sc;
+    unb = (M > 1) ? (float)(var * (double)M / (double)(M - 1)) : varf;
+}
+
+__device__ __forceinline__ void bn_update_running(float* __restrict__ rmean, float* __restrict__ rvar, int c, float meanf,
+                                                  float unb, float momentum, int n_updates) {
+    float rm = rmean[c], rv = rvar[c];
+    for (int u = 0; u < n_updates; ++u) {
+        rm = (1.f - momentum) * rm + momentum * meanf;
+        rv = (1.f - momentum) * rv + momentum * unb;
+    }
+    rmean[c] = rm;
+    rvar[c] = rv;
+}
+
 __global__ void bn_finalize_train_kernel(const double* __restrict__ sums, long long M, int C,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float eps, float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
@@ -157,28 +185,13 @@ __global__ void bn_finalize_train_kernel(const double* __restrict__ sums, long l
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && nbt) *nbt += n_updates;
     if (c >= C) return;
-    double m = sums[c] / (double)M;
-    double var = sums[C + c] / (double)M - m * m;
-    if (var < 0) var = 0;
-    float meanf = (float)m;
-    float varf = (float)var;
-    float is = 1.0f / sqrtf(varf + eps);
-    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-    float sc = g * is;
+    float sc, sh, meanf, is, unb;
+    bn_channel_coeffs(sums, M, C, c, gamma, beta, eps, sc, sh, meanf, is, unb);
     scale[c] = sc;
-    shift[c] = b - meanf * sc;
+    shift[c] = sh;
     if (mean_out) mean_out[c] = meanf;
     if (invstd_out) invstd_out[c] = is;
-    if (rmean && rvar) {
-        float unb = (M > 1) ? (float)(var * (double)M / (double)(M - 1)) : varf;
-        float rm = rmean[c], rv = rvar[c];
-        for (int u = 0; u < n_updates; ++u) {
-            rm = (1.f - momentum) * rm + momentum * meanf;
-            rv = (1.f - momentum) * rv + momentum * unb;
-        }
-        rmean[c] = rm;
-        rvar[c] = rv;
-    }
+    if (rmean && rvar) bn_update_running(rmean, rvar, c, meanf, unb, momentum, n_updates);
 }
 
 __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -205,6 +218,60 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
     float sc[V], sh[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; }
+    auto apply = [&](float* v) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { v[j] = fmaf(v[j], sc[j], sh[j]); if (relu) v[j] = fmaxf(v[j], 0.f); }
+    };
+    for (; i + stride < nvec; i += 2 * stride) {
+        float a[V], b[V];
+        ldv<V>(x + i * V, a);
+        ldv<V>(x + (i + stride) * V, b);
+        apply(a); apply(b);
+        stv<V>(y + i * V, a);
+        stv<V>(y + (i + stride) * V, b);
+    }
+    if (i < nvec) {
+        float a[V];
+        ldv<V>(x + i * V, a);
+        apply(a);
+        stv<V>(y + i * V, a);
+    }
+}
+
+// Train-mode finalize + apply in one launch: every block derives the per-channel coefficients from the batch sums into
+// shared memory (C <= 1024), block 0 also publishes them (backward needs scale/shift/mean/invstd) and advances the
+// running statistics.  Saves one tiny launch per BatchNorm layer.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) bn_apply_train_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec, int cg,
+                                                              long long M, int C, const double* __restrict__ sums,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float eps, float momentum, float* __restrict__ rmean,
+                                                              float* __restrict__ rvar, long long* __restrict__ nbt, int n_updates,
+                                                              int relu, float* __restrict__ scale, float* __restrict__ shift,
+                                                              float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+    pdl_entry();
+    __shared__ float s_sc[1024], s_sh[1024];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sc, sh, meanf, is, unb;
+        bn_channel_coeffs(sums, M, C, c, gamma, beta, eps, sc, sh, meanf, is, unb);
+        s_sc[c] = sc;
+        s_sh[c] = sh;
+        if (blockIdx.x == 0) {
+            scale[c] = sc;
+            shift[c] = sh;
+            if (mean_out) mean_out[c] = meanf;
+            if (invstd_out) invstd_out[c] = is;
+            if (rmean && rvar) bn_update_running(rmean, rvar, c, meanf, unb, momentum, n_updates);
+            if (c == 0 && nbt) *nbt += n_updates;
+        }
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c0 = (int)(i % cg) * V;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { sc[j] = s_sc[c0 + j]; sh[j] = s_sh[c0 + j]; }
     auto apply = [&](float* v) {
 #pragma unroll
         for (int j = 0; j < V; ++j) { v[j] = fmaf(v[j], sc[j], sh[j]); if (relu) v[j] = fmaxf(v[j], 0.f); }
@@ -359,6 +426,25 @@ extern "C" int svrs_bn_apply(const void* x, void* y, int dtype, int64_t M, int C
         SVRS_LAUNCH((bn_apply_kernel<__nv_bfloat16, 4>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 4, scale, shift, relu);
     else { set_error("bn_apply: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_apply");
+}
+
+extern "C" int svrs_bn_apply_train(const void* x, void* y, int dtype, int64_t M, int C, const double* sums,
+                                   const float* gamma, const float* beta, float eps, float momentum,
+                                   float* running_mean, float* running_var, int64_t* num_batches_tracked, int n_updates,
+                                   int relu, float* scale, float* shift, float* mean, float* invstd, void* stream) {
+    SVRS_CHECK_ARG(x && y && sums && scale && shift && M > 0 && c_ok(C) && C <= 1024, "bn_apply_train: bad args (C=%d must be 4*2^k <= 1024)", C);
+    const bool w8 = wide(dtype, C);
+    long long nvec = M * C / (w8 ? 8 : 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    long long* nbt = (long long*)num_batches_tracked;
+    if (dtype == SVRS_F32)
+        SVRS_LAUNCH((bn_apply_train_kernel<float, 4>), ew_grid(nvec), 256, 0, st, (const float*)x, (float*)y, nvec, C / 4, (long long)M, C, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, n_updates, relu, scale, shift, mean, invstd);
+    else if (dtype == SVRS_BF16 && w8)
+        SVRS_LAUNCH((bn_apply_train_kernel<__nv_bfloat16, 8>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 8, (long long)M, C, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, n_updates, relu, scale, shift, mean, invstd);
+    else if (dtype == SVRS_BF16)
+        SVRS_LAUNCH((bn_apply_train_kernel<__nv_bfloat16, 4>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 4, (long long)M, C, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, n_updates, relu, scale, shift, mean, invstd);
+    else { set_error("bn_apply_train: bad dtype"); return SVRS_E_ARG; }
+    return check_launch("bn_apply_train");
 }
 
 extern "C" int svrs_bn_bwd_reduce(const void* x, const void* dy, int dtype, int64_t M, int C, const float* scale,

@@ -464,12 +464,17 @@ class Runtime:
                     lib.bn_stats(_p(x), self.dt, m, cch, _p(op.sums_f), st)
                     mom = 0.1 if bn.momentum is None else bn.momentum
                     track = bn.track_running_stats and bn.running_mean is not None
-                    lib.bn_finalize_train(_p(op.sums_f), m, cch, _p(bn.weight), _p(bn.bias), bn.eps, mom,
-                                          _p(bn.running_mean) if track else None,
-                                          _p(bn.running_var) if track else None,
-                                          _p(bn.num_batches_tracked) if track else None, bn_updates,
-                                          _p(scale), _p(shift), _p(mean), _p(invstd), st)
+                    y = torch.empty_like(x) if save else x
+                    lib.bn_apply_train(_p(x), _p(y), self.dt, m, cch, _p(op.sums_f), _p(bn.weight), _p(bn.bias), bn.eps, mom,
+                                       _p(bn.running_mean) if track else None,
+                                       _p(bn.running_var) if track else None,
+                                       _p(bn.num_batches_tracked) if track else None, bn_updates, int(op.relu),
+                                       _p(scale), _p(shift), _p(mean), _p(invstd), st)
                     self.launches += 3
+                    if save:
+                        tape.append((op, x, scale, shift, mean, invstd))
+                    x = y
+                    continue
                 else:
                     mean = invstd = None
                     lib.bn_finalize_eval(cch, _p(bn.weight), _p(bn.bias), bn.eps, _p(bn.running_mean),

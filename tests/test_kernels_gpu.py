@@ -213,6 +213,39 @@ def test_batchnorm_eval():
     report("bn eval", nchw(xd), yr, 1e-5)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(4, 16, 8, 8), (2, 64, 16, 16), (3, 256, 4, 4), (2, 1024, 2, 2)])
+def test_bn_apply_train_fused_equals_two_step(shape, dtype):
+    """svrs_bn_apply_train == svrs_bn_finalize_train + svrs_bn_apply, bit for bit (outputs, saved statistics, running stats)."""
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(N * C + H)
+    x = nhwc((torch.randn(shape, generator=g) * 1.7 + 0.6).to(DEV), dtype)
+    M = N * H * W
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    beta = torch.randn(C, generator=g).to(DEV)
+    sums = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    lib.bn_stats(x.data_ptr(), dt(dtype), M, C, sums.data_ptr(), st())
+    outs = []
+    for fused in (0, 1):
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        nbt = torch.zeros((), device=DEV, dtype=torch.int64)
+        scale, shift, mean, invstd = (torch.empty(C, device=DEV) for _ in range(4))
+        y = torch.empty_like(x)
+        if fused:
+            lib.bn_apply_train(x.data_ptr(), y.data_ptr(), dt(dtype), M, C, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1,
+                               rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(), 2, 1, scale.data_ptr(), shift.data_ptr(),
+                               mean.data_ptr(), invstd.data_ptr(), st())
+        else:
+            lib.bn_finalize_train(sums.data_ptr(), M, C, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(),
+                                  nbt.data_ptr(), 2, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), st())
+            lib.bn_apply(x.data_ptr(), y.data_ptr(), dt(dtype), M, C, scale.data_ptr(), shift.data_ptr(), 1, st())
+        torch.cuda.synchronize()
+        outs.append((y, scale, shift, mean, invstd, rm, rv, nbt))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert int(outs[1][7]) == 2
+
+
 def test_layout_roundtrip_and_views():
     g = torch.Generator().manual_seed(2)
     x = torch.randn(3, 6, 4, 5, generator=g).to(DEV)
