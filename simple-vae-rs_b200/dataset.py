@@ -70,6 +70,58 @@ class TileDataset(torch.utils.data.Dataset):
         return self.lr[i], self.hr[i]
 
 
+class TilePrefetcher:
+    """Double-buffered host->device feed: the pinned tile batch of step i+1 is copied on a dedicated copy stream while
+    step i computes (what DataLoader(pin_memory=True) + .to(non_blocking=True) gives the reference).  `batches` yields
+    (lr_host, hr_host) tensors of constant shape; iteration yields device tensors that stay valid until the next but one
+    iteration.  Synchronisation is by CUDA events only (no host sync)."""
+
+    def __init__(self, batches, device="cuda", depth: int = 2):
+        self.batches, self.device, self.depth = batches, torch.device(device), depth
+
+    def __iter__(self):
+        it = iter(self.batches)
+        copy_stream = torch.cuda.Stream(device=self.device)
+        bufs, ready, free = [], [], []
+        pending = []          # slots whose copy has been issued, in order
+
+        def issue(slot):
+            try:
+                lr_h, hr_h = next(it)
+            except StopIteration:
+                return False
+            if slot == len(bufs):
+                bufs.append((torch.empty(lr_h.shape, dtype=lr_h.dtype, device=self.device),
+                             torch.empty(hr_h.shape, dtype=hr_h.dtype, device=self.device)))
+                ready.append(torch.cuda.Event())
+                free.append(None)
+            with torch.cuda.stream(copy_stream):
+                if free[slot] is not None:
+                    copy_stream.wait_event(free[slot])       # the step that last read this slot has finished
+                bufs[slot][0].copy_(lr_h, non_blocking=True)
+                bufs[slot][1].copy_(hr_h, non_blocking=True)
+                ready[slot].record(copy_stream)
+            pending.append(slot)
+            return True
+
+        nxt = 0
+        for _ in range(self.depth - 1):
+            if issue(nxt % self.depth):
+                nxt += 1
+        while True:
+            if issue(nxt % self.depth):
+                nxt += 1
+            if not pending:
+                return
+            slot = pending.pop(0)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready[slot])
+            yield bufs[slot]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            free[slot] = ev
+
+
 class GridPatchLoader:
     """Iterates tile batches and emits (y, x) patch batches produced on the device - the on-device equivalent
     of DataLoader(Sen2VenDataset(crop="grid"), collate_fn=grid_collate)."""
@@ -85,11 +137,30 @@ class GridPatchLoader:
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         n = len(self.ds)
         order = torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
-        for i in range(0, n, self.tpb):
-            idx = order[i:i + self.tpb]
-            lr = self.ds.lr[idx].to(self.device, non_blocking=True)
-            hr = self.ds.hr[idx].to(self.device, non_blocking=True)
-            yield grid_batch(lr, hr, self.P)
+        if self.ds.lr.is_cuda:
+            for i in range(0, n, self.tpb):
+                idx = order[i:i + self.tpb]
+                yield grid_batch(self.ds.lr[idx.to(self.ds.lr.device)], self.ds.hr[idx.to(self.ds.hr.device)], self.P)
+            return
+
+        def host_batches():
+            full = [order[i:i + self.tpb] for i in range(0, n, self.tpb)]
+            for idx in full:
+                lr_h, hr_h = self.ds.lr[idx], self.ds.hr[idx]
+                if len(idx) == self.tpb:                    # constant-shape batches go through pinned staging
+                    lr_h, hr_h = lr_h.pin_memory(), hr_h.pin_memory()
+                yield lr_h, hr_h
+
+        tail = n % self.tpb
+        batches = list(host_batches()) if tail else None
+        if tail:                                            # ragged last batch: plain copy (shape differs from the buffers)
+            for lr_h, hr_h in TilePrefetcher(batches[:-1], self.device):
+                yield grid_batch(lr_h, hr_h, self.P)
+            lr_h, hr_h = batches[-1]
+            yield grid_batch(lr_h.to(self.device), hr_h.to(self.device), self.P)
+        else:
+            for lr_d, hr_d in TilePrefetcher(host_batches(), self.device):
+                yield grid_batch(lr_d, hr_d, self.P)
 
 
 def init_dataloader(dataset: str, batch_size: int = 16, patch_size: int = 64, device="cuda", n_tiles: int = 64):
