@@ -124,7 +124,10 @@ int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, float* dw_packe
                        int N, int H, int W, int Cin, int Cout, int ksplit, void* stream);
 
 /* ---- nn.BatchNorm2d (+ nn.ReLU) of down_block / up_block (layers.py:237-238,252-255,278-279,293-296)
- *      x viewed as [M = N*H*W][C].  `sums` is a zeroed double[2*C] scratch (sum, sum of squares). */
+ *      x viewed as [M = N*H*W][C].  `sums` is a zeroed scratch of SVRS_BN_REPLICAS x double[2*C] (sum, sum of squares):
+ *      the reduce kernels spread their atomics over the replicas (same-line double atomics serialise), every consumer
+ *      (finalize, apply_train, bwd_apply) adds the replicas up. */
+#define SVRS_BN_REPLICAS 8
 int svrs_bn_stats(const void* x, int dtype, int64_t M, int C, double* sums, void* stream);
 /* train: batch stats -> scale/shift (+ saved mean/invstd), running stats updated `n_updates` times
  * (y_to_z runs twice per forward) and *num_batches_tracked += n_updates (may be NULL). */

@@ -2,6 +2,8 @@
 // Statistics are accumulated in double (per-thread double partials, double atomics) so that the
 // E[x^2]-E[x]^2 form is exact to fp32 output precision (fp32 parity mode needs 1e-5).
 #include "common.cuh"
+#include <stdlib.h>
+#include "tc_ptx.cuh"
 
 namespace svrs {
 
@@ -54,6 +56,54 @@ template <int V> __device__ __forceinline__ void stv(__nv_bfloat16* p, const flo
     else *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
 }
 
+// Forward statistics of bf16 tensors are accumulated as fp32 sums of (x - k) and (x - k)^2 with k = the channel's first
+// sample (FP64 throughput, not HBM, bound the per-element double version: 2.7 TB/s).  A shift within a few sigma of the mean
+// removes the E[x^2] - E[x]^2 cancellation that rules out plain fp32 sums; the shift is undone in double per thread:
+//   sum x = S1 + n k ,  sum x^2 = S2 + 2 k S1 + n k^2.   fp32 tensors (parity mode) keep the per-element double path.
+template <int V>
+__device__ __forceinline__ void unshift_sums(double* s0, double* s1, const float* k, long long n) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const double kd = (double)k[j], S1 = s0[j], S2 = s1[j];
+        s0[j] = S1 + (double)n * kd;
+        s1[j] = S2 + 2.0 * kd * S1 + (double)n * kd * kd;
+    }
+}
+
+// End of a reduce block: fold the row lanes through shared memory (`red`: 256 x V doubles) and add the block's 2C sums
+// to ONE of SVRS_BN_REPLICAS copies of the `sums` scratch (replica = block index mod R); every reader adds the replicas
+// up (bn_load_sums).  Measured: double atomics on the same 128-byte line serialise at ~3 ns each, so ~300 blocks x 16
+// channels per line put a ~15 us floor under every reduce launch, whatever the tensor size; 8 replicas cut it 8x.
+// (Thread-block clusters + DSMEM gave the same reduction in atomics but halved the bandwidth of the large launches:
+// clusters of 8 one-CTA-per-SM blocks leave SMs of every GPC unused.)
+template <int V>
+__device__ __forceinline__ void block_sums_to_global(const double* s0, const double* s1, double* red, int C, int cg, int q,
+                                                     int lane, int lanes, int c, double* __restrict__ sums) {
+    double* dst = sums + (size_t)(blockIdx.x % SVRS_BN_REPLICAS) * 2 * C;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < V; ++j) red[threadIdx.x * V + j] = half ? s1[j] : s0[j];
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                double acc = 0;
+                for (int l = 0; l < lanes; ++l) acc += red[(l * cg + q) * V + j];
+                atomicAdd(&dst[half * C + c + j], acc);
+            }
+        }
+    }
+}
+// entry e (0 <= e < 2C) of the replicated sums
+__device__ __forceinline__ double bn_load_sums(const double* __restrict__ sums, int C, int e) {
+    double acc = 0;
+#pragma unroll
+    for (int r = 0; r < SVRS_BN_REPLICAS; ++r) acc += sums[(size_t)r * 2 * C + e];
+    return acc;
+}
+
 // thread t owns channel group (t % cg) of V channels and row lane (t / cg); cg = C/V divides 256.  Four rows are loaded
 // per trip so every thread keeps 4 (forward) or 8 (backward) 16-byte loads in flight - these kernels are pure streaming.
 template <typename T, int V, bool BWD>
@@ -85,10 +135,17 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const T* __restrict__
     float p0[V], p1[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) { p0[j] = 0.f; p1[j] = 0.f; }
+    float kshift[V];
+    long long nrows_t = 0;
+    if (!BWD && sizeof(T) == 2) ldv<V>(x + c, kshift);
     auto accumulate = [&](const float* xs, const float* gs) {
-        if (!BWD) {
+        if (!BWD && sizeof(T) == 4) {
 #pragma unroll
             for (int j = 0; j < V; ++j) { s0[j] += (double)xs[j]; s1[j] += (double)xs[j] * (double)xs[j]; }
+        } else if (!BWD) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) { const float d = xs[j] - kshift[j]; p0[j] += d; p1[j] = fmaf(d, d, p1[j]); }
+            ++nrows_t;
         } else {
 #pragma unroll
             for (int j = 0; j < V; ++j) {
@@ -129,22 +186,131 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const T* __restrict__
         accumulate(xs, gs);
     }
     fold();
-    // cross-lane reduction, one statistic at a time (256 x 8 doubles of shared memory)
+    if (!BWD && sizeof(T) == 2) unshift_sums<V>(s0, s1, kshift, nrows_t);
+    block_sums_to_global<V>(s0, s1, red, C, cg, q, lane, lanes, c, sums);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming variant of bn_reduce_kernel for large tensors.  The register-file version above can keep at most
+// threads x 4 rows x 16 B in flight and drains that window every trip (measured 2.0-2.7 TB/s); here ONE thread streams
+// the block's contiguous row range through a shared-memory ring with 1-D bulk copies (cp.async.bulk, mbarrier
+// complete_tx), so 64 KB (forward) / 128 KB (backward) per SM are in flight continuously while all 256 threads only
+// read shared memory and accumulate.  Same thread <-> (channel group, row lane) mapping, same final reduction.
+// ------------------------------------------------------------------------------------------------
+constexpr int BNS_CHUNK = 16384;      // bytes per tensor per stage
+constexpr int BNS_STAGES = 4;
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <typename T, int V, bool BWD>
+__global__ void __launch_bounds__(256) bn_reduce_stream_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                long long M, int C, long long rows_per_block,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                int relu, double* __restrict__ sums) {
+    pdl_entry();
+    extern __shared__ __align__(128) uint8_t bns_smem[];
+    __shared__ __align__(8) unsigned long long bars[BNS_STAGES];
+    constexpr int NT = BWD ? 2 : 1;
+    const int cg = C / V;
+    const int q = threadIdx.x % cg, lane = threadIdx.x / cg, lanes = 256 / cg;
+    const int c = q * V;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    const int row_bytes = C * (int)sizeof(T);
+    const int rows_per_chunk = BNS_CHUNK / row_bytes;
+    const long long nrows = r1 > r0 ? r1 - r0 : 0;
+    const int nchunks = (int)((nrows + rows_per_chunk - 1) / rows_per_chunk);
+    const uint32_t smem0 = smem_u32(bns_smem);
+    auto bar = [&](int s_) { return smem_u32(&bars[s_]); };
+    auto issue = [&](int chunk) {          // thread 0 only
+        const int s_ = chunk % BNS_STAGES;
+        const long long row = r0 + (long long)chunk * rows_per_chunk;
+        long long nr = r1 - row;
+        if (nr > rows_per_chunk) nr = rows_per_chunk;
+        const uint32_t bytes = (uint32_t)nr * (uint32_t)row_bytes;
+        mbar_expect_tx(bar(s_), bytes * NT);
+        bulk_load_1d(smem0 + (uint32_t)(s_ * NT) * BNS_CHUNK, x + row * C, bytes, bar(s_));
+        if (BWD) bulk_load_1d(smem0 + (uint32_t)(s_ * NT + 1) * BNS_CHUNK, dy + row * C, bytes, bar(s_));
+    };
+    if (threadIdx.x == 0) {
+        for (int s_ = 0; s_ < BNS_STAGES; ++s_) mbar_init(bar(s_), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int k = 0; k < BNS_STAGES && k < nchunks; ++k) issue(k);
+
+    double s0[V], s1[V];
+    float p0[V], p1[V];
+    float sc[V], sh[V], mu[V], is[V];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        __syncthreads();
+    for (int j = 0; j < V; ++j) { s0[j] = 0; s1[j] = 0; p0[j] = 0.f; p1[j] = 0.f; }
+    if (BWD) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) red[threadIdx.x * V + j] = half ? s1[j] : s0[j];
-        __syncthreads();
-        if (lane == 0) {
+        for (int j = 0; j < V; ++j) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j]; }
+    }
+    float kshift[V];
+    long long nrows_t = 0;
+    if (!BWD && sizeof(T) == 2) ldv<V>(x + c, kshift);
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int s_ = chunk % BNS_STAGES;
+        mbar_wait(bar(s_), (uint32_t)((chunk / BNS_STAGES) & 1));
+        long long nr = nrows - (long long)chunk * rows_per_chunk;
+        if (nr > rows_per_chunk) nr = rows_per_chunk;
+        const T* xs_ = reinterpret_cast<const T*>(bns_smem + (size_t)(s_ * NT) * BNS_CHUNK);
+        const T* gs_ = reinterpret_cast<const T*>(bns_smem + (size_t)(s_ * NT + 1) * BNS_CHUNK);
+        for (int r = lane; r < (int)nr; r += lanes) {
+            RawVec<T, V> xr, gr;
+            constexpr int NW = V * sizeof(T) / 4;
+            const uint32_t* px = reinterpret_cast<const uint32_t*>(xs_ + (size_t)r * C + c);
+            if (NW == 4) { uint4 v = *reinterpret_cast<const uint4*>(px); xr.w[0] = v.x; xr.w[1] = v.y; xr.w[2] = v.z; xr.w[NW - 1] = v.w; }
+            else { uint2 v = *reinterpret_cast<const uint2*>(px); xr.w[0] = v.x; xr.w[1] = v.y; }
+            float xs[V], gs[V];
+            raw_cvt<V>(xr, xs);
+            if (BWD) {
+                const uint32_t* pg = reinterpret_cast<const uint32_t*>(gs_ + (size_t)r * C + c);
+                if (NW == 4) { uint4 v = *reinterpret_cast<const uint4*>(pg); gr.w[0] = v.x; gr.w[1] = v.y; gr.w[2] = v.z; gr.w[NW - 1] = v.w; }
+                else { uint2 v = *reinterpret_cast<const uint2*>(pg); gr.w[0] = v.x; gr.w[1] = v.y; }
+                raw_cvt<V>(gr, gs);
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                double acc = 0;
-                for (int l = 0; l < lanes; ++l) acc += red[(l * cg + q) * V + j];
-                atomicAdd(&sums[half * C + c + j], acc);
+                for (int j = 0; j < V; ++j) {
+                    float g = gs[j];
+                    if (relu && !(fmaf(xs[j], sc[j], sh[j]) > 0.f)) g = 0.f;
+                    float xh = (xs[j] - mu[j]) * is[j];
+                    p0[j] += g;
+                    p1[j] = fmaf(g, xh, p1[j]);
+                }
+            } else if (sizeof(T) == 4) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) { s0[j] += (double)xs[j]; s1[j] += (double)xs[j] * (double)xs[j]; }
+            } else {
+                // bf16 input: fp32 sums of (x - k), k = the channel's first sample (see bn_reduce_kernel)
+#pragma unroll
+                for (int j = 0; j < V; ++j) { const float d = xs[j] - kshift[j]; p0[j] += d; p1[j] = fmaf(d, d, p1[j]); }
+                ++nrows_t;
             }
         }
+        if ((BWD || sizeof(T) == 2) && (chunk & 3) == 3) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) { s0[j] += (double)p0[j]; s1[j] += (double)p1[j]; p0[j] = 0.f; p1[j] = 0.f; }
+        }
+        __syncthreads();                                   // everyone is done with stage s_
+        if (threadIdx.x == 0 && chunk + BNS_STAGES < nchunks) issue(chunk + BNS_STAGES);
     }
+    if (BWD || sizeof(T) == 2) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { s0[j] += (double)p0[j]; s1[j] += (double)p1[j]; }
+    }
+    if (!BWD && sizeof(T) == 2) unshift_sums<V>(s0, s1, kshift, nrows_t);
+    // cross-lane reduction through the (now idle) ring: 256 x 8 doubles = 16 KB
+    __syncthreads();
+    block_sums_to_global<V>(s0, s1, reinterpret_cast<double*>(bns_smem), C, cg, q, lane, lanes, c, sums);
 }
 
 // scale/shift (+ mean, invstd, unbiased variance) of one channel from its batch sums: the single definition used by the
@@ -152,8 +318,8 @@ __global__ void __launch_bounds__(256, 2) bn_reduce_kernel(const T* __restrict__
 __device__ __forceinline__ void bn_channel_coeffs(const double* __restrict__ sums, long long M, int C, int c,
                                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                   float& sc, float& sh, float& meanf, float& is, float& unb) {
-    double m = sums[c] / (double)M;
-    double var = sums[C + c] / (double)M - m * m;
+    double m = bn_load_sums(sums, C, c) / (double)M;
+    double var = bn_load_sums(sums, C, C + c) / (double)M - m * m;
     if (var < 0) var = 0;
     meanf = (float)m;
     float varf = (float)var;
@@ -301,13 +467,19 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                             const double* __restrict__ sums,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
     pdl_entry();
-    if (blockIdx.x == 0) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            if (dbeta) dbeta[c] += (float)sums[c];
-            if (dgamma) dgamma[c] += (float)sums[C + c];
+    // collapse the replicated sums once per block (C x 2 x R loads) instead of once per thread
+    __shared__ float s_mg[1024], s_mgx[1024];
+    const float invM = 1.0f / (float)M;
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+        const double sg = bn_load_sums(sums, C, cc), sgx = bn_load_sums(sums, C, C + cc);
+        s_mg[cc] = (float)sg * invM;
+        s_mgx[cc] = (float)sgx * invM;
+        if (blockIdx.x == 0) {
+            if (dbeta) dbeta[cc] += (float)sg;
+            if (dgamma) dgamma[cc] += (float)sgx;
         }
     }
-    const float invM = 1.0f / (float)M;
+    __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c = (int)(i % cg) * V;
@@ -315,8 +487,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         sc[j] = scale[c + j]; sh[j] = shift[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j];
-        mg[j] = (float)sums[c + j] * invM;
-        mgx[j] = (float)sums[C + c + j] * invM;
+        mg[j] = s_mg[c + j];
+        mgx[j] = s_mgx[c + j];
         gi[j] = (gamma ? gamma[c + j] : 1.f) * is[j];
     }
     auto apply = [&](const float* xs, float* gs) {
@@ -373,6 +545,30 @@ static unsigned ew_grid(long long n) {
     return (unsigned)b;
 }
 
+// large tensors go through the bulk-copy streaming kernel (one or two blocks per SM); returns false if not applicable
+template <typename T, int V, bool BWD>
+static bool launch_reduce_stream(const void* x, const void* dy, long long M, int C, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, int relu, double* sums, cudaStream_t st) {
+    const long long bytes = M * C * (long long)sizeof(T);
+    const int row_bytes = C * (int)sizeof(T);
+    static const bool off = getenv("SVRS_BN_STREAM") && getenv("SVRS_BN_STREAM")[0] == '0';
+    if (off || bytes < (4ll << 20) || row_bytes > BNS_CHUNK || row_bytes % 16 != 0) return false;
+    const int smem = BNS_STAGES * BNS_CHUNK * (BWD ? 2 : 1);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(bn_reduce_stream_kernel<T, V, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    long long blocks = (long long)num_sms() * (BWD ? 1 : 2);
+    const int rows_per_chunk = BNS_CHUNK / row_bytes;
+    long long rpb = (M + blocks - 1) / blocks;
+    rpb = (rpb + rows_per_chunk - 1) / rows_per_chunk * rows_per_chunk;     // whole chunks per block
+    blocks = (M + rpb - 1) / rpb;
+    SVRS_LAUNCH((bn_reduce_stream_kernel<T, V, BWD>), (unsigned)blocks, 256, smem, st, (const T*)x, (const T*)dy, M, C, rpb,
+                scale, shift, mean, invstd, relu, sums);
+    return true;
+}
+
 }  // namespace svrs
 
 using namespace svrs;
@@ -383,6 +579,10 @@ extern "C" int svrs_bn_stats(const void* x, int dtype, int64_t M, int C, double*
     const bool w8 = wide(dtype, C);
     reduce_grid(M, C, w8 ? 8 : 4, blocks, rpb);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SVRS_F32 ? launch_reduce_stream<float, 4, false>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, sums, st)
+        : (w8 ? launch_reduce_stream<__nv_bfloat16, 8, false>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, sums, st)
+              : launch_reduce_stream<__nv_bfloat16, 4, false>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, sums, st)))
+        return check_launch("bn_stats");
     if (dtype == SVRS_F32)
         SVRS_LAUNCH((bn_reduce_kernel<float, 4, false>), blocks, 256, 0, st, (const float*)x, nullptr, M, C, rpb, nullptr, nullptr, nullptr, nullptr, 0, sums);
     else if (dtype == SVRS_BF16 && w8)
@@ -455,6 +655,10 @@ extern "C" int svrs_bn_bwd_reduce(const void* x, const void* dy, int dtype, int6
     const bool w8 = wide(dtype, C);
     reduce_grid(M, C, w8 ? 8 : 4, blocks, rpb);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SVRS_F32 ? launch_reduce_stream<float, 4, true>(x, dy, M, C, scale, shift, mean, invstd, relu, sums, st)
+        : (w8 ? launch_reduce_stream<__nv_bfloat16, 8, true>(x, dy, M, C, scale, shift, mean, invstd, relu, sums, st)
+              : launch_reduce_stream<__nv_bfloat16, 4, true>(x, dy, M, C, scale, shift, mean, invstd, relu, sums, st)))
+        return check_launch("bn_bwd_reduce");
     if (dtype == SVRS_F32)
         SVRS_LAUNCH((bn_reduce_kernel<float, 4, true>), blocks, 256, 0, st, (const float*)x, (const float*)dy, M, C, rpb, scale, shift, mean, invstd, relu, sums);
     else if (dtype == SVRS_BF16 && w8)

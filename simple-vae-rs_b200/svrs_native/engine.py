@@ -34,6 +34,9 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+BN_REPLICAS = 8      # SVRS_BN_REPLICAS of include/svrs_b200.h (checked against the header in tests/test_cpu_abi_and_geometry.py)
+
+
 def _st() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -263,13 +266,13 @@ class Runtime:
             for net in self.nets:
                 for op in net.ops:
                     if isinstance(op, BNOp):
-                        n += 4 * op.mod.num_features
+                        n += 4 * op.mod.num_features * BN_REPLICAS
             self._scratch = torch.zeros(max(n, 1), device=dev, dtype=torch.float64)
             off = 0
             for net in self.nets:
                 for op in net.ops:
                     if isinstance(op, BNOp):
-                        c = op.mod.num_features
+                        c = op.mod.num_features * BN_REPLICAS     # SVRS_BN_REPLICAS copies of double[2C] each
                         op.sums_f = self._scratch[off:off + 2 * c]
                         op.sums_b = self._scratch[off + 2 * c:off + 4 * c]
                         off += 4 * c
@@ -460,7 +463,7 @@ class Runtime:
                     mean = torch.empty(cch, device=dev, dtype=torch.float32)
                     invstd = torch.empty(cch, device=dev, dtype=torch.float32)
                     if not self.scratch_prezeroed:
-                        lib.fill_zero(_p(op.sums_f), 16 * cch, st)
+                        lib.fill_zero(_p(op.sums_f), 16 * cch * BN_REPLICAS, st)
                     lib.bn_stats(_p(x), self.dt, m, cch, _p(op.sums_f), st)
                     mom = 0.1 if bn.momentum is None else bn.momentum
                     track = bn.track_running_stats and bn.running_mean is not None
@@ -532,7 +535,7 @@ class Runtime:
                 m = n * h * w
                 bn = op.mod
                 if not self.scratch_prezeroed:
-                    lib.fill_zero(_p(op.sums_b), 16 * cch, st)
+                    lib.fill_zero(_p(op.sums_b), 16 * cch * BN_REPLICAS, st)
                 lib.bn_bwd_reduce(_p(x), _p(dy), self.dt, m, cch, _p(scale), _p(shift), _p(mean), _p(invstd),
                                   int(op.relu), _p(op.sums_b), st)
                 lib.bn_bwd_apply(_p(x), _p(dy), _p(dy), self.dt, m, cch, _p(scale), _p(shift), _p(mean), _p(invstd),

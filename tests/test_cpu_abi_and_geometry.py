@@ -22,6 +22,14 @@ def test_header_symbols_exported():
     assert lib.abi_version() == 1
 
 
+def test_header_constants_match_host_code():
+    """Constants the Python host mirrors from the header stay in sync with it."""
+    import re
+    from svrs_native import engine
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "svrs_b200.h")).read()
+    assert int(re.search(r"#define\s+SVRS_BN_REPLICAS\s+(\d+)", hdr).group(1)) == engine.BN_REPLICAS
+
+
 def test_header_cites_reference_call_sites():
     src = open(libmod.HEADER).read()
     for cite in ("layers.py:231-236", "layers.py:275-277", "cond_vae.py:261-265", "loss/cond_vae_loss.py:39-58",

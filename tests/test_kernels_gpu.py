@@ -144,7 +144,8 @@ def test_conv_epilogue_activation_and_backward(act, fn):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("shape", [(4, 16, 8, 8), (2, 64, 16, 16), (3, 256, 4, 4), (1, 128, 2, 2)])
+@pytest.mark.parametrize("shape", [(4, 16, 8, 8), (2, 64, 16, 16), (3, 256, 4, 4), (1, 128, 2, 2),
+                                   (9, 64, 64, 61), (70, 256, 16, 15), (40, 1024, 8, 8)])   # >= 4 MB: bulk-copy streaming reduce, ragged tails
 def test_batchnorm_train_fwd_bwd(shape, dtype):
     N, C, H, W = shape
     g = torch.Generator().manual_seed(C)
@@ -161,7 +162,7 @@ def test_batchnorm_train_fwd_bwd(shape, dtype):
     yr.backward(gy.double())
     M = N * H * W
     xd, gyd = nhwc(x.to(DEV), dtype), nhwc(gy.to(DEV), dtype)
-    sums = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    sums = torch.zeros(2 * C * 8, device=DEV, dtype=torch.float64)   # SVRS_BN_REPLICAS copies
     rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
     nbt = torch.zeros((), device=DEV, dtype=torch.int64)
     scale, shift, mean, invstd = (torch.empty(C, device=DEV) for _ in range(4))
@@ -175,7 +176,7 @@ def test_batchnorm_train_fwd_bwd(shape, dtype):
     report("bn running_mean", rm, bn.running_mean, 1e-6)
     report("bn running_var", rv, bn.running_var, 1e-5)
     assert int(nbt) == 1
-    sums2 = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    sums2 = torch.zeros(2 * C * 8, device=DEV, dtype=torch.float64)
     dgam, dbet = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     lib.bn_bwd_reduce(xd.data_ptr(), gyd.data_ptr(), dt(dtype), M, C, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
                       invstd.data_ptr(), 1, sums2.data_ptr(), st())
@@ -223,7 +224,7 @@ def test_bn_apply_train_fused_equals_two_step(shape, dtype):
     M = N * H * W
     gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
     beta = torch.randn(C, generator=g).to(DEV)
-    sums = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    sums = torch.zeros(2 * C * 8, device=DEV, dtype=torch.float64)   # SVRS_BN_REPLICAS copies
     lib.bn_stats(x.data_ptr(), dt(dtype), M, C, sums.data_ptr(), st())
     outs = []
     for fused in (0, 1):
