@@ -210,8 +210,9 @@ class Runtime:
         self._scratch: Optional[torch.Tensor] = None
         self._pack_jobs: Optional[torch.Tensor] = None
         self._pack_key = None
-        self._unpack_jobs: Optional[torch.Tensor] = None
-        self._unpack_key = None
+        self._unpack_cache: Dict = {}
+        self._unpacked_early: set = set()
+        self.after_phase1 = None   # optional hook(list of Nets whose backward is complete), see CondEngine.backward
         self.scratch_prezeroed = False   # the fused step zeroes all BatchNorm scratch once per step
         self.packs_dirty = True
         self._replayed = 0         # kernels re-issued by CUDA-graph replays (not seen by the library's own counter)
@@ -347,13 +348,12 @@ class Runtime:
             self._side_busy = False
         self._wg_keep.clear()
 
-    def finish_grads(self):
-        """Add the per-tap packed weight-gradient scratch of every conv layer into the torch-layout flat gradient
-        (one launch).  Must run after the last net_backward of a step and before anything reads store.grad."""
-        self.join_wgrads()
-        if self._unpack_jobs is None or self._unpack_key != (self.store.grad.data_ptr(), self.store.gpack.data_ptr()):
+    def _unpack_table(self, convs):
+        """Device job table (cached) for svrs_unpack_grads_multi over the given conv ops."""
+        key = (self.store.grad.data_ptr(), self.store.gpack.data_ptr(), tuple(id(op) for op in convs))
+        hit = self._unpack_cache.get(key)
+        if hit is None:
             import numpy as np
-            convs = [op for net in self.nets for op in net.ops if isinstance(op, ConvOp)]
             rec = np.dtype([("w", "<u8"), ("p01", "<u8"), ("p10", "<u8"), ("d0", "<i4"), ("d1", "<i4"), ("kk", "<i4"),
                             ("tile0", "<i4"), ("tiles_b", "<i4"), ("pad", "<i4")])
             jobs = np.zeros(len(convs), dtype=rec)
@@ -364,10 +364,32 @@ class Runtime:
                 tiles_b = (d1 + 15) // 16
                 jobs[i] = (self.store.grad_ptr(w), self.store.gpack_ptr(w), 0, d0, d1, op.kk, tile0, tiles_b, 0)
                 tile0 += ((d0 + 31) // 32) * tiles_b
-            self._unpack_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).to(self.device)
-            self._unpack_tiles, self._unpack_n = tile0, len(convs)
-            self._unpack_key = (self.store.grad.data_ptr(), self.store.gpack.data_ptr())
-        lib.unpack_grads_multi(_p(self._unpack_jobs), self._unpack_n, self._unpack_tiles, 16, _st())
+            hit = (torch.from_numpy(jobs.view(np.uint8).copy()).to(self.device), tile0, len(convs))
+            self._unpack_cache[key] = hit
+        return hit
+
+    def unpack_nets(self, nets):
+        """Add the packed weight-gradient scratch of the given nets' conv layers into the flat gradient NOW (current
+        stream) and remember them, so that finish_grads() only handles the rest.  Used by the data-parallel trainer to
+        start the all-reduce of the decoders' gradients while the encoders' backward pass is still running."""
+        convs = [op for net in nets for op in net.ops if isinstance(op, ConvOp)]
+        if not convs:
+            return
+        jobs, tiles, n = self._unpack_table(convs)
+        lib.unpack_grads_multi(_p(jobs), n, tiles, 16, _st())
+        self.launches += 1
+        self._unpacked_early = {id(op) for op in convs}
+
+    def finish_grads(self):
+        """Add the per-tap packed weight-gradient scratch of every conv layer into the torch-layout flat gradient
+        (one launch).  Must run after the last net_backward of a step and before anything reads store.grad."""
+        self.join_wgrads()
+        convs = [op for net in self.nets for op in net.ops if isinstance(op, ConvOp) and id(op) not in self._unpacked_early]
+        self._unpacked_early = set()
+        if not convs:
+            return
+        jobs, tiles, n = self._unpack_table(convs)
+        lib.unpack_grads_multi(_p(jobs), n, tiles, 16, _st())
         self.launches += 1
 
     def pack_weights(self, force: bool = False):
@@ -737,6 +759,9 @@ class CondEngine:
             d_stack = torch.empty((B, 2 * Wz), **f32)
             rt.to_nchw(ds8, d_stack, 2 * Wz)
         rt.join(0, 1)
+        if rt.after_phase1 is not None:
+            # decoders, prior heads and u_to_z are done (their wgrads are queued on the wgrad stream)
+            rt.after_phase1([N[k] for k in ("decoder_x", "decoder_y", "mu_u_y_to_z", "logvar_u_y_to_z", "u_to_z")])
         if du16 is not None:
             if d_u is None:
                 d_u = zeros(B, Wu)

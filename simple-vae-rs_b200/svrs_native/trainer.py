@@ -78,6 +78,8 @@ class _FusedBase:
             rt.packs_dirty = True
             if self.world > 1:
                 self._comm_stream = torch.cuda.Stream(device=dev)
+                import os
+                self._ar_overlap = os.environ.get("SVRS_AR_OVERLAP", "1") != "0"
 
     def _gamma_attrs(self):
         raise NotImplementedError
@@ -110,10 +112,58 @@ class _FusedBase:
         rt.packs_dirty = True
         rt.pack_weights()
 
+    # ---- data-parallel gradient exchange ---------------------------------------------------------------
+    # The flat fp32 gradient is SUM-all-reduced (NCCL).  With SVRS_AR_OVERLAP != 0 the part that belongs to the nets whose
+    # backward finishes first (decoders, prior heads, u_to_z: CondEngine.backward phase 1) is unpacked and reduced on a
+    # communication stream while the encoders' backward pass is still running; the rest follows after the backward pass.
+    def _net_segments(self, nets):
+        """Merged [lo, hi) element ranges of the flat buffers covered by the parameters of `nets`."""
+        store = self.rt.store
+        A = store.ALIGN
+        spans = []
+        for net in nets:
+            for op in net.ops:
+                for p in op.mod.parameters(recurse=False):
+                    i = store._index[id(p)]
+                    lo = store.offsets[i]
+                    spans.append((lo, lo + (p.numel() + A - 1) // A * A))
+        spans.sort()
+        merged = []
+        for lo, hi in spans:
+            if merged and lo <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], hi)
+            else:
+                merged.append([lo, hi])
+        return [(lo, min(hi, store.total)) for lo, hi in merged]
+
+    def _early_allreduce(self, nets):
+        rt = self.rt
+        comm = self._comm_stream
+        comm.wait_stream(torch.cuda.current_stream())
+        if rt._side_busy:
+            comm.wait_stream(rt._side)                 # the wgrads queued so far are exactly those of `nets`
+        segs = self._net_segments(nets)
+        with torch.cuda.stream(comm):
+            rt.unpack_nets(nets)
+            for lo, hi in segs:
+                torch.distributed.all_reduce(rt.store.grad[lo:hi], group=self.pg)
+        self._early_segs = segs
+
     def _allreduce_all(self):
         if self.world == 1:
             return
-        torch.distributed.all_reduce(self.rt.store.grad, group=self.pg)
+        store = self.rt.store
+        early = getattr(self, "_early_segs", None)
+        self._early_segs = None
+        if not early:
+            torch.distributed.all_reduce(store.grad, group=self.pg)
+        else:
+            lo0 = 0
+            for lo, hi in early + [(store.total, store.total)]:
+                if lo > lo0:
+                    torch.distributed.all_reduce(store.grad[lo0:lo], group=self.pg)
+                lo0 = hi
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
         torch.distributed.all_reduce(self.dgam, group=self.pg)
 
     # ---- public ------------------------------------------------------------------------------------
@@ -198,10 +248,14 @@ class FusedCondTrainer(_FusedBase):
                      B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), st)
         rt.launches += 3
         rt.scratch_prezeroed = True
+        self._early_segs = None
+        if self.world > 1 and getattr(self, "_ar_overlap", False):
+            rt.after_phase1 = self._early_allreduce      # only while the fused step's backward runs
         try:
             eng.backward(ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3)
         finally:
             rt.scratch_prezeroed = False
+            rt.after_phase1 = None
         self._allreduce_all()
         self._optim_tail()
         return terms

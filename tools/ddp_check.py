@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Data-parallel consistency check (run under torchrun, one rank per GPU): K fused CondVAE steps on seeded synthetic
+tiles, then rank 0 saves the flat parameter buffer.  Run once with SVRS_AR_OVERLAP=0 and once with =1 and compare the two
+files (tools/ddp_check.py --compare a.pt b.pt): overlapping the gradient all-reduce with the backward pass must not
+change the result beyond fp32 atomic-order noise, and all ranks must hold identical parameters."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "simple-vae-rs_b200"))
+import torch
+
+if len(sys.argv) > 1 and sys.argv[1] == "--compare":
+    a, b = torch.load(sys.argv[2]), torch.load(sys.argv[3])
+    d = (a["flat"] - b["flat"]).abs().max().item()
+    scale = a["flat"].abs().max().item()
+    upd = (a["flat"] - a["init"]).abs().max().item()
+    print(f"max |delta| between runs = {d:.3e} (param scale {scale:.3e}, largest update {upd:.3e}); rank spread {a['spread']:.3e} / {b['spread']:.3e}")
+    ok = d <= 2e-3 * upd + 1e-7 and a["spread"] == 0.0 and b["spread"] == 0.0
+    print("DDP_CHECK", "OK" if ok else "FAIL")
+    sys.exit(0 if ok else 1)
+
+import torch.distributed as dist
+import models
+from dataset import synthetic_tiles, grid_patch_normalize
+from svrs_native.trainer import FusedCondTrainer
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+torch.manual_seed(0)
+model = models.Cond_SRVAE(2, 64).cuda()
+model.set_compute_dtype(torch.bfloat16)
+opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+tr = FusedCondTrainer(model, opt, compute_dtype=torch.bfloat16)      # picks the default process group up
+lr, hr = synthetic_tiles(2 * world, seed=3)
+lr, hr = lr[2 * rank:2 * rank + 2].cuda(), hr[2 * rank:2 * rank + 2].cuda()
+y, x = grid_patch_normalize(lr, 32), grid_patch_normalize(hr, 64)
+init = None
+for i in range(4):
+    out = tr.step(x, y)
+    if init is None:
+        init = tr.rt.store.flat.detach().clone()   # after step 1 (state exists)
+torch.cuda.synchronize()
+flat = tr.rt.store.flat.detach().clone()
+ref = flat.clone()
+dist.broadcast(ref, 0)
+spread = torch.tensor([(flat - ref).abs().max().item()], device="cuda")
+dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+if rank == 0:
+    torch.save({"flat": flat.cpu(), "init": init.cpu(), "spread": float(spread)}, sys.argv[1])
+    print("saved", sys.argv[1], "loss", float(out[4]), "spread", float(spread))
+dist.barrier()
+torch.cuda.synchronize()
+os._exit(0)
