@@ -10,11 +10,18 @@ import torch
 
 if len(sys.argv) > 1 and sys.argv[1] == "--compare":
     a, b = torch.load(sys.argv[2]), torch.load(sys.argv[3])
-    d = (a["flat"] - b["flat"]).abs().max().item()
-    scale = a["flat"].abs().max().item()
-    upd = (a["flat"] - a["init"]).abs().max().item()
-    print(f"max |delta| between runs = {d:.3e} (param scale {scale:.3e}, largest update {upd:.3e}); rank spread {a['spread']:.3e} / {b['spread']:.3e}")
-    ok = d <= 2e-3 * upd + 1e-7 and a["spread"] == 0.0 and b["spread"] == 0.0
+    # Compared: the all-reduced gradient of the FIRST step (identical weights in both runs).  Parameters after several
+    # Adam steps are not comparable between ANY two runs: early Adam updates are ~lr*sign(g), and elements whose gradient
+    # is rounding noise flip sign with the fp32 atomic order (measured: 2.7e-3 between two identical runs).
+    d, worst = 0.0, ""
+    gmax = a["grad"].abs().max().item()
+    for name, (lo, hi) in a["spans"].items():
+        dd = (a["grad"][lo:hi] - b["grad"][lo:hi]).abs().max().item()
+        if dd > d:
+            d, worst = dd, name
+    print(f"step-1 gradient: max |delta| = {d:.3e} at {worst} (max |g| {gmax:.3e}); loss {a['loss']:.4f} vs {b['loss']:.4f}; "
+          f"rank spread of the parameters after 4 steps {a['spread']:.3e} / {b['spread']:.3e}")
+    ok = d <= 1e-4 * gmax and abs(a["loss"] - b["loss"]) <= 1e-5 * abs(a["loss"]) and a["spread"] == 0.0 and b["spread"] == 0.0
     print("DDP_CHECK", "OK" if ok else "FAIL")
     sys.exit(0 if ok else 1)
 
@@ -34,11 +41,13 @@ tr = FusedCondTrainer(model, opt, compute_dtype=torch.bfloat16)      # picks the
 lr, hr = synthetic_tiles(2 * world, seed=3)
 lr, hr = lr[2 * rank:2 * rank + 2].cuda(), hr[2 * rank:2 * rank + 2].cuda()
 y, x = grid_patch_normalize(lr, 32), grid_patch_normalize(hr, 64)
-init = None
+grad1 = loss1 = None
 for i in range(4):
     out = tr.step(x, y)
-    if init is None:
-        init = tr.rt.store.flat.detach().clone()   # after step 1 (state exists)
+    if grad1 is None:
+        torch.cuda.synchronize()
+        grad1 = tr.rt.store.grad.detach().clone()  # all-reduced gradient of step 1
+        loss1 = float(out[4])
 torch.cuda.synchronize()
 flat = tr.rt.store.flat.detach().clone()
 ref = flat.clone()
@@ -46,7 +55,9 @@ dist.broadcast(ref, 0)
 spread = torch.tensor([(flat - ref).abs().max().item()], device="cuda")
 dist.all_reduce(spread, op=dist.ReduceOp.MAX)
 if rank == 0:
-    torch.save({"flat": flat.cpu(), "init": init.cpu(), "spread": float(spread)}, sys.argv[1])
+    store = tr.rt.store
+    spans = {n: (o, o + p.numel()) for n, o, p in zip(store.names, store.offsets, store.params)}
+    torch.save({"grad": grad1.cpu(), "loss": loss1, "spread": float(spread), "spans": spans}, sys.argv[1])
     print("saved", sys.argv[1], "loss", float(out[4]), "spread", float(spread))
 dist.barrier()
 torch.cuda.synchronize()
