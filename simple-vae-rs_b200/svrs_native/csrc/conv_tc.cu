@@ -279,6 +279,9 @@ int make_w_map_pub(CUtensorMap* m, const void* base, int K, int Nc, int taps, in
     return make_w_map(m, base, K, Nc, taps, n_tile, cw);
 }
 bool halo_supported(int form, int Cr, int Cw, int OW, int OH);
+bool convT_halo_supported(int Cr, int Cw, int W, int H);
+int launch_convT_halo(const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw, int act,
+                      cudaStream_t st);
 int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
                       int act, cudaStream_t st);
 
@@ -303,6 +306,7 @@ bool tc_supported(int dtype, int K, int Nc, int OW, int OH) {
 int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
                    int act, cudaStream_t st) {
     if (halo_supported(form, Cr, Cw, W, H)) return launch_conv3_halo(form, in, w_nk, bias, out, N, H, W, Cr, Cw, act, st);
+    if (form == 3 && convT_halo_supported(Cr, Cw, W, H)) return launch_convT_halo(in, w_nk, bias, out, N, H, W, Cr, Cw, act, st);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
