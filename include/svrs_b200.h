@@ -67,7 +67,7 @@ int svrs_pack_weights(const float* w, int d0, int d1, int kk, void* p01, void* p
 /* All layers in one launch: `jobs` is a DEVICE array of njobs records
  *   { const float* w; void* p01; void* p10; int d0, d1, kk; int tile0; int tiles_b; int pad; }   (svrs_pack_job_bytes() each)
  * where a layer is cut into 32 x 16 tiles of its (d0, d1) plane, tiles_b = ceil(d1/16), and tile0 is the running sum of
- * the tile counts of the preceding jobs; total_tiles = sum of all tile counts; max_kk = largest kk (<= 16). */
+ * the tile counts of the preceding jobs; total_tiles = sum of all tile counts; max_kk = largest kk (<= 16); njobs <= 128. */
 int svrs_pack_job_bytes(void);
 int svrs_pack_weights_multi(const void* jobs, int njobs, int total_tiles, int max_kk, int dtype, void* stream);
 /* inverse direction for gradients: same job records with w = torch-layout fp32 gradient (+=) and p01 = the packed

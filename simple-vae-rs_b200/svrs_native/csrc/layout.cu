@@ -275,13 +275,32 @@ struct PackJob {
 };
 constexpr int PK_TA = 32, PK_TB = 16;
 
+// job of a tile: binary search over the jobs' first-tile indices (staged in shared memory by one coalesced load; the
+// former linear scan cost every CTA up to njobs dependent global loads - more than its whole 5k-element tile)
+__device__ __forceinline__ int find_job(const PackJob* __restrict__ jobs, int njobs, int tile, int* s_tile0) {
+    for (int i = threadIdx.x; i < njobs; i += blockDim.x) s_tile0[i] = jobs[i].tile0;
+    __syncthreads();
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_tile0[mid] <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+// i -> (b = i / kk, t = i % kk) for the two kernel sizes on the path without a runtime division
+__device__ __forceinline__ void split_kk(int i, int kk, int& b, int& t) {
+    if (kk == 16) { b = i >> 4; t = i & 15; }
+    else if (kk == 9) { b = i / 9; t = i - 9 * b; }
+    else { b = i / kk; t = i - kk * b; }
+}
+constexpr int PK_MAX_JOBS = 128;
+
 template <typename TD>
 __global__ void __launch_bounds__(256) pack_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
     pdl_entry();
     extern __shared__ float tile[];
-    int j = 0;
-    while (j + 1 < njobs && jobs[j + 1].tile0 <= (int)blockIdx.x) ++j;
-    const PackJob jb = jobs[j];
+    __shared__ int s_tile0[PK_MAX_JOBS];
+    const PackJob jb = jobs[find_job(jobs, njobs, blockIdx.x, s_tile0)];
     const int lt = blockIdx.x - jb.tile0;
     const int a0 = (lt / jb.tiles_b) * PK_TA, b0 = (lt % jb.tiles_b) * PK_TB;
     const int kk = jb.kk, d0 = jb.d0, d1 = jb.d1;
@@ -289,37 +308,40 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackJob* __restri
     const int ROW = PK_TB * (kk + 1) + 1;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int run = nb * kk;
-    for (int a = warp; a < na; a += 8) {
+    for (int a = warp; a < na; a += 8) {                           // read torch layout: contiguous runs of nb*kk floats
         const float* src = jb.w + ((long long)(a0 + a) * d1 + b0) * kk;
-        for (int i = lane; i < run; i += 32) tile[a * ROW + (i / kk) * (kk + 1) + (i % kk)] = src[i];
+        for (int i = lane; i < run; i += 32) {
+            int b, t;
+            split_kk(i, kk, b, t);
+            tile[a * ROW + b * (kk + 1) + t] = src[i];
+        }
     }
     __syncthreads();
     TD* p01 = reinterpret_cast<TD*>(jb.p01);
     TD* p10 = reinterpret_cast<TD*>(jb.p10);
-    const int total = kk * na * nb;
-    if (p01) {
-        for (int idx = threadIdx.x; idx < total; idx += 256) {
-            int b = idx % nb, a = (idx / nb) % na, t = idx / (nb * na);
-            p01[((long long)t * d0 + a0 + a) * d1 + b0 + b] = Cvt<TD>::from_f(tile[a * ROW + b * (kk + 1) + t]);
-        }
+    if (p01) {                                                     // [t][a][b]: half-warps write 16 consecutive b
+        const int tx = threadIdx.x % PK_TB, ty = threadIdx.x / PK_TB;
+        if (tx < nb)
+            for (int t = 0; t < kk; ++t)
+                for (int a = ty; a < na; a += 256 / PK_TB)
+                    p01[((long long)t * d0 + a0 + a) * d1 + b0 + tx] = Cvt<TD>::from_f(tile[a * ROW + tx * (kk + 1) + t]);
     }
-    if (p10) {
-        for (int idx = threadIdx.x; idx < total; idx += 256) {
-            int a = idx % na, b = (idx / na) % nb, t = idx / (nb * na);
-            p10[((long long)t * d1 + b0 + b) * d0 + a0 + a] = Cvt<TD>::from_f(tile[a * ROW + b * (kk + 1) + t]);
-        }
+    if (p10) {                                                     // [t][b][a]: warps write 32 consecutive a
+        if (lane < na)
+            for (int t = 0; t < kk; ++t)
+                for (int b = warp; b < nb; b += 8)
+                    p10[((long long)t * d1 + b0 + b) * d0 + a0 + lane] = Cvt<TD>::from_f(tile[lane * ROW + b * (kk + 1) + t]);
     }
 }
 }  // namespace svrs
 
 namespace svrs {
-// gradients: packed fp32 scratch [tap][d0][d1] -> torch layout [d0][d1][tap] (+=), same tiling as pack_multi_kernel
+// gradients: packed fp32 scratch [tap][d1][d0] -> torch layout [d0][d1][tap] (+=), same tiling as pack_multi_kernel
 __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
     pdl_entry();
     extern __shared__ float tile[];
-    int j = 0;
-    while (j + 1 < njobs && jobs[j + 1].tile0 <= (int)blockIdx.x) ++j;
-    const PackJob jb = jobs[j];
+    __shared__ int s_tile0[PK_MAX_JOBS];
+    const PackJob jb = jobs[find_job(jobs, njobs, blockIdx.x, s_tile0)];
     const int lt = blockIdx.x - jb.tile0;
     const int a0 = (lt / jb.tiles_b) * PK_TA, b0 = (lt % jb.tiles_b) * PK_TB;
     const int kk = jb.kk, d0 = jb.d0, d1 = jb.d1;
@@ -327,23 +349,26 @@ __global__ void __launch_bounds__(256) unpack_multi_kernel(const PackJob* __rest
     const int ROW = PK_TB * (kk + 1) + 1;
     const float* src = reinterpret_cast<const float*>(jb.p01);
     float* dst = const_cast<float*>(jb.w);
-    const int total = kk * na * nb;
-    for (int idx = threadIdx.x; idx < total; idx += 256) {       // read packed [kk][d1][d0]: a fastest (runs of na)
-        int a = idx % na, b = (idx / na) % nb, t = idx / (nb * na);
-        tile[a * ROW + b * (kk + 1) + t] = src[((long long)t * d1 + b0 + b) * d0 + a0 + a];
-    }
-    __syncthreads();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (lane < na)                                                 // read packed [kk][d1][d0]: warps read 32 consecutive a
+        for (int t = 0; t < kk; ++t)
+            for (int b = warp; b < nb; b += 8)
+                tile[lane * ROW + b * (kk + 1) + t] = src[((long long)t * d1 + b0 + b) * d0 + a0 + lane];
+    __syncthreads();
     const int run = nb * kk;
     for (int a = warp; a < na; a += 8) {                          // write torch layout: contiguous runs of nb*kk
         float* d = dst + ((long long)(a0 + a) * d1 + b0) * kk;
-        for (int i = lane; i < run; i += 32) d[i] += tile[a * ROW + (i / kk) * (kk + 1) + (i % kk)];
+        for (int i = lane; i < run; i += 32) {
+            int b, t;
+            split_kk(i, kk, b, t);
+            d[i] += tile[a * ROW + b * (kk + 1) + t];
+        }
     }
 }
 }  // namespace svrs
 
 extern "C" int svrs_unpack_grads_multi(const void* jobs, int njobs, int total_tiles, int max_kk, void* stream) {
-    SVRS_CHECK_ARG(jobs && njobs > 0 && total_tiles > 0 && max_kk > 0 && max_kk <= 16, "unpack_grads_multi: bad args");
+    SVRS_CHECK_ARG(jobs && njobs > 0 && njobs <= svrs::PK_MAX_JOBS && total_tiles > 0 && max_kk > 0 && max_kk <= 16, "unpack_grads_multi: bad args (at most 128 jobs)");
     size_t smem = (size_t)svrs::PK_TA * (svrs::PK_TB * (max_kk + 1) + 1) * sizeof(float);
     SVRS_LAUNCH((svrs::unpack_multi_kernel), total_tiles, 256, smem, (cudaStream_t)stream, (const svrs::PackJob*)jobs, njobs);
     return check_launch("unpack_grads_multi");
@@ -352,7 +377,7 @@ extern "C" int svrs_unpack_grads_multi(const void* jobs, int njobs, int total_ti
 extern "C" int svrs_pack_job_bytes(void) { return (int)sizeof(svrs::PackJob); }
 
 extern "C" int svrs_pack_weights_multi(const void* jobs, int njobs, int total_tiles, int max_kk, int dtype, void* stream) {
-    SVRS_CHECK_ARG(jobs && njobs > 0 && total_tiles > 0 && max_kk > 0 && max_kk <= 16, "pack_weights_multi: bad args");
+    SVRS_CHECK_ARG(jobs && njobs > 0 && njobs <= svrs::PK_MAX_JOBS && total_tiles > 0 && max_kk > 0 && max_kk <= 16, "pack_weights_multi: bad args (at most 128 jobs)");
     size_t smem = (size_t)svrs::PK_TA * (svrs::PK_TB * (max_kk + 1) + 1) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32) SVRS_LAUNCH((svrs::pack_multi_kernel<float>), total_tiles, 256, smem, st, (const svrs::PackJob*)jobs, njobs);
