@@ -220,7 +220,7 @@ class Runtime:
         # dgrad -> BatchNorm chain of the main stream (most of them are small, latency-bound launches that leave SMs
         # idle).  SVRS_WGRAD_STREAM=0 keeps everything on one stream.
         self.wgrad_side = os.environ.get("SVRS_WGRAD_STREAM", "1") != "0"
-        self._side: Optional[torch.cuda.Stream] = None
+        self._sides: Dict[int, torch.cuda.Stream] = {}    # producer stream handle -> its wgrad stream
         self._side_busy = False
         self._wg_keep: list = []   # operands of in-flight side-stream wgrads (kept alive until the join)
         # Independent sub-networks (encoder_y | encoder_x | y_to_z, decoder_y | prior heads | decoder_x, and their
@@ -331,20 +331,29 @@ class Runtime:
 
     def _wgrad_stream(self, *operands) -> int:
         """Stream handle for a weight-gradient launch whose operands were produced by work already enqueued on the
-        current stream.  The operands are kept alive until join_wgrads(): the caching allocator must not hand their
-        memory to a later main-stream allocation while the side stream still reads them."""
+        current stream.  Every producer stream (main, branch 0, branch 1) has its OWN wgrad stream, so the weight
+        gradients of nets that run in parallel do not serialise behind each other.  The operands are kept alive until
+        join_wgrads(): the caching allocator must not hand their memory to a later allocation while a side stream still
+        reads them."""
         if not self.wgrad_side:
             return _st()
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        self._side.wait_stream(torch.cuda.current_stream())
+        cur = torch.cuda.current_stream()
+        side = self._sides.get(cur.cuda_stream)
+        if side is None:
+            side = self._sides[cur.cuda_stream] = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
         self._side_busy = True
         self._wg_keep.append(operands)
-        return self._side.cuda_stream
+        return side.cuda_stream
+
+    def wgrad_streams(self):
+        return list(self._sides.values())
 
     def join_wgrads(self):
         if self._side_busy:
-            torch.cuda.current_stream().wait_stream(self._side)
+            cur = torch.cuda.current_stream()
+            for side in self._sides.values():
+                cur.wait_stream(side)
             self._side_busy = False
         self._wg_keep.clear()
 

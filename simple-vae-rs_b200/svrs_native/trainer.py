@@ -141,7 +141,8 @@ class _FusedBase:
         comm = self._comm_stream
         comm.wait_stream(torch.cuda.current_stream())
         if rt._side_busy:
-            comm.wait_stream(rt._side)                 # the wgrads queued so far are exactly those of `nets`
+            for side in rt.wgrad_streams():            # the wgrads queued so far are exactly those of `nets`
+                comm.wait_stream(side)
         segs = self._net_segments(nets)
         with torch.cuda.stream(comm):
             rt.unpack_nets(nets)
