@@ -221,6 +221,7 @@ class Runtime:
         # idle).  SVRS_WGRAD_STREAM=0 keeps everything on one stream.
         self.wgrad_side = os.environ.get("SVRS_WGRAD_STREAM", "1") != "0"
         self._sides: Dict[int, torch.cuda.Stream] = {}    # producer stream handle -> its wgrad stream
+        self._busy_sides: List[torch.cuda.Stream] = []
         self._side_busy = False
         self._wg_keep: list = []   # operands of in-flight side-stream wgrads (kept alive until the join)
         # Independent sub-networks (encoder_y | encoder_x | y_to_z, decoder_y | prior heads | decoder_x, and their
@@ -343,18 +344,23 @@ class Runtime:
             side = self._sides[cur.cuda_stream] = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)
         self._side_busy = True
+        if side not in self._busy_sides:
+            self._busy_sides.append(side)
         self._wg_keep.append(operands)
         return side.cuda_stream
 
     def wgrad_streams(self):
-        return list(self._sides.values())
+        """wgrad streams with work of the current step (only these may be waited on: under CUDA-graph capture the
+        streams used by earlier eager steps are not part of the capture)."""
+        return list(self._busy_sides)
 
     def join_wgrads(self):
         if self._side_busy:
             cur = torch.cuda.current_stream()
-            for side in self._sides.values():
+            for side in self._busy_sides:
                 cur.wait_stream(side)
             self._side_busy = False
+        self._busy_sides = []
         self._wg_keep.clear()
 
     def _unpack_table(self, convs):
