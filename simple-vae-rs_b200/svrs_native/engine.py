@@ -220,8 +220,10 @@ class Runtime:
         # dgrad -> BatchNorm chain of the main stream (most of them are small, latency-bound launches that leave SMs
         # idle).  SVRS_WGRAD_STREAM=0 keeps everything on one stream.
         self.wgrad_side = os.environ.get("SVRS_WGRAD_STREAM", "1") != "0"
-        self._sides: Dict[int, torch.cuda.Stream] = {}    # producer stream handle -> its wgrad stream
+        self._sides: Dict[tuple, torch.cuda.Stream] = {}    # producer stream handle -> its wgrad stream
         self._busy_sides: List[torch.cuda.Stream] = []
+        self.wgrad_ways = int(os.environ.get("SVRS_WGRAD_WAYS", "1"))    # measured: more than one stream per producer does not help
+        self._wg_rr = 0
         self._side_busy = False
         self._wg_keep: list = []   # operands of in-flight side-stream wgrads (kept alive until the join)
         # Independent sub-networks (encoder_y | encoder_x | y_to_z, decoder_y | prior heads | decoder_x, and their
@@ -339,9 +341,11 @@ class Runtime:
         if not self.wgrad_side:
             return _st()
         cur = torch.cuda.current_stream()
-        side = self._sides.get(cur.cuda_stream)
+        self._wg_rr = (self._wg_rr + 1) % self.wgrad_ways
+        key = (cur.cuda_stream, self._wg_rr)          # round-robin over `wgrad_ways` streams per producer
+        side = self._sides.get(key)
         if side is None:
-            side = self._sides[cur.cuda_stream] = torch.cuda.Stream(device=self.device)
+            side = self._sides[key] = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)
         self._side_busy = True
         if side not in self._busy_sides:
@@ -705,10 +709,12 @@ class CondEngine:
             rt.copy2d(yz, c16, joint, 2 * c16, rows, c16)
             lib.copy2d(_p(uz), rt.dt, c16, joint.data_ptr() + es * c16, rt.dt, 2 * c16, rows, c16, 0, _st())
             rt.launches += 1
+            with rt.branch(2):                           # the two prior heads only share their input
+                l3, ctx["t_lv"] = rt.net_forward(N["logvar_u_y_to_z"], joint, training, save)
+                rt.to_nchw(l3, lv3, Wz)
             m3, ctx["t_mu"] = rt.net_forward(N["mu_u_y_to_z"], joint, training, save)
-            l3, ctx["t_lv"] = rt.net_forward(N["logvar_u_y_to_z"], joint, training, save)
             rt.to_nchw(m3, mu3, Wz)
-            rt.to_nchw(l3, lv3, Wz)
+            rt.join(2)
         # decode_x(z, y): stack viewed (2L/64, P/8, P/8)
         s8 = rt.to_nhwc(stack, 2 * Wz, B, 2 * self.cz, h8, h8)
         xh, ctx["t_dx"] = rt.net_forward(N["decoder_x"], s8, training, save)
@@ -749,16 +755,20 @@ class CondEngine:
                 d_u = torch.empty((B, Wu), **f32)
                 rt.to_nchw(du8, d_u, Wu)
         with rt.branch(1):
-            d_joint = None
-            for key, tape, net in ((d_mu3, "t_mu", "mu_u_y_to_z"), (d_lv3, "t_lv", "logvar_u_y_to_z")):
-                if key is None:
-                    continue
-                g_h = rt.to_nhwc(key.contiguous(), Wz, B, c16, h16, h16)
-                dj = rt.net_backward(N[net], ctx[tape], g_h, True)
+            d_joint = dj_lv = None
+            with rt.branch(2):                           # the two prior heads run in parallel
+                if d_lv3 is not None:
+                    g_l = rt.to_nhwc(d_lv3.contiguous(), Wz, B, c16, h16, h16)
+                    dj_lv = rt.net_backward(N["logvar_u_y_to_z"], ctx["t_lv"], g_l, True)
+            if d_mu3 is not None:
+                g_h = rt.to_nhwc(d_mu3.contiguous(), Wz, B, c16, h16, h16)
+                d_joint = rt.net_backward(N["mu_u_y_to_z"], ctx["t_mu"], g_h, True)
+            rt.join(2)
+            if dj_lv is not None:
                 if d_joint is None:
-                    d_joint = dj
+                    d_joint = dj_lv
                 else:
-                    rt.copy2d(dj, 2 * c16, d_joint, 2 * c16, rows, 2 * c16, accumulate=True)
+                    rt.copy2d(dj_lv, 2 * c16, d_joint, 2 * c16, rows, 2 * c16, accumulate=True)
             # gradient wrt y_to_z output (NHWC) and u_to_z output
             if d_joint is not None:
                 es = d_joint.element_size()
