@@ -85,8 +85,9 @@ int svrs_unpack_grads_multi(const void* jobs, int njobs, int total_tiles, int ma
 void svrs_set_tc_enabled(int enabled);   /* default 1; 0 forces the SIMT kernels everywhere (A/B tests) */
 /* conv3_halo (csrc/conv_halo.cu): 3x3 stride-1 fprop/dgrad on maps tiling into 8x16 blocks load each tile's activation
  * halo ONCE and address the nine taps as shared-memory descriptors.  mode 0 = off (per-tap TMA kernel), 1 = on (default),
- * 2 = on WITH the descriptor base-offset field set to (start >> 7) & 7 (hardware experiment: gives wrong results on B200,
- * which shows the UMMA swizzle is a function of the absolute shared-memory address). */
+ * 2 = historical: in the first revision of the kernel (git e22cd04) it set the descriptor base-offset field to
+ * (start >> 7) & 7, which gave WRONG results on B200 - the measurement that showed the UMMA swizzle to be a function of the
+ * absolute shared-memory address.  The single-lane issue loop that replaced it has no such variant: 2 now behaves like 1. */
 void svrs_set_halo_mode(int mode);
 int svrs_tc_would_run(int dtype, int K, int Nc, int OH, int OW); /* 1 if conv_tc takes a GEMM of these dims */
 

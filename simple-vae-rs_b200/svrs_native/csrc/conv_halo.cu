@@ -9,7 +9,7 @@
 //     tap (dy, dx): descriptor start = halo + ((dy+1) * 16 + (dx+1)) * 128 B, 8-row groups 2048 B apart (one halo row)
 // The start address is 128-B but not 1024-B aligned.  MEASURED on B200: the UMMA applies the 128B-swizzle XOR to the
 // ABSOLUTE shared-memory address bits (same function TMA used when writing), so such a start needs NO descriptor
-// base-offset; filling the base-offset field with (start >> 7) & 7 produces wrong results (tests/test_kernels_gpu.py).
+// base-offset; filling the base-offset field with (start >> 7) & 7 produced wrong results (first revision of this kernel).
 // Weights are either RESIDENT in shared memory for the whole kernel (9 * Cin/64 * n_tile * 128 B <= 96 KB, e.g. the
 // 64->64 layers) or streamed through a 4-slot ring of (chunk, tap) slices.
 // Warp roles / TMEM double buffering / epilogue are those of conv_tc.cu.
