@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark: train patches/sec of the 64x64 SR CondVAE step on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cond_grid|vae]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload cond_grid|cond_grid1024|vae|cond256|sample]
 
-Workload at every N (weak scaling): BASELINE.json config 3 - CondVAE cr=2, P=64, grid mode: 8 synthetic 256x256
+Default workload at every N (weak scaling): BASELINE.json config 3 - CondVAE cr=2, P=64, grid mode: 8 synthetic 256x256
 multispectral tiles per GPU -> 128 patches per GPU (64 tiles / 1024 patches at N=8), bf16 compute, fp32 master
 weights, gradients SUM-all-reduced over NCCL.  One "step" = grid-patch gather + normalise, forward, ELBO, backward,
 clip, Adam (the reference's models/base.py:103-107 body preceded by its dataset.py grid mode).
+Other BASELINE configs are selectable with --workload (config 2 `vae`, config 3 on ONE GPU `cond_grid1024`, config 4
+`cond256` = P=256 cr=16, config 5 `sample` = 32 posterior samples per LR patch).
 
-Prints ONE JSON line (rank 0).  `value` = device-timed whole-job patches/s with tiles resident in HBM;
+Prints ONE JSON line (rank 0).  `value` = device-timed whole-job units/s with tiles resident in HBM;
 `e2e` = the same through the public API with HOST (pinned) tile buffers: H2D copy of every step's tiles and a D2H read
 of the loss inside the timed region.  `--impl reference` times the CPU restatement of the reference (oracle/) on the
-host cores on a bounded sample of the same workload.
+host cores on a bounded sample of the same workload (same per-step batch).  Outside the timed regions the default line
+also carries `roofline` (dominant kernel), `roofline_hbm` (the bandwidth-bound kernels at the bench batch),
+`cpu_baseline`, `gpu_reference` (the reference's torch ops under cuDNN on the same GPU) and, for N > 1, `ddp_check`.
 """
 from __future__ import annotations
 
@@ -31,12 +36,26 @@ for p in (ROOT, PKG):
 
 import torch  # noqa: E402
 
-TILES_PER_GPU = 8
-PATCH = 64
-CR = 2
-# algorithmic FLOPs per patch of one CondVAE(cr=2,P=64) optimisation step (SURVEY 8.4 row d / BASELINE.md section 4)
-FLOP_PER_PATCH_TRAIN = 8.13e9
-FLOP_PER_PATCH_VAE = 4.44e9
+# ---- workloads (BASELINE.json configs 2-5).  flop = algorithmic FLOPs per unit of one optimisation step / sample
+# (SURVEY 8.4 row d)
+WORKLOADS = {
+    "cond_grid": dict(model="cond", cr=2, P=64, tiles=8, S=256, flop=8.13e9, unit="patches/s",
+                      metric="train patches/sec (64x64 SR CondVAE, device-timed)",
+                      name="CondVAE cr=2 P=64 grid mode: 8 tiles (256x256x4) -> 128 patches per GPU"),
+    "cond_grid1024": dict(model="cond", cr=2, P=64, tiles=64, S=256, flop=8.13e9, unit="patches/s",
+                          metric="train patches/sec (64x64 SR CondVAE, device-timed)",
+                          name="CondVAE cr=2 P=64 grid mode: 64 tiles (256x256x4) -> 1024 patches per GPU (config 3 on one GPU)"),
+    "vae": dict(model="vae", cr=2, P=64, tiles=16, S=256, flop=4.44e9, unit="patches/s",
+                metric="train patches/sec (64x64 VAE, device-timed)",
+                name="VAE cr=2 P=64, 16 tiles -> 256 patches per GPU (config 2)"),
+    "cond256": dict(model="cond", cr=16, P=256, tiles=16, S=256, flop=222e9, unit="crops/s",
+                    metric="train crops/sec (256x256 SR CondVAE cr=16, device-timed)",
+                    name="CondVAE cr=16 P=256 full 256x256 crops, 16 crops per GPU (config 4: 128 crops at 8 GPUs)"),
+    "sample": dict(model="cond", cr=2, P=64, tiles=1, S=256, flop=1.752e9, unit="samples/s",
+                   metric="posterior samples/sec (CondVAE sample(), 32 per LR patch, device-timed)",
+                   name="CondVAE cr=2 P=64 inference: 1 LR tile -> 16 patches x 32 posterior samples per step (config 5)"),
+}
+SAMPLES_PER_PATCH = 32
 
 
 def peaks():
@@ -89,39 +108,179 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_arm(args, workload: str):
-    """The reference's CPU implementation of the step (oracle restatement: same ATen CPU kernels, fp32), all host threads."""
+# ------------------------------------------------------------------------------------------------------------------
+# reference arms (the oracle's restatement of the reference's call sequence; same ATen kernels as the reference)
+# ------------------------------------------------------------------------------------------------------------------
+def _oracle_problem(wl, batch, device="cpu"):
+    """Weights (reference constructor under torch.manual_seed(0)), inputs and a step closure factory for the oracle."""
     from oracle import ref_oracle as O
     import models
-    torch.set_num_threads(os.cpu_count())
-    B = 8                                    # bounded sample: one config-1 sized batch per step (SURVEY 8.4 row d)
+    cr, P = wl["cr"], wl["P"]
     torch.manual_seed(0)
-    if workload == "vae":
-        m = models.VAE(CR, PATCH)
-    else:
-        m = models.Cond_SRVAE(CR, PATCH)
-    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = models.VAE(cr, P) if wl["model"] == "vae" else models.Cond_SRVAE(cr, P)
+    sd = {k: v.detach().clone().to(device) for k, v in m.state_dict().items()}
     g = torch.Generator().manual_seed(1)
-    x = torch.rand(B, 4, PATCH, PATCH, generator=g)
-    y = torch.rand(B, 4, PATCH // 2, PATCH // 2, generator=g)
+    x = torch.rand(batch, 4, P, P, generator=g).to(device)
+    y = torch.rand(batch, 4, P // 2, P // 2, generator=g).to(device)
+    if wl["model"] == "vae":
+        Wd = (m.latent_size // 64) * (P // 4) ** 2
+        widths = (Wd,)
+    else:
+        widths = ((m.latent_size_y // 64) * (P // 8) ** 2, (m.latent_size // 64) * (P // 8) ** 2)
+    return O, sd, x, y, widths
+
+
+def cpu_reference_arm(args, wl, batch, steps, warmup):
+    """The reference's CPU implementation of the step (oracle restatement, fp32), all host threads, on `batch` patches
+    per step - the SAME per-step batch as one GPU of the b200 arm."""
+    torch.set_num_threads(os.cpu_count())
+    O, sd, x, y, widths = _oracle_problem(wl, batch)
     opt = O.AdamState()
-    if workload == "vae":
+    cr, P = wl["cr"], wl["P"]
+    if wl["model"] == "vae":
         gam = {"gamma": torch.tensor(1.0)}
-        Wd = (m.latent_size // 64) * (PATCH // 4) ** 2
-        fn = lambda: O.vae_train_step(sd, gam, opt, CR, PATCH, x, torch.randn(B, Wd))
+        fn = lambda: O.vae_train_step(sd, gam, opt, cr, P, x, torch.randn(batch, widths[0]))
+    elif args.workload == "sample":
+        S = SAMPLES_PER_PATCH
+        fn = lambda: [O.cond_sample(sd, cr, P, y[i:i + 1], torch.randn(1, widths[0]), torch.randn(S, widths[1]))
+                      for i in range(batch)]
     else:
         gam = {"gammax": torch.tensor(1.0), "gammay": torch.tensor(1.0)}
-        L, Lu = O.cond_latent_sizes(CR, PATCH)
-        fn = lambda: O.cond_train_step(sd, gam, opt, CR, PATCH, x, y, torch.randn(B, Lu), torch.randn(B, L))
-    for _ in range(max(1, min(args.warmup, 2))):
-        fn()
-    steps = max(1, min(args.steps, 20))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        fn()
-    dt = (time.perf_counter() - t0) / steps
-    return dict(value=B / dt, ms=dt * 1e3, cores=os.cpu_count(), steps=steps,
-                sample=f"{steps} steps x batch {B} patches, fp32, torch CPU ops, {os.cpu_count()} threads")
+        fn = lambda: O.cond_train_step(sd, gam, opt, cr, P, x, y, torch.randn(batch, widths[0]), torch.randn(batch, widths[1]))
+    with torch.no_grad() if args.workload == "sample" else torch.enable_grad():
+        for _ in range(warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (time.perf_counter() - t0) / steps
+    units = batch * (SAMPLES_PER_PATCH if args.workload == "sample" else 1)
+    return dict(value=units / dt, ms=dt * 1e3, cores=os.cpu_count(), steps=steps,
+                sample=f"{steps} steps x batch {batch} per step (= one GPU's share of the workload), fp32, torch CPU ops, "
+                       f"{os.cpu_count()} threads")
+
+
+def gpu_reference_arm(wl, batch, dev, steps=10):
+    """THE BAR (SURVEY 2.1 / BASELINE.md section 5): the reference's own torch call sequence (oracle restatement ->
+    F.conv2d / F.conv_transpose2d / F.batch_norm / autograd / clip_grad_norm_ / torch.optim.Adam) on the same B200,
+    i.e. cuDNN/cuBLAS kernels: fp32 with TF32 convs (torch default) and autocast(bf16) + channels_last, each eager and
+    as a whole-step CUDA graph.  Device-timed with CUDA events; not part of the timed regions of this repo's arm."""
+    from oracle import ref_oracle as O
+    cr, P = wl["cr"], wl["P"]
+    _, sd0, x, y, widths = _oracle_problem(wl, batch, dev)
+    out = {}
+
+    def build(bf16):
+        sd = {k: v.clone() for k, v in sd0.items()}
+        pk = O.param_keys(sd)
+        params = {k: torch.nn.Parameter(sd[k].to(memory_format=torch.channels_last) if (bf16 and sd[k].dim() == 4) else sd[k])
+                  for k in pk}
+        work = dict(sd)
+        work.update(params)
+        gam = [torch.nn.Parameter(torch.tensor(1.0, device=dev)) for _ in range(1 if wl["model"] == "vae" else 2)]
+        opt = torch.optim.Adam([{"params": list(params.values())}, {"params": gam}], lr=1e-4, capturable=True)
+        xi = x.to(memory_format=torch.channels_last) if bf16 else x
+        yi = y.to(memory_format=torch.channels_last) if bf16 else y
+        eps = [torch.randn(batch, w, device=dev) for w in widths]
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+                if wl["model"] == "vae":
+                    x_hat, mu, lv = O.vae_forward(work, cr, P, xi, eps[0], training=True)
+                    terms = O.base_loss(x_hat.float(), x, mu.float(), lv.float(), gam[0])
+                else:
+                    o = O.cond_forward(work, cr, P, xi, yi, eps[0], eps[1], training=True)
+                    x_hat, y_hat, mu_z, lv_z, mu_u, lv_u, mu3, lv3 = [t.float() for t in o]
+                    terms = O.cond_loss(x_hat, x, y_hat, y, mu_u, lv_u, mu_z, lv_z, mu3, lv3, gam[0], gam[1])
+            loss = sum(terms)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+            opt.step()
+            return loss
+        return step
+
+    def timeit(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for name, bf16 in (("fp32_tf32", False), ("bf16_autocast_channels_last", True)):
+        try:
+            step = build(bf16)
+            for _ in range(3):
+                step()
+            ms = timeit(step, steps)
+            out[name + "_eager"] = {"ms_per_step": ms, "value": batch / (ms * 1e-3)}
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            g.replay()
+            ms = timeit(g.replay, steps)
+            out[name + "_cuda_graph"] = {"ms_per_step": ms, "value": batch / (ms * 1e-3)}
+            del g
+        except Exception as ex:  # keep whatever was measured
+            out[name + "_error"] = repr(ex)[:300]
+    best = max((v["value"] for v in out.values() if isinstance(v, dict)), default=None)
+    return {"what": "reference call sequence as torch CUDA ops (cuDNN %s, torch %s) on this GPU, batch %d, device-timed over "
+                    "%d steps" % (torch.backends.cudnn.version(), torch.__version__, batch, steps),
+            "unit": wl["unit"], "variants": out, "best": best}
+
+
+def ddp_check(dev, rank, world, pg=None):
+    """Hardware parity of the data-parallel step (printed by rank 0 under `ddp_check`): every rank runs ONE fp32 fused
+    step on its own shard of a small global batch (sync_bn on, so BatchNorm sees the global batch); rank 0 then repeats
+    the step single-process on the gathered global batch.  grad_rel_err = |g_ddp - g_single|_2 / |g_single|_2 on the
+    all-reduced flat gradient; param_spread = max |p_rank - p_rank0| after the update."""
+    import models
+    from svrs_native.trainer import FusedCondTrainer
+    B = 4
+    res = {}
+    g = torch.Generator().manual_seed(77)
+    X = torch.rand(B * world, 4, 64, 64, generator=g).to(dev)
+    Y = torch.rand(B * world, 4, 32, 32, generator=g).to(dev)
+    eu_all, ez_all = None, None
+
+    def fresh(sync_bn, w):
+        torch.manual_seed(0)
+        m = models.Cond_SRVAE(2, 64).to(dev).train()
+        tr = FusedCondTrainer(m, sync_bn=sync_bn, process_group=pg if w > 1 else None, world_override=w)
+        tr.eng.rng.seed = 99
+        return m, tr
+
+    m, tr = fresh(True, world)
+    tr.eng.rng.sample_offset = rank * B
+    tr.keep_grad = True
+    tr.step(X[rank * B:(rank + 1) * B], Y[rank * B:(rank + 1) * B])
+    g_ddp = tr.last_grad.clone()
+    p_ddp = tr.rt.store.flat.clone()
+    p0 = p_ddp.clone()
+    torch.distributed.broadcast(p0, 0, group=pg)
+    spread = (p_ddp - p0).abs().max()
+    torch.distributed.all_reduce(spread, op=torch.distributed.ReduceOp.MAX, group=pg)
+    res["param_spread"] = float(spread)
+    if rank == 0:
+        m1, tr1 = fresh(False, 1)
+        tr1.keep_grad = True
+        tr1.step(X, Y)
+        g1 = tr1.last_grad
+        res["grad_rel_err"] = float((g_ddp - g1).norm() / g1.norm())
+        res["param_max_abs_diff_vs_single_process"] = float((p_ddp - tr1.rt.store.flat).abs().max())
+        res["what"] = (f"fp32, {B} patches per rank x {world} ranks vs one process on the {B * world}-patch global batch; sync_bn; "
+                       "SUM all-reduce with KL upstream gradients scaled 1/world")
+    torch.distributed.barrier(group=pg)
+    return res
 
 
 def main():
@@ -130,31 +289,40 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", type=str, default="cond_grid", choices=["cond_grid", "vae"])
+    ap.add_argument("--workload", type=str, default="cond_grid", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", type=str, default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl_name = ("CondVAE cr=2 P=64 grid mode: 8 tiles (256x256x4) -> 128 patches per GPU" if args.workload == "cond_grid"
-               else "VAE cr=2 P=64, 256 patches per GPU")
-    metric = "train patches/sec (64x64 SR CondVAE, device-timed)"
+    wl = WORKLOADS[args.workload]
+    P, S = wl["P"], wl["S"]
+    per_tile = (S // P) ** 2
+    per_gpu = wl["tiles"] * per_tile                     # patches (crops) per GPU and step
+    units_per_gpu = per_gpu * (SAMPLES_PER_PATCH if args.workload == "sample" else 1)
+    metric, unit = wl["metric"], wl["unit"]
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_arm(args, args.workload)
+        steps = max(1, min(args.steps, 20))
+        warm = max(1, min(args.warmup, 2))
+        if per_gpu >= 512 or args.workload == "cond256":   # keep the CPU arm within minutes
+            steps, warm = min(steps, 3), 1
+        r = cpu_reference_arm(args, wl, per_gpu, steps, warm)
         print(json.dumps({
-            "impl": "reference", "metric": metric, "value": r["value"], "unit": "patches/s", "n_gpus": args.gpus,
+            "impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
             "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": wl_name, "note": "CPU arm runs a bounded sample: batch 8 patches per step"},
-            "cpu_baseline": {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
-            "e2e": {"value": r["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": {"workload": wl["name"], "note": f"CPU arm: one GPU's share of the workload ({per_gpu} per step) on the host cores"},
+            "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
 
@@ -165,46 +333,46 @@ def main():
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     import models
-    from dataset import grid_patch_normalize, synthetic_tiles
+    from dataset import TilePrefetcher, grid_patch_pair, synthetic_tiles
     from svrs_native.trainer import FusedCondTrainer, FusedVaeTrainer
 
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     torch.manual_seed(0)
-    if args.workload == "cond_grid":
-        model = models.Cond_SRVAE(CR, PATCH).to(dev)
-        per_gpu = TILES_PER_GPU * (256 // PATCH) ** 2
-        flop_per_patch = FLOP_PER_PATCH_TRAIN
-    else:
-        model = models.VAE(CR, PATCH).to(dev)
-        per_gpu = 256
-        flop_per_patch = FLOP_PER_PATCH_VAE
+    is_vae = wl["model"] == "vae"
+    model = (models.VAE(wl["cr"], P) if is_vae else models.Cond_SRVAE(wl["cr"], P)).to(dev)
     model.set_compute_dtype(dtype)
-    model.train()
-    Trainer = FusedCondTrainer if args.workload == "cond_grid" else FusedVaeTrainer
-    tr = Trainer(model)
-    tr.eng.rng.seed = 2026
-    tr.eng.rng.sample_offset = rank * per_gpu           # partition-invariant eps (SURVEY 8.4 row e iii)
     use_graph = not args.no_graph
+    is_sample = args.workload == "sample"
+    if is_sample:
+        model.eval()
+        eng = model._engine()
+        eng.rng.seed = 2026
+        rt = eng.rt
+    else:
+        model.train()
+        tr = (FusedVaeTrainer if is_vae else FusedCondTrainer)(model)
+        tr.eng.rng.seed = 2026
+        tr.eng.rng.sample_offset = rank * per_gpu           # partition-invariant eps (SURVEY 8.4 row e iii)
+        rt = tr.rt
 
     # synthetic tiles: a few distinct tile sets rotated across steps; pinned host copies for the e2e leg
-    n_sets = 4
+    n_sets = 4 if wl["tiles"] <= 16 else 2
     host_sets = []
     for s in range(n_sets):
-        lr, hr = synthetic_tiles(TILES_PER_GPU if args.workload == "cond_grid" else per_gpu // 16, 256, seed=100 + 17 * rank + s)
+        lr, hr = synthetic_tiles(wl["tiles"], S, seed=100 + 17 * rank + s)
         host_sets.append((lr.pin_memory(), hr.pin_memory()))
     dev_sets = [(lr.to(dev), hr.to(dev)) for lr, hr in host_sets]
-    lr_buf, hr_buf = torch.empty_like(dev_sets[0][0]), torch.empty_like(dev_sets[0][1])
-    h2d_bytes = lr_buf.numel() * 4 + hr_buf.numel() * 4
+    h2d_bytes = sum(t.numel() * 4 for t in dev_sets[0])
 
     def step_from_device(lr, hr):
-        if args.workload == "cond_grid":
-            y = grid_patch_normalize(lr, PATCH // 2)
-            x = grid_patch_normalize(hr, PATCH)
-            tr.rt.launches += 2
-            return tr.step(x, y, use_graph=use_graph)
-        x = grid_patch_normalize(hr, PATCH)
-        tr.rt.launches += 1
-        return tr.step(x, use_graph=use_graph)
+        """One step from device-resident tiles: grid-patch gather + normalise (dual emit: fp32 targets and the
+        compute-dtype NHWC operands of the first conv layers), then the fused step / the sample decode."""
+        if is_sample:
+            yb = grid_patch_pair(lr, P // 2, dtype)
+            return eng.sample_stats_batch(yb, SAMPLES_PER_PATCH)
+        if is_vae:
+            return tr.step_tiles(hr, patch_size=P, use_graph=use_graph)
+        return tr.step_tiles(hr, lr, patch_size=P, use_graph=use_graph)
 
     def barrier():
         if world > 1:
@@ -217,7 +385,7 @@ def main():
     barrier()
 
     # ---------------- timed region 1: device-resident inputs (value)
-    l0 = tr.rt.launches
+    l0 = rt.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         barrier()
@@ -227,17 +395,18 @@ def main():
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
-    launches = tr.rt.launches - l0
-    last_loss = float(out[4])
+    launches = rt.launches - l0
+    out_small = out if out.numel() <= 8 else out.flatten()[:5]
+    last_loss = float(out_small.flatten()[-1])
 
     # ---------------- timed region 2: host buffers through the public API (e2e)
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    loss_host = torch.empty(5, dtype=torch.float32).pin_memory()
+    d2h_elems = out.numel()
+    loss_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
     barrier()
     e2.record()
     # the package's own feed (dataset.TilePrefetcher): pinned host tiles -> device on a copy stream, double-buffered, so the
-    # H2D copy of step i+1 overlaps step i; every step's copy and the D2H of its loss terms are inside the timed region
-    from dataset import TilePrefetcher
+    # H2D copy of step i+1 overlaps step i; every step's copy and the D2H of its result are inside the timed region
     feed = TilePrefetcher((host_sets[i % n_sets] for i in range(args.steps)), dev)
     for lr_d, hr_d in feed:
         out = step_from_device(lr_d, hr_d)
@@ -250,54 +419,76 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    total_patches = per_gpu * world * args.steps
-    value = total_patches / (ms * 1e-3)
-    e2e_value = total_patches / (ms_e2e * 1e-3)
+    total_units = units_per_gpu * world * args.steps
+    value = total_units / (ms * 1e-3)
+    e2e_value = total_units / (ms_e2e * 1e-3)
 
     # ---------------- roofline of the dominant kernel family (eager, per-launch CUDA events; not in the timed region)
     pk = peaks()
-    roof = None
-    try:
-        from svrs_native import profile as prof
-        roof = prof.dominant_kernel_roofline(tr, step_from_device, dev_sets[0], pk, steps=2)
-        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (tools/ncu_traffic.py)
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            if tj.get("kernel") and tj["kernel"] in roof.get("kernel", ""):
-                roof["traffic"] = tj["dram_bytes_per_launch"]
-                roof["traffic_source"] = "profiles/traffic_r01.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
-    except Exception as ex:  # keep the headline number even if the profiling pass fails
-        roof = {"error": repr(ex)}
+    roof, roof_hbm = None, None
+    if not args.no_profile and not is_sample:
+        try:
+            from svrs_native import profile as prof
+            roof, roof_hbm = prof.dominant_kernel_roofline(tr, dev_sets[0], pk, steps=2, dtype=dtype)
+            # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (tools/ncu_traffic.py)
+            for tname in ("traffic_r02.json", "traffic_r01.json"):
+                tpath = os.path.join(ROOT, "profiles", tname)
+                if os.path.exists(tpath):
+                    tj = json.load(open(tpath))
+                    if tj.get("kernel") and tj["kernel"] in roof.get("kernel", ""):
+                        roof["traffic"] = tj["dram_bytes_per_launch"]
+                        roof["traffic_source"] = f"profiles/{tname} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+                        break
+        except Exception as ex:  # keep the headline number even if the profiling pass fails
+            roof = {"error": repr(ex)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            class A: steps, warmup = 3, 1
-            r = cpu_reference_arm(A, args.workload)
-            cpu = {"value": r["value"], "unit": "patches/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+            r = cpu_reference_arm(args, wl, min(per_gpu, 128) if args.workload != "cond256" else 2, 2, 1)
+            cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         except Exception as ex:
             cpu = {"error": repr(ex)}
 
+    gref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference and not is_sample:
+        try:
+            gref = gpu_reference_arm(wl, per_gpu, dev)
+            if gref.get("best"):
+                gref["this_repo_over_best_reference_variant"] = value / gref["best"]
+        except Exception as ex:
+            gref = {"error": repr(ex)[:300]}
+
+    ddp = None
+    if world > 1 and not is_sample and not is_vae and P == 64:
+        try:
+            ddp = ddp_check(dev, rank, world)
+        except Exception as ex:
+            ddp = {"error": repr(ex)[:300]}
+
     if rank == 0:
-        act_mb = 6.24 * 3 * per_gpu
         line = {
-            "metric": metric, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": wl_name, "global_patches": per_gpu * world, "parallelism": f"dp{world}",
-                       "cuda_graph": use_graph, "l2": f"working set per step ~{act_mb:.0f} MB of activations + 82 MB weights "
-                       f"+ 247 MB Adam state per GPU, larger than the 126 MB L2; {n_sets} tile sets rotated",
-                       "tensor_roofline_patches_per_s_per_gpu": pk["tf_sus"] * 1e12 / flop_per_patch,
-                       "frac_of_step_roofline": (value / world) / (pk["tf_sus"] * 1e12 / flop_per_patch),
+            "config": {"workload": wl["name"], "global_units_per_step": units_per_gpu * world, "parallelism": f"dp{world}",
+                       "cuda_graph": use_graph and not is_sample,
+                       "l2": f"inputs + activations + weights + Adam state per step far exceed the 126 MB L2 "
+                             f"(~{6.24 * 3 * per_gpu * (P // 64) ** 2:.0f} MB of activations); {n_sets} tile sets rotated",
+                       "tensor_roofline_units_per_s_per_gpu": pk["tf_sus"] * 1e12 / wl["flop"],
+                       "frac_of_step_roofline": (value / world) / (pk["tf_sus"] * 1e12 / wl["flop"]),
                        "last_loss": last_loss},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 20,
-                    "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_elems * out.element_size(), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "roofline": roof,
+            "roofline_hbm": roof_hbm,
             "cpu_baseline": cpu,
+            "gpu_reference": gref,
         }
+        if ddp is not None:
+            line["ddp_check"] = ddp
         print(json.dumps(line), flush=True)
     if world > 1:
         # Leave without tearing NCCL down: communicators captured inside CUDA graphs make destroy_process_group() hang

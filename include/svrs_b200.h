@@ -84,10 +84,7 @@ int svrs_unpack_grads_multi(const void* jobs, int njobs, int total_tiles, int ma
  * of fprop is the NK pack of dgrad and vice versa.  w_nk may be NULL (forces the SIMT kernel). */
 void svrs_set_tc_enabled(int enabled);   /* default 1; 0 forces the SIMT kernels everywhere (A/B tests) */
 /* conv3_halo (csrc/conv_halo.cu): 3x3 stride-1 fprop/dgrad on maps tiling into 8x16 blocks load each tile's activation
- * halo ONCE and address the nine taps as shared-memory descriptors.  mode 0 = off (per-tap TMA kernel), 1 = on (default),
- * 2 = historical: in the first revision of the kernel (git e22cd04) it set the descriptor base-offset field to
- * (start >> 7) & 7, which gave WRONG results on B200 - the measurement that showed the UMMA swizzle to be a function of the
- * absolute shared-memory address.  The single-lane issue loop that replaced it has no such variant: 2 now behaves like 1. */
+ * halo ONCE and address the nine taps as shared-memory descriptors.  mode 0 = off (per-tap TMA kernel), 1 = on (default). */
 void svrs_set_halo_mode(int mode);
 int svrs_tc_would_run(int dtype, int K, int Nc, int OH, int OW); /* 1 if conv_tc takes a GEMM of these dims */
 
@@ -96,6 +93,22 @@ int svrs_tc_would_run(int dtype, int K, int Nc, int OH, int OW); /* 1 if conv_tc
  *      ksize 3 => stride 1, ksize 4 => stride 2 (pad 1 both). */
 int svrs_conv2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
                       int N, int H, int W, int Cin, int Cout, int ksize, int act, void* stream);
+/* Extended fprop (same call sites).  Extras, each optional:
+ *   out_dtype - storage type of y when it differs from `dtype`: SVRS_F32 output of a bf16 conv is available on the
+ *               narrow per-pixel kernel (the 16->4 + Sigmoid tail of both decoders, cond_vae.py:79-80,142-143: x_hat reaches
+ *               the NLL without a bf16 rounding);
+ *   y_nchw    - second output, fp32, in the reference's NCHW-flat order: y_nchw[n*y_nchw_ld + c*OH*OW + oy*OW + ox], written
+ *               by the tcgen05 epilogue straight from the fp32 accumulators (after bias / activation).  This is how the
+ *               posterior and prior heads (nn.Flatten + torch.chunk, cond_vae.py:47,106,163,209,229,254,259) leave the
+ *               conv stacks: no bf16 rounding of mu / logvar and no separate layout kernel.  y may then be NULL;
+ *   bn_sums   - SVRS_BN_REPLICAS x double[2*Cout]: per-channel sum and sum of squares of the conv output (before the
+ *               activation), accumulated in the epilogue from the fp32 accumulators - the batch statistics of the
+ *               nn.BatchNorm2d that follows (layers.py:237,252-253) without re-reading the tensor (replaces svrs_bn_stats).
+ * Returns SVRS_E_UNSUPPORTED when the kernel that takes this shape cannot provide a requested extra (callers then use the
+ * separate kernels: svrs_nhwc_to_nchw / svrs_bn_stats). */
+int svrs_conv2d_fprop_ex(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
+                         int out_dtype, float* y_nchw, int64_t y_nchw_ld, double* bn_sums,
+                         int N, int H, int W, int Cin, int Cout, int ksize, int act, void* stream);
 /* dgrad: dy [N,H/s,W/s,Cout] -> dx [N,H,W,Cin]; w_kn = p01 pack [tap][Cout][Cin].
  * (autograd of the same call sites, reached through loss.backward() models/base.py:105) */
 int svrs_conv2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
@@ -117,12 +130,21 @@ int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float* dw_packed
  *      four output-parity sub-convolutions of 2x2 taps.  w_kn = p01 pack [tap][Cin][Cout]. */
 int svrs_convT2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
                        int N, int H, int W, int Cin, int Cout, int act, void* stream);
+/* with the fused BatchNorm statistics of svrs_conv2d_fprop_ex (up_block: ConvTranspose2d -> BatchNorm2d, layers.py:275-278) */
+int svrs_convT2d_fprop_ex(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
+                          double* bn_sums, int N, int H, int W, int Cin, int Cout, int act, void* stream);
 /* dgrad: dy [N,2H,2W,Cout] -> dx [N,H,W,Cin]; w_kn = p10 pack [tap][Cout][Cin]. */
 int svrs_convT2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
                        int N, int H, int W, int Cin, int Cout, void* stream);
 /* wgrad: dw[Cin][Cout][4][4] += ... ; db[Cout] += column sums of dy. */
 int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, float* dw_packed, float* db, int dtype,
                        int N, int H, int W, int Cin, int Cout, int ksplit, void* stream);
+
+/* Layout the wgrad entry points leave in dw_packed for a problem: 1 = per-tap packed [tap][d1][d0] (tcgen05 kernels),
+ * 0 = nothing (a SIMT kernel accumulates torch layout into dw).  The fused optimiser (svrs_adam_multi) passes the SAME
+ * buffer as dw and dw_packed and reads the gradient in whichever layout this reports, so no unpack pass is needed. */
+int svrs_conv2d_wgrad_layout(int dtype, int N, int H, int W, int Cin, int Cout, int ksize);
+int svrs_convT2d_wgrad_layout(int dtype, int N, int H, int W, int Cin, int Cout);
 
 /* ---- nn.BatchNorm2d (+ nn.ReLU) of down_block / up_block (layers.py:237-238,252-255,278-279,293-296)
  *      x viewed as [M = N*H*W][C].  `sums` is a zeroed scratch of SVRS_BN_REPLICAS x double[2*C] (sum, sum of squares):
@@ -137,8 +159,10 @@ int svrs_bn_finalize_train(const double* sums, int64_t M, int C, const float* ga
                            int64_t* num_batches_tracked, int n_updates,
                            float* scale, float* shift, float* mean, float* invstd, void* stream);
 /* train, fused: svrs_bn_finalize_train + svrs_bn_apply in one launch (same coefficients bit for bit; every block derives
- * them from `sums`, block 0 publishes scale/shift/mean/invstd and advances the running statistics).  C <= 1024. */
-int svrs_bn_apply_train(const void* x, void* y, int dtype, int64_t M, int C, const double* sums,
+ * them from `sums`, block 0 publishes scale/shift/mean/invstd and advances the running statistics).  C <= 1024.
+ * M_stat (0 = M): number of rows the statistics in `sums` were taken over when it differs from the rows of THIS tensor -
+ * sync_bn data parallelism all-reduces `sums` across ranks, so M_stat is then the global row count. */
+int svrs_bn_apply_train(const void* x, void* y, int dtype, int64_t M, int64_t M_stat, int C, const double* sums,
                         const float* gamma, const float* beta, float eps, float momentum,
                         float* running_mean, float* running_var, int64_t* num_batches_tracked, int n_updates,
                         int relu, float* scale, float* shift, float* mean, float* invstd, void* stream);
@@ -155,7 +179,7 @@ int svrs_bn_bwd_reduce(const void* x, const void* dy, int dtype, int64_t M, int 
                        const float* shift, const float* mean, const float* invstd, int relu,
                        double* sums, void* stream);
 /* pass 2: dx = gamma*invstd*(dym - mean(dym) - xhat*mean(dym*xhat)); dgamma += sums[C:], dbeta += sums[:C] */
-int svrs_bn_bwd_apply(const void* x, const void* dy, void* dx, int dtype, int64_t M, int C,
+int svrs_bn_bwd_apply(const void* x, const void* dy, void* dx, int dtype, int64_t M, int64_t M_stat, int C,
                       const float* scale, const float* shift, const float* mean, const float* invstd,
                       const float* gamma, int relu, const double* sums, float* dgamma, float* dbeta,
                       void* stream);
@@ -184,9 +208,11 @@ int svrs_philox_normal(float* out, int B, int Wd, uint64_t seed, uint32_t stream
  *   kl23 :  sum (lv3 - lv2 - 1) + exp(lv2 - lv3) + (mu2-mu3)^2 exp(-lv3)   width W2, strides ld2/ld3
  * fwd accumulates the four raw sums in double acc[4] = {ssq_x, ssq_y, kl1, kl23} (zeroed by caller);
  * finalize turns them into the reference's terms out[5] = {mse_x, kld_u, mse_y, kld_z, their sum} (fp32):
- *   mse = ssq/(2 g^2) + n log g ;  kld = 0.5 * sum / B.   Unused pieces: pass NULL / n = 0. */
-int svrs_elbo_fwd(const void* recon_x, const void* x, int dt_x, int64_t n_x,
-                  const void* recon_y, const void* y, int dt_y, int64_t n_y,
+ *   mse = ssq/(2 g^2) + n log g ;  kld = 0.5 * sum / B.   Unused pieces: pass NULL / n = 0.
+ * dt_x / dt_y are the dtypes of the reconstructions, dt_tx / dt_ty those of the targets (the fused step keeps the
+ * targets in fp32 NHWC next to the bf16 conv operands; any layout works as long as recon and target share it). */
+int svrs_elbo_fwd(const void* recon_x, const void* x, int dt_x, int dt_tx, int64_t n_x,
+                  const void* recon_y, const void* y, int dt_y, int dt_ty, int64_t n_y,
                   const float* mu1, const float* lv1, int64_t ld1, int W1,
                   const float* mu2, const float* lv2, int64_t ld2,
                   const float* mu3, const float* lv3, int64_t ld3, int W2,
@@ -198,14 +224,16 @@ int svrs_elbo_finalize(const double* acc, int64_t n_x, int64_t n_y, int B, const
  * d_mu1 = g*mu1/B ; d_lv1 = g*0.5*(exp(lv1)-1)/B
  * d_mu2 = g*(mu2-mu3)exp(-lv3)/B = -d_mu3 ; d_lv2 = g*0.5*(exp(lv2-lv3)-1)/B
  * d_lv3 = g*0.5*(1 - exp(lv2-lv3) - (mu2-mu3)^2 exp(-lv3))/B
- * latent grads are written with the same row strides as their inputs (dst strides dld1/dld2/dld3). */
-int svrs_elbo_bwd(const void* recon_x, const void* x, int dt_x, int64_t n_x, void* d_recon_x,
-                  const void* recon_y, const void* y, int dt_y, int64_t n_y, void* d_recon_y,
+ * latent grads are written with the same row strides as their inputs (dst strides dld1/dld2/dld3).
+ * dt_dx / dt_dy: dtype of d_recon_x / d_recon_y.  act = SVRS_ACT_SIGMOID: the reconstructions are sigmoid outputs and
+ * d_recon_* receives the gradient wrt the PRE-activation, d * r * (1 - r) (nn.Sigmoid backward folded in); else SVRS_ACT_NONE. */
+int svrs_elbo_bwd(const void* recon_x, const void* x, int dt_x, int dt_tx, int64_t n_x, void* d_recon_x, int dt_dx,
+                  const void* recon_y, const void* y, int dt_y, int dt_ty, int64_t n_y, void* d_recon_y, int dt_dy,
                   const float* mu1, const float* lv1, int64_t ld1, int W1, float* d_mu1, float* d_lv1, int64_t dld1,
                   const float* mu2, const float* lv2, int64_t ld2, float* d_mu2, float* d_lv2, int64_t dld2,
                   const float* mu3, const float* lv3, int64_t ld3, int W2, float* d_mu3, float* d_lv3, int64_t dld3,
                   int B, const double* acc, const float* gammas, const float* gout, float* d_gammas,
-                  void* stream);
+                  int act, void* stream);
 
 /* ---- clip_grad_norm_(params, 1.0) + torch.optim.Adam (models/base.py:106-107, train.py:65) on flat buffers */
 int svrs_sumsq(const float* g, int64_t n, double* acc /* += */, void* stream);
@@ -217,6 +245,20 @@ int svrs_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, cons
                    float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
                    const int64_t* step_ptr, void* stream);
 int svrs_step_increment(int64_t* step_ptr, void* stream);
+/* The optimiser tail of the fused step in ONE launch (csrc/optim.cu adam_multi_kernel): for every conv / convT weight the
+ * gradient is read in the layout the wgrad kernel left it in (see svrs_conv2d_wgrad_layout), clip + Adam run on the
+ * torch-layout fp32 master weight and moments, and the updated weight is written into both compute-dtype packs
+ * ([kk][d0][d1] and [kk][d1][d0], see svrs_pack_weights) - replacing svrs_unpack_grads_multi + svrs_clip_adam +
+ * svrs_pack_weights_multi.  `jobs`: DEVICE array of njobs records (svrs_adam_job_bytes() each)
+ *   { int64 off; void* p01; void* p10; int d0, d1, kk; int layout; int tile0; int tiles_b; }
+ * off = element offset of the parameter in the flat buffers p / g / m / v.  Conv jobs (d1 > 0) are cut into 32 x 16 tiles
+ * of the (d0, d1) plane (tiles_b = ceil(d1/16)); plain jobs (d1 == 0: biases, BatchNorm affine) into runs of 2048 of
+ * their d0 elements.  tile0 = running sum of tile counts, total_tiles their total, max_kk <= 16, njobs <= 512.
+ * sumsq / max_norm / grad_scale / step_ptr as in svrs_clip_adam. */
+int svrs_adam_job_bytes(void);
+int svrs_adam_multi(const void* jobs, int njobs, int total_tiles, int max_kk, float* p, const float* g, float* m, float* v,
+                    int pack_dtype, const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
+                    float beta2, float eps, const int64_t* step_ptr, void* stream);
 
 /* ---- grid patching + per-patch per-channel min-max normalisation
  *      (dataset.py:220-247,265-274 ; utils.py:4-23).  tiles [T][C][S][S] (fp32, or int16 when
@@ -225,6 +267,17 @@ int svrs_step_increment(int64_t* step_ptr, void* stream);
  *      the reference: (x - min) / ((max - min) + 1e-5f). */
 int svrs_grid_patch_normalize(const void* tiles, int src_is_i16, void* dst, int dst_dtype, int nhwc,
                               int T, int C, int S, int P, void* stream);
+
+/* General form (TMA gather, csrc/patch.cu): one CTA per patch fetches the patch's C channel planes with ONE 3-D TMA box
+ * into shared memory (tiles are read from HBM once), takes min/max there and emits up to three layouts from the staged
+ * data: out_nchw_f32 [npatch][C][P][P] (the reference's layout), out_nhwc_f32 [npatch][P][P][C] (NLL target of the fused
+ * step) and out_nhwc_bf16 (operand of the first conv layer); any may be NULL.  origins == NULL: grid mode as above;
+ * otherwise a DEVICE array int32[npatch][3] = (tile, top, left): the reference's random crop (dataset.py:205-216:
+ * LR at (top, left), HR at (2*top, 2*left)) with the draws made by the caller.  Needs S*elem and P*elem multiples of 16
+ * bytes and 8 <= P <= 256. */
+int svrs_patch_gather_normalize(const void* tiles, int src_is_i16, int T, int C, int S, int P,
+                                const int32_t* origins, int npatch, float* out_nchw_f32, float* out_nhwc_f32,
+                                void* out_nhwc_bf16, void* stream);
 
 /* ---- backward of the fused epilogue activations from their OUTPUT y:
  *      sigmoid: dx = dy*y*(1-y) ; hardtanh(-7,7): dx = dy if -7 < y < 7 else 0.  In-place (dx == dy) allowed. */

@@ -37,6 +37,71 @@ def grid_patch_normalize(tiles: torch.Tensor, patch_size: int, out_dtype=torch.f
     return out
 
 
+def _gather(tiles: torch.Tensor, patch_size: int, origins, npatch: int, compute_dtype, want_nchw: bool, rt=None):
+    """svrs_patch_gather_normalize (TMA gather): tiles [T,C,S,S] -> (nchw fp32 | None, PatchBatch)."""
+    from svrs_native.engine import PatchBatch
+    from svrs_native.lib import lib
+
+    if not tiles.is_cuda:
+        raise RuntimeError("patch gather: tiles must be on a CUDA device (no CPU fallback)")
+    if tiles.dtype not in (torch.float32, torch.int16):
+        tiles = tiles.float()
+    tiles = tiles.contiguous()
+    T, C, S, S2 = tiles.shape
+    assert S == S2
+    dev = tiles.device
+    P = patch_size
+    nchw = torch.empty((npatch, C, P, P), device=dev, dtype=torch.float32) if want_nchw else None
+    f32 = torch.empty((npatch, P, P, C), device=dev, dtype=torch.float32)
+    bf = torch.empty((npatch, P, P, C), device=dev, dtype=torch.bfloat16) if compute_dtype == torch.bfloat16 else None
+    lib.patch_gather_normalize(tiles.data_ptr(), int(tiles.dtype == torch.int16), T, C, S, P,
+                               None if origins is None else origins.data_ptr(), npatch,
+                               None if nchw is None else nchw.data_ptr(), f32.data_ptr(),
+                               None if bf is None else bf.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if rt is not None:
+        rt.launches += 1
+    return nchw, PatchBatch(f32, f32 if bf is None else bf)
+
+
+def grid_patch_pair(tiles: torch.Tensor, patch_size: int, compute_dtype=torch.float32, rt=None):
+    """Grid-mode patches of `tiles` as the fused step consumes them (one launch, tiles read once): a PatchBatch holding the
+    NHWC fp32 patches (NLL target) and their NHWC copy in the compute dtype (operand of the first conv layer)."""
+    T, _, S, _ = tiles.shape
+    assert S % patch_size == 0
+    return _gather(tiles, patch_size, None, T * (S // patch_size) ** 2, compute_dtype, False, rt)[1]
+
+
+def random_crop_origins(n_tiles: int, lr_size: int, patch_size: int, generator: Optional[torch.Generator] = None,
+                        device="cpu") -> torch.Tensor:
+    """The reference's random-crop draws (dataset.py:205-208): one crop per tile, top / left uniform in
+    [0, lr_size - patch_size//2) on the LR tile.  Returns int32 [n_tiles, 3] = (tile, top, left) for the LR tiles; the
+    HR origins are (tile, 2*top, 2*left) (dataset.py:212-216), see hr_origins()."""
+    half = patch_size // 2
+    top = torch.randint(0, lr_size - half, (n_tiles,), generator=generator)
+    left = torch.randint(0, lr_size - half, (n_tiles,), generator=generator)
+    o = torch.stack((torch.arange(n_tiles), top, left), dim=1).to(torch.int32)
+    return o.to(device)
+
+
+def hr_origins(lr_origins: torch.Tensor) -> torch.Tensor:
+    o = lr_origins.clone()
+    o[:, 1:] *= 2
+    return o
+
+
+def random_crop_batch(lr_tiles: torch.Tensor, hr_tiles: torch.Tensor, patch_size: int, lr_origins: torch.Tensor,
+                      compute_dtype=torch.float32, want_nchw: bool = True):
+    """On-device equivalent of Sen2VenDataset(crop="random") (dataset.py:140-218): the same-origin LR / HR crops of every
+    tile at the given origins, min-max normalised per patch and channel (utils.py:4-23), gathered by TMA from the
+    device-resident tile pool.  Returns ((y_nchw, y_batch), (x_nchw, x_batch))."""
+    n = lr_origins.shape[0]
+    lo = lr_origins.to(lr_tiles.device, torch.int32).contiguous()
+    ho = hr_origins(lo).contiguous()
+    y = _gather(lr_tiles, patch_size // 2, lo, n, compute_dtype, want_nchw)
+    x = _gather(hr_tiles, patch_size, ho, n, compute_dtype, want_nchw)
+    return y, x
+
+
 def grid_batch(lr_tiles: torch.Tensor, hr_tiles: torch.Tensor, patch_size: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """(LR tiles [T,4,S/2,S/2], HR tiles [T,4,S,S]) -> (y, x) patch batch in the (y, x) order of
     Cond_SRVAE.train_step (cond_vae.py:327)."""

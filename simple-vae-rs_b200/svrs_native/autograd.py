@@ -35,7 +35,7 @@ class CondForwardFn(torch.autograd.Function):
         rt = eng.rt
         rt.zero_grads()
         cl = lambda t: None if t is None else t.contiguous().clone()
-        eng.backward(ctx.ectx, d_xhat, d_yhat, cl(d_enc_z), cl(d_enc_u), d_mu3, d_lv3)
+        eng.backward(ctx.ectx, d_xhat, d_yhat, cl(d_enc_z), cl(d_enc_u), d_mu3, cl(d_lv3))
         _publish_grads(rt)
         ctx.ectx = None
         return (None,) * 8

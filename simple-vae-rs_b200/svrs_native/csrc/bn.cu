@@ -628,21 +628,22 @@ extern "C" int svrs_bn_apply(const void* x, void* y, int dtype, int64_t M, int C
     return check_launch("bn_apply");
 }
 
-extern "C" int svrs_bn_apply_train(const void* x, void* y, int dtype, int64_t M, int C, const double* sums,
+extern "C" int svrs_bn_apply_train(const void* x, void* y, int dtype, int64_t M, int64_t M_stat, int C, const double* sums,
                                    const float* gamma, const float* beta, float eps, float momentum,
                                    float* running_mean, float* running_var, int64_t* num_batches_tracked, int n_updates,
                                    int relu, float* scale, float* shift, float* mean, float* invstd, void* stream) {
     SVRS_CHECK_ARG(x && y && sums && scale && shift && M > 0 && c_ok(C) && C <= 1024, "bn_apply_train: bad args (C=%d must be 4*2^k <= 1024)", C);
     const bool w8 = wide(dtype, C);
+    const long long Ms = M_stat > 0 ? M_stat : M;       // rows the statistics in `sums` were taken over (sync_bn: global batch)
     long long nvec = M * C / (w8 ? 8 : 4);
     cudaStream_t st = (cudaStream_t)stream;
     long long* nbt = (long long*)num_batches_tracked;
     if (dtype == SVRS_F32)
-        SVRS_LAUNCH((bn_apply_train_kernel<float, 4>), ew_grid(nvec), 256, 0, st, (const float*)x, (float*)y, nvec, C / 4, (long long)M, C, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, n_updates, relu, scale, shift, mean, invstd);
+        SVRS_LAUNCH((bn_apply_train_kernel<float, 4>), ew_grid(nvec), 256, 0, st, (const float*)x, (float*)y, nvec, C / 4, Ms, C, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, n_updates, relu, scale, shift, mean, invstd);
     else if (dtype == SVRS_BF16 && w8)
-        SVRS_LAUNCH((bn_apply_train_kernel<__nv_bfloat16, 8>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 8, (long long)M, C, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, n_updates, relu, scale, shift, mean, invstd);
+        SVRS_LAUNCH((bn_apply_train_kernel<__nv_bfloat16, 8>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 8, Ms, C, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, n_updates, relu, scale, shift, mean, invstd);
     else if (dtype == SVRS_BF16)
-        SVRS_LAUNCH((bn_apply_train_kernel<__nv_bfloat16, 4>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 4, (long long)M, C, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, n_updates, relu, scale, shift, mean, invstd);
+        SVRS_LAUNCH((bn_apply_train_kernel<__nv_bfloat16, 4>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, nvec, C / 4, Ms, C, sums, gamma, beta, eps, momentum, running_mean, running_var, nbt, n_updates, relu, scale, shift, mean, invstd);
     else { set_error("bn_apply_train: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_apply_train");
 }
@@ -669,20 +670,21 @@ extern "C" int svrs_bn_bwd_reduce(const void* x, const void* dy, int dtype, int6
     return check_launch("bn_bwd_reduce");
 }
 
-extern "C" int svrs_bn_bwd_apply(const void* x, const void* dy, void* dx, int dtype, int64_t M, int C,
+extern "C" int svrs_bn_bwd_apply(const void* x, const void* dy, void* dx, int dtype, int64_t M, int64_t M_stat, int C,
                                  const float* scale, const float* shift, const float* mean, const float* invstd,
                                  const float* gamma, int relu, const double* sums, float* dgamma, float* dbeta,
                                  void* stream) {
     SVRS_CHECK_ARG(x && dy && dx && sums && scale && shift && mean && invstd && M > 0 && c_ok(C), "bn_bwd_apply: bad args");
     const bool w8 = wide(dtype, C);
+    const long long Ms = M_stat > 0 ? M_stat : M;
     long long nvec = M * C / (w8 ? 8 : 4);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SVRS_F32)
-        SVRS_LAUNCH((bn_bwd_apply_kernel<float, 4>), ew_grid(nvec), 256, 0, st, (const float*)x, (const float*)dy, (float*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
+        SVRS_LAUNCH((bn_bwd_apply_kernel<float, 4>), ew_grid(nvec), 256, 0, st, (const float*)x, (const float*)dy, (float*)dx, nvec, C / 4, Ms, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
     else if (dtype == SVRS_BF16 && w8)
-        SVRS_LAUNCH((bn_bwd_apply_kernel<__nv_bfloat16, 8>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 8, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
+        SVRS_LAUNCH((bn_bwd_apply_kernel<__nv_bfloat16, 8>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 8, Ms, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
     else if (dtype == SVRS_BF16)
-        SVRS_LAUNCH((bn_bwd_apply_kernel<__nv_bfloat16, 4>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 4, M, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
+        SVRS_LAUNCH((bn_bwd_apply_kernel<__nv_bfloat16, 4>), ew_grid(nvec), 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nvec, C / 4, Ms, C, scale, shift, mean, invstd, gamma, relu, sums, dgamma, dbeta);
     else { set_error("bn_bwd_apply: bad dtype"); return SVRS_E_ARG; }
     return check_launch("bn_bwd_apply");
 }

@@ -40,6 +40,9 @@ struct alignas(64) HaloParams {
     int act, resident, base_off_mode;
     int cw;                         // channels per chunk: 64 / 32 / 16 (SWIZZLE_128B / 64B / 32B rows of 2*cw bytes)
     int hy[9], hx[9], wtap[9];      // tap -> halo offset (dy+1, dx+1) and packed-weight tap index
+    float* out2;                    // optional fp32 NCHW-flat second output (EpiRow), per-sample stride out2_ld
+    long long out2_ld;
+    double* bn_sums;                // optional BatchNorm statistics scratch
 };
 
 __device__ __forceinline__ uint64_t halo_desc(uint32_t saddr, int mode) {
@@ -73,6 +76,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
     const uint32_t tmem_slot = bar_base + 8u * (2 * HL_HALO_SLOTS + 2 * HL_W_SLOTS + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    __shared__ float s_bn[2 * EPI_BN_MAXC];
+    if (p.bn_sums) epi_bn_zero(s_bn);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.in_map);
@@ -206,12 +211,17 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
             mbar_wait(tfull(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-            epi_dispatch(p.act, taddr, p.n_tile, half, orow, p.bias, c_base, p.Nc, true);
+            EpiRow er;
+            er.o2 = p.out2 ? p.out2 + (long long)n * p.out2_ld + (long long)(ty * 16 + iy) * p.OW + (tx * 8 + ix) : nullptr;
+            er.hw = p.OH * p.OW;
+            er.sbn = p.bn_sums ? s_bn : nullptr;
+            epi_dispatch(p.act, taddr, p.n_tile, half, p.out ? orow : nullptr, p.bias, c_base, p.Nc, true, er);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.bn_sums) epi_bn_flush(s_bn, p.bn_sums, p.Nc, threadIdx.x - 64, 32 * TC_EPI_WARPS);
     }
 
     tc_fence_before();
@@ -240,6 +250,7 @@ struct alignas(64) HaloTParams {
     long long o_sn, o_sy, o_sx;         // element strides of one output-parity view of the fine tensor
     long long out_off[4];               // element offset of each parity view
     int hy[16], hx[16], wtap[16];       // index = parity * 4 + tap
+    double* bn_sums;                    // optional BatchNorm statistics scratch (SVRS_BN_REPLICAS x double[2*Nc])
 };
 
 template <int KSUB>
@@ -262,6 +273,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) convT_halo_kernel(const __grid_
     const uint32_t tmem_slot = bar_base + 8u * (2 * HL_HALO_SLOTS + 2 * HL_W_SLOTS + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    __shared__ float s_bn[2 * EPI_BN_MAXC];
+    if (p.bn_sums) epi_bn_zero(s_bn);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.in_map);
@@ -361,15 +374,19 @@ __global__ void __launch_bounds__(HL_THREADS, 1) convT_halo_kernel(const __grid_
             mbar_wait(tfull(acc), acc_phase);
             tc_fence_after();
 #pragma unroll 1
+            EpiRow er;
+            er.o2 = nullptr; er.hw = 0;
+            er.sbn = p.bn_sums ? s_bn : nullptr;
             for (int par = 0; par < 4; ++par) {
                 const uint32_t taddr = tmem_base + acc * 256u + (uint32_t)(par * p.n_tile) + ((uint32_t)(q * 32) << 16);
-                epi_dispatch(p.act, taddr, p.n_tile, half, p.out + p.out_off[par] + pix, p.bias, c_base, p.Nc, true);
+                epi_dispatch(p.act, taddr, p.n_tile, half, p.out + p.out_off[par] + pix, p.bias, c_base, p.Nc, true, er);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.bn_sums) epi_bn_flush(s_bn, p.bn_sums, p.Nc, threadIdx.x - 64, 32 * TC_EPI_WARPS);
     }
 
     tc_fence_before();
@@ -397,7 +414,7 @@ bool convT_halo_supported(int Cr, int Cw, int W, int H) {      // W, H: coarse (
 }
 
 int launch_convT_halo(const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw, int act,
-                      cudaStream_t st) {
+                      const ConvExtra& ex, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(convT_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
@@ -419,6 +436,7 @@ int launch_convT_halo(const void* in, const void* w_nk, const float* bias, void*
     p.cw = Cr % 64 == 0 ? 64 : Cr;
     p.kchunks = Cr / p.cw;
     p.act = act;
+    p.bn_sums = ex.bn_sums;
     p.o_sn = g.o_sn; p.o_sy = g.o_sy; p.o_sx = g.o_sx;
     for (int q = 0; q < 4; ++q) {
         p.out_off[q] = g.prob[q].out_off;
@@ -443,7 +461,7 @@ int launch_convT_halo(const void* in, const void* w_nk, const float* bias, void*
 }
 
 int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
-                      int act, cudaStream_t st) {
+                      int act, const ConvExtra& ex, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
@@ -463,6 +481,7 @@ int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* b
     p.cw = Cr % 64 == 0 ? 64 : Cr;
     p.kchunks = Cr / p.cw;
     p.act = act;
+    p.out2 = ex.out2; p.out2_ld = ex.out2_ld; p.bn_sums = ex.bn_sums;
     p.resident = (9 * p.kchunks * p.n_tile * 2 * p.cw <= HL_W_RESIDENT_MAX) ? 1 : 0;
     p.base_off_mode = g_halo_mode == 2 ? 1 : 0;
     for (int ky = 0; ky < 3; ++ky)

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include "taps.cuh"
+#include "tc_ptx.cuh"
 
 namespace svrs {
 
@@ -14,6 +15,7 @@ struct ConvArgs {
     const void* w;      // KN pack [tap][K][Nc]
     const float* bias;  // [Nc] or null
     int act;
+    double* bn_sums;    // optional: SVRS_BN_REPLICAS x double[2*Nc] BatchNorm statistics of the output (conv_pixel only)
     TapGeom g;
 };
 
@@ -174,74 +176,106 @@ __global__ void __launch_bounds__(256) conv_taps_kernel(const __grid_constant__ 
 // barriers: here one thread owns one output pixel, the per-tap weights sit in shared memory (broadcast float4 reads) and
 // the taps are a register loop.  No barriers after the weight stage-in.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int CR, int CW>
+// TO = storage type of the OUTPUT (fp32 output from bf16 operands: the sigmoid tail that feeds the NLL, so x_hat is
+// never rounded to bf16).  a.bn_sums != NULL: per-channel sum / sum of squares of the fp32 results (BatchNorm batch
+// statistics fused into the producer; warp shuffle -> shared -> one double atomic per channel and block).
+template <typename T, int CR, int CW, typename TO>
 __global__ void __launch_bounds__(256) conv_pixel_kernel(const __grid_constant__ ConvArgs a) {
     pdl_entry();
     __shared__ __align__(16) float ws[16 * CR * CW];
+    __shared__ float s_bn[2 * CW];
     const TapGeom& g = a.g;
     const Prob& pb = g.prob[blockIdx.z];
     const T* __restrict__ in = reinterpret_cast<const T*>(a.in);
     const T* __restrict__ w = reinterpret_cast<const T*>(a.w);
-    T* __restrict__ out = reinterpret_cast<T*>(a.out) + pb.out_off;
+    TO* __restrict__ out = reinterpret_cast<TO*>(a.out) + pb.out_off;
     for (int i = threadIdx.x; i < pb.ntaps * CR * CW; i += 256)
         ws[i] = Cvt<T>::to_f(w[pb.taps[i / (CR * CW)].w_off + i % (CR * CW)]);
+    if (threadIdx.x < 2 * CW) s_bn[threadIdx.x] = 0.f;
     __syncthreads();
     const long long M = (long long)g.N * g.OH * g.OW;
     const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (m >= M) return;
-    const int n = (int)(m / ((long long)g.OH * g.OW));
-    const int r = (int)(m % ((long long)g.OH * g.OW));
-    const int oy = r / g.OW, ox = r % g.OW;
+    const bool live = m < M;
+    if (!live && !a.bn_sums) return;
     float acc[CW];
 #pragma unroll
-    for (int c = 0; c < CW; ++c) acc[c] = a.bias ? a.bias[c] : 0.f;
-    const T* base = in + (long long)n * g.i_sn;
-    for (int t = 0; t < pb.ntaps; ++t) {
-        const Tap tp = pb.taps[t];
-        const int iy = oy + tp.dy, ix = ox + tp.dx;
-        if (iy < 0 || iy >= g.IH || ix < 0 || ix >= g.IW) continue;
-        const T* px = base + tp.in_off + (long long)iy * g.i_sy + (long long)ix * g.i_sx;
-        float xv[CR];
+    for (int c = 0; c < CW; ++c) acc[c] = 0.f;
+    if (live) {
+        const int n = (int)(m / ((long long)g.OH * g.OW));
+        const int r = (int)(m % ((long long)g.OH * g.OW));
+        const int oy = r / g.OW, ox = r % g.OW;
 #pragma unroll
-        for (int k = 0; k < CR; k += 4) {
-            float4 v = ld4(px + k);
-            xv[k] = v.x; xv[k + 1] = v.y; xv[k + 2] = v.z; xv[k + 3] = v.w;
-        }
-        const float* wt = ws + t * CR * CW;
+        for (int c = 0; c < CW; ++c) acc[c] = a.bias ? a.bias[c] : 0.f;
+        const T* base = in + (long long)n * g.i_sn;
+        for (int t = 0; t < pb.ntaps; ++t) {
+            const Tap tp = pb.taps[t];
+            const int iy = oy + tp.dy, ix = ox + tp.dx;
+            if (iy < 0 || iy >= g.IH || ix < 0 || ix >= g.IW) continue;
+            const T* px = base + tp.in_off + (long long)iy * g.i_sy + (long long)ix * g.i_sx;
+            float xv[CR];
 #pragma unroll
-        for (int k = 0; k < CR; ++k)
-#pragma unroll
-            for (int c = 0; c < CW; c += 4) {
-                float4 wv = *reinterpret_cast<const float4*>(wt + k * CW + c);
-                acc[c] = fmaf(xv[k], wv.x, acc[c]); acc[c + 1] = fmaf(xv[k], wv.y, acc[c + 1]);
-                acc[c + 2] = fmaf(xv[k], wv.z, acc[c + 2]); acc[c + 3] = fmaf(xv[k], wv.w, acc[c + 3]);
+            for (int k = 0; k < CR; k += 4) {
+                float4 v = ld4(px + k);
+                xv[k] = v.x; xv[k + 1] = v.y; xv[k + 2] = v.z; xv[k + 3] = v.w;
             }
-    }
-    T* po = out + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx;
+            const float* wt = ws + t * CR * CW;
 #pragma unroll
-    for (int c = 0; c < CW; c += 4)
-        st4(po + c, make_float4(apply_act(acc[c], a.act), apply_act(acc[c + 1], a.act), apply_act(acc[c + 2], a.act),
-                                apply_act(acc[c + 3], a.act)));
+            for (int k = 0; k < CR; ++k)
+#pragma unroll
+                for (int c = 0; c < CW; c += 4) {
+                    float4 wv = *reinterpret_cast<const float4*>(wt + k * CW + c);
+                    acc[c] = fmaf(xv[k], wv.x, acc[c]); acc[c + 1] = fmaf(xv[k], wv.y, acc[c + 1]);
+                    acc[c + 2] = fmaf(xv[k], wv.z, acc[c + 2]); acc[c + 3] = fmaf(xv[k], wv.w, acc[c + 3]);
+                }
+        }
+        TO* po = out + (long long)n * g.o_sn + (long long)oy * g.o_sy + (long long)ox * g.o_sx;
+#pragma unroll
+        for (int c = 0; c < CW; c += 4)
+            st4(po + c, make_float4(apply_act(acc[c], a.act), apply_act(acc[c + 1], a.act), apply_act(acc[c + 2], a.act),
+                                    apply_act(acc[c + 3], a.act)));
+    }
+    if (a.bn_sums) {                     // block-uniform; dead threads of the last block contribute zeros
+#pragma unroll
+        for (int c = 0; c < CW; ++c) {
+            const float s1 = warp_sum(acc[c]), s2 = warp_sum(acc[c] * acc[c]);
+            if (threadIdx.x % 32 == 0) { atomicAdd(&s_bn[c], s1); atomicAdd(&s_bn[CW + c], s2); }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * CW && s_bn[threadIdx.x] != 0.f)
+            atomicAdd(a.bn_sums + (size_t)((blockIdx.x + blockIdx.z) % SVRS_BN_REPLICAS) * 2 * CW + threadIdx.x, (double)s_bn[threadIdx.x]);
+    }
 }
 
-template <typename T>
+template <typename T, typename TO>
 static void launch_pixel(const ConvArgs& a, dim3 grid, cudaStream_t st) {
     const int K = a.g.K, Nc = a.g.Nc;
-    if (K == 4 && Nc == 4) SVRS_LAUNCH((conv_pixel_kernel<T, 4, 4>), grid, 256, 0, st, a);
-    else if (K == 4 && Nc == 16) SVRS_LAUNCH((conv_pixel_kernel<T, 4, 16>), grid, 256, 0, st, a);
-    else if (K == 16 && Nc == 4) SVRS_LAUNCH((conv_pixel_kernel<T, 16, 4>), grid, 256, 0, st, a);
-    else SVRS_LAUNCH((conv_pixel_kernel<T, 16, 16>), grid, 256, 0, st, a);
+    if (K == 4 && Nc == 4) SVRS_LAUNCH((conv_pixel_kernel<T, 4, 4, TO>), grid, 256, 0, st, a);
+    else if (K == 4 && Nc == 16) SVRS_LAUNCH((conv_pixel_kernel<T, 4, 16, TO>), grid, 256, 0, st, a);
+    else if (K == 16 && Nc == 4) SVRS_LAUNCH((conv_pixel_kernel<T, 16, 4, TO>), grid, 256, 0, st, a);
+    else SVRS_LAUNCH((conv_pixel_kernel<T, 16, 16, TO>), grid, 256, 0, st, a);
 }
 
-static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
+static bool pixel_kernel_takes(const TapGeom& g, int dtype) {
+    return (g.K == 4 || g.K == 16) && (g.Nc == 4 || g.Nc == 16) && (g.K == 4 || g.Nc == 4 || dtype == SVRS_F32);
+}
+
+// out_dtype: storage type of the output (== dtype except for the bf16 -> fp32 tail, conv_pixel only)
+static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st, int out_dtype = -1) {
     const TapGeom& g = a.g;
     long long M = (long long)g.N * g.OH * g.OW;
     if (M == 0) return 0;
-    if ((g.K == 4 || g.K == 16) && (g.Nc == 4 || g.Nc == 16) && (g.K == 4 || g.Nc == 4 || dtype == SVRS_F32)) {
+    if (out_dtype < 0) out_dtype = dtype;
+    if (pixel_kernel_takes(g, dtype)) {
         dim3 grid((unsigned)((M + 255) / 256), 1, g.nprob);
-        if (dtype == SVRS_F32) launch_pixel<float>(a, grid, st);
-        else launch_pixel<__nv_bfloat16>(a, grid, st);
+        if (dtype == SVRS_F32 && out_dtype == SVRS_F32) launch_pixel<float, float>(a, grid, st);
+        else if (dtype == SVRS_BF16 && out_dtype == SVRS_BF16) launch_pixel<__nv_bfloat16, __nv_bfloat16>(a, grid, st);
+        else if (dtype == SVRS_BF16 && out_dtype == SVRS_F32) launch_pixel<__nv_bfloat16, float>(a, grid, st);
+        else { set_error("conv: unsupported (dtype, out_dtype) = (%d, %d)", dtype, out_dtype); return SVRS_E_UNSUPPORTED; }
         return check_launch("conv_pixel_kernel");
+    }
+    if (out_dtype != dtype || a.bn_sums) {
+        set_error("conv: fp32 output / fused BatchNorm statistics are not available on the generic SIMT kernel (K=%d Nc=%d)", g.K, g.Nc);
+        return SVRS_E_UNSUPPORTED;
     }
     if (g.Nc <= 16) {
         dim3 grid((unsigned)((M + 255) / 256), (g.Nc + 15) / 16, g.nprob);
@@ -759,7 +793,7 @@ static int launch_colsum(const void* x, int dtype, long long M, int C, float* ou
 namespace svrs {
 bool tc_supported(int dtype, int K, int Nc, int OW, int OH);
 int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
-                   int act, cudaStream_t st);
+                   int act, const ConvExtra& ex, cudaStream_t st);
 bool wgrad_tc_supported(int dtype, int Ca, int Cb, int OW, int OH);
 int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, int KK, float* db, cudaStream_t st);
 bool wgrad_halo_supported(const TapGeom& g, int KK);
@@ -782,18 +816,29 @@ extern "C" int svrs_tc_would_run(int dtype, int K, int Nc, int OH, int OW) {
     return svrs::g_tc_enabled && svrs::tc_supported(dtype, K, Nc, OW, OH) ? 1 : 0;
 }
 
-extern "C" int svrs_conv2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
-                                 int N, int H, int W, int Cin, int Cout, int ksize, int act, void* stream) {
-    SVRS_CHECK_ARG(x && w_kn && y && dtype_ok(dtype), "conv2d_fprop: null pointer or bad dtype");
+extern "C" int svrs_conv2d_fprop_ex(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
+                                    int out_dtype, float* y_nchw, int64_t y_nchw_ld, double* bn_sums,
+                                    int N, int H, int W, int Cin, int Cout, int ksize, int act, void* stream) {
+    SVRS_CHECK_ARG(x && w_kn && (y || y_nchw) && dtype_ok(dtype) && dtype_ok(out_dtype), "conv2d_fprop: null pointer or bad dtype");
     SVRS_CHECK_ARG(ksize == 3 || (ksize == 4 && H % 2 == 0 && W % 2 == 0), "conv2d_fprop: ksize must be 3, or 4 with even H,W");
     SVRS_CHECK_ARG(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv2d_fprop: bad dims");
-    if (N > 0 && use_tc(w_nk, dtype, Cin, Cout, ksize == 3 ? W : W / 2, ksize == 3 ? H : H / 2))
-        return launch_conv_tc(ksize == 3 ? 0 : 2, x, w_nk, bias, y, N, H, W, Cin, Cout, act, (cudaStream_t)stream);
+    if (N > 0 && use_tc(w_nk, dtype, Cin, Cout, ksize == 3 ? W : W / 2, ksize == 3 ? H : H / 2)) {
+        if (out_dtype != dtype) { set_error("conv2d_fprop_ex: the tensor-core kernels store bf16 (use y_nchw for an fp32 copy)"); return SVRS_E_UNSUPPORTED; }
+        ConvExtra ex;
+        ex.out2 = y_nchw; ex.out2_ld = y_nchw_ld; ex.bn_sums = bn_sums;
+        return launch_conv_tc(ksize == 3 ? 0 : 2, x, w_nk, bias, y, N, H, W, Cin, Cout, act, ex, (cudaStream_t)stream);
+    }
+    if (y_nchw || !y) { set_error("conv2d_fprop_ex: the NCHW second output needs the tensor-core kernel (Cin=%d Cout=%d)", Cin, Cout); return SVRS_E_UNSUPPORTED; }
     ConvArgs a;
-    a.in = x; a.out = y; a.w = w_kn; a.bias = bias; a.act = act;
+    a.in = x; a.out = y; a.w = w_kn; a.bias = bias; a.act = act; a.bn_sums = bn_sums;
     if (ksize == 3) geom_conv3(a.g, N, H, W, Cin, Cout, false);
     else geom_conv4s2(a.g, N, H, W, Cin, Cout);
-    return launch_conv(a, dtype, (cudaStream_t)stream);
+    return launch_conv(a, dtype, (cudaStream_t)stream, out_dtype);
+}
+
+extern "C" int svrs_conv2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
+                                 int N, int H, int W, int Cin, int Cout, int ksize, int act, void* stream) {
+    return svrs_conv2d_fprop_ex(x, w_kn, w_nk, bias, y, dtype, dtype, nullptr, 0, nullptr, N, H, W, Cin, Cout, ksize, act, stream);
 }
 
 extern "C" int svrs_conv2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
@@ -801,34 +846,42 @@ extern "C" int svrs_conv2d_dgrad(const void* dy, const void* w_kn, const void* w
     SVRS_CHECK_ARG(dy && w_kn && dx && dtype_ok(dtype), "conv2d_dgrad: null pointer or bad dtype");
     SVRS_CHECK_ARG(ksize == 3 || (ksize == 4 && H % 2 == 0 && W % 2 == 0), "conv2d_dgrad: ksize must be 3, or 4 with even H,W");
     if (N > 0 && ksize == 3 && use_tc(w_nk, dtype, Cout, Cin, W, H))
-        return launch_conv_tc(1, dy, w_nk, nullptr, dx, N, H, W, Cout, Cin, SVRS_ACT_NONE, (cudaStream_t)stream);
+        return launch_conv_tc(1, dy, w_nk, nullptr, dx, N, H, W, Cout, Cin, SVRS_ACT_NONE, ConvExtra(), (cudaStream_t)stream);
     if (N > 0 && ksize == 4 && use_tc(w_nk, dtype, Cout, Cin, W / 2, H / 2))     // per-parity output grid == coarse grid
-        return launch_conv_tc(3, dy, w_nk, nullptr, dx, N, H / 2, W / 2, Cout, Cin, SVRS_ACT_NONE, (cudaStream_t)stream);
+        return launch_conv_tc(3, dy, w_nk, nullptr, dx, N, H / 2, W / 2, Cout, Cin, SVRS_ACT_NONE, ConvExtra(), (cudaStream_t)stream);
     ConvArgs a;
-    a.in = dy; a.out = dx; a.w = w_kn; a.bias = nullptr; a.act = SVRS_ACT_NONE;
+    a.in = dy; a.out = dx; a.w = w_kn; a.bias = nullptr; a.act = SVRS_ACT_NONE; a.bn_sums = nullptr;
     if (ksize == 3) geom_conv3(a.g, N, H, W, Cout, Cin, true);
     else geom_convT4s2(a.g, N, H / 2, W / 2, Cout, Cin);
     return launch_conv(a, dtype, (cudaStream_t)stream);
 }
 
-extern "C" int svrs_convT2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
-                                  int N, int H, int W, int Cin, int Cout, int act, void* stream) {
+extern "C" int svrs_convT2d_fprop_ex(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
+                                     double* bn_sums, int N, int H, int W, int Cin, int Cout, int act, void* stream) {
     SVRS_CHECK_ARG(x && w_kn && y && dtype_ok(dtype), "convT2d_fprop: null pointer or bad dtype");
-    if (N > 0 && use_tc(w_nk, dtype, Cin, Cout, W, H))
-        return launch_conv_tc(3, x, w_nk, bias, y, N, H, W, Cin, Cout, act, (cudaStream_t)stream);
+    if (N > 0 && use_tc(w_nk, dtype, Cin, Cout, W, H)) {
+        ConvExtra ex;
+        ex.bn_sums = bn_sums;
+        return launch_conv_tc(3, x, w_nk, bias, y, N, H, W, Cin, Cout, act, ex, (cudaStream_t)stream);
+    }
     ConvArgs a;
-    a.in = x; a.out = y; a.w = w_kn; a.bias = bias; a.act = act;
+    a.in = x; a.out = y; a.w = w_kn; a.bias = bias; a.act = act; a.bn_sums = bn_sums;
     geom_convT4s2(a.g, N, H, W, Cin, Cout);
     return launch_conv(a, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int svrs_convT2d_fprop(const void* x, const void* w_kn, const void* w_nk, const float* bias, void* y, int dtype,
+                                  int N, int H, int W, int Cin, int Cout, int act, void* stream) {
+    return svrs_convT2d_fprop_ex(x, w_kn, w_nk, bias, y, dtype, nullptr, N, H, W, Cin, Cout, act, stream);
 }
 
 extern "C" int svrs_convT2d_dgrad(const void* dy, const void* w_kn, const void* w_nk, void* dx, int dtype,
                                   int N, int H, int W, int Cin, int Cout, void* stream) {
     SVRS_CHECK_ARG(dy && w_kn && dx && dtype_ok(dtype), "convT2d_dgrad: null pointer or bad dtype");
     if (N > 0 && use_tc(w_nk, dtype, Cout, Cin, W, H))
-        return launch_conv_tc(2, dy, w_nk, nullptr, dx, N, 2 * H, 2 * W, Cout, Cin, SVRS_ACT_NONE, (cudaStream_t)stream);
+        return launch_conv_tc(2, dy, w_nk, nullptr, dx, N, 2 * H, 2 * W, Cout, Cin, SVRS_ACT_NONE, ConvExtra(), (cudaStream_t)stream);
     ConvArgs a;
-    a.in = dy; a.out = dx; a.w = w_kn; a.bias = nullptr; a.act = SVRS_ACT_NONE;
+    a.in = dy; a.out = dx; a.w = w_kn; a.bias = nullptr; a.act = SVRS_ACT_NONE; a.bn_sums = nullptr;
     geom_conv4s2(a.g, N, 2 * H, 2 * W, Cout, Cin);
     return launch_conv(a, dtype, (cudaStream_t)stream);
 }
@@ -879,6 +932,25 @@ extern "C" int svrs_convT2d_wgrad(const void* x, const void* dy, float* dw, floa
     }
     if (db) rc = launch_colsum(dy, dtype, (long long)N * 4 * H * W, Cout, db, (cudaStream_t)stream);
     return rc;
+}
+
+// Which layout the weight-gradient kernels leave in `dw_packed` for this problem: 1 = the tcgen05 kernels take it and
+// accumulate the per-tap packed scratch [tap][d1][d0]; 0 = a SIMT kernel takes it and accumulates torch layout into `dw`.
+// (Same decision tree as svrs_conv2d_wgrad / svrs_convT2d_wgrad; the fused optimiser reads the gradient accordingly.)
+extern "C" int svrs_conv2d_wgrad_layout(int dtype, int N, int H, int W, int Cin, int Cout, int ksize) {
+    if (!(ksize == 3 || (ksize == 4 && H % 2 == 0 && W % 2 == 0)) || N <= 0) return 0;
+    TapGeom g;
+    if (ksize == 3) geom_conv3(g, N, H, W, Cin, Cout, false);
+    else geom_conv4s2(g, N, H, W, Cin, Cout);
+    if (g_tc_enabled && dtype == SVRS_BF16 && wgrad_halo_supported(g, ksize * ksize)) return 1;
+    if (g_tc_enabled && wgrad_tc_supported(dtype, Cout, Cin, g.OW, g.OH)) return 1;
+    return 0;
+}
+extern "C" int svrs_convT2d_wgrad_layout(int dtype, int N, int H, int W, int Cin, int Cout) {
+    if (N <= 0) return 0;
+    TapGeom g;
+    geom_conv4s2(g, N, 2 * H, 2 * W, Cout, Cin);
+    return (g_tc_enabled && wgrad_tc_supported(dtype, Cin, Cout, g.OW, g.OH)) ? 1 : 0;
 }
 
 // Host-only: dump the tap geometry of a conv form so the host logic can be verified without a GPU.

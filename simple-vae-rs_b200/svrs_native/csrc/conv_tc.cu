@@ -57,6 +57,9 @@ struct alignas(64) TcParams {
     int Nc, n_tile, n_tiles, kchunks;
     int cw, tg;          // channel chunk width (16/32/64), (tap,chunk) pairs per pipeline stage (64/cw)
     int act, nprob;
+    float* out2;             // optional fp32 NCHW-flat second output (see EpiRow), per-sample stride out2_ld
+    long long out2_ld;
+    double* bn_sums;         // optional BatchNorm statistics scratch (SVRS_BN_REPLICAS x double[2*Nc])
     TcProb prob[4];
 };
 
@@ -75,6 +78,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    __shared__ float s_bn[2 * EPI_BN_MAXC];
+    if (p.bn_sums) epi_bn_zero(s_bn);
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) prefetch_tmap(&p.in_maps[i]);
@@ -192,12 +197,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-            epi_dispatch(p.act, taddr, p.n_tile, half, orow, p.bias, c_base, p.Nc, n < p.N);
+            EpiRow er;
+            er.o2 = p.out2 ? p.out2 + (long long)n * p.out2_ld + (long long)(ty * p.BH + iy) * p.OW + (tx * p.BW + ix) : nullptr;
+            er.hw = p.OH * p.OW;
+            er.sbn = p.bn_sums ? s_bn : nullptr;
+            epi_dispatch(p.act, taddr, p.n_tile, half, p.out ? orow : nullptr, p.bias, c_base, p.Nc, n < p.N, er);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.bn_sums) epi_bn_flush(s_bn, p.bn_sums, p.Nc, threadIdx.x - 64, 32 * TC_EPI_WARPS);
     }
 
     tc_fence_before();
@@ -275,15 +285,30 @@ static int make_w_map(CUtensorMap* m, const void* base, int K, int Nc, int taps,
     return 0;
 }
 
+// image planes [planes][S][S] of 2- or 4-byte elements (no swizzle): dims (S, S, planes), box (box_w, box_h, box_c)
+int make_plane_map_3d(CUtensorMap* m, const void* base, int elem_bytes, int S, long long planes, int box_w, int box_h, int box_c) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SVRS_E_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)S * elem_bytes, (cuuint64_t)S * S * elem_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base),
+                     dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(planes) failed: %d (S=%d planes=%lld box %dx%dx%d)", (int)r, S, planes, box_w, box_h, box_c); return SVRS_E_CUDA; }
+    return 0;
+}
+
 int make_w_map_pub(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile, int cw) {
     return make_w_map(m, base, K, Nc, taps, n_tile, cw);
 }
 bool halo_supported(int form, int Cr, int Cw, int OW, int OH);
 bool convT_halo_supported(int Cr, int Cw, int W, int H);
 int launch_convT_halo(const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw, int act,
-                      cudaStream_t st);
+                      const ConvExtra& ex, cudaStream_t st);
 int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
-                      int act, cudaStream_t st);
+                      int act, const ConvExtra& ex, cudaStream_t st);
 
 bool pick_box(int OW, int OH, int& BW, int& BH, int& BNI) {
     BW = OW < 128 ? OW : 128;
@@ -304,9 +329,11 @@ bool tc_supported(int dtype, int K, int Nc, int OW, int OH) {
 // form: 0 conv3 fprop, 1 conv3 dgrad, 2 conv4s2 (strided read), 3 convT4s2 (strided write).
 // in: tensor being read [N, H, W, Cr] ; out: tensor written ; w_nk: NK pack [tap][Cw][Cr]
 int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias, void* out, int N, int H, int W, int Cr, int Cw,
-                   int act, cudaStream_t st) {
-    if (halo_supported(form, Cr, Cw, W, H)) return launch_conv3_halo(form, in, w_nk, bias, out, N, H, W, Cr, Cw, act, st);
-    if (form == 3 && convT_halo_supported(Cr, Cw, W, H)) return launch_convT_halo(in, w_nk, bias, out, N, H, W, Cr, Cw, act, st);
+                   int act, const ConvExtra& ex, cudaStream_t st) {
+    if (ex.bn_sums && Cw > EPI_BN_MAXC) { set_error("conv_tc: fused BatchNorm statistics need Cout <= %d", EPI_BN_MAXC); return SVRS_E_UNSUPPORTED; }
+    if (ex.out2 && form == 3) { set_error("conv_tc: NCHW second output is not available for the transposed form"); return SVRS_E_UNSUPPORTED; }
+    if (halo_supported(form, Cr, Cw, W, H)) return launch_conv3_halo(form, in, w_nk, bias, out, N, H, W, Cr, Cw, act, ex, st);
+    if (form == 3 && convT_halo_supported(Cr, Cw, W, H)) return launch_convT_halo(in, w_nk, bias, out, N, H, W, Cr, Cw, act, ex, st);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
@@ -325,6 +352,7 @@ int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias
     if (!pick_box(g.OW, g.OH, p.BW, p.BH, p.BNI)) { set_error("conv_tc: unsupported spatial dims %dx%d", g.OW, g.OH); return SVRS_E_UNSUPPORTED; }
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.bias = bias;
+    p.out2 = ex.out2; p.out2_ld = ex.out2_ld; p.bn_sums = ex.bn_sums;
     p.o_sn = g.o_sn; p.o_sy = g.o_sy; p.o_sx = g.o_sx;
     p.N = N; p.OH = g.OH; p.OW = g.OW;
     p.tiles_x = g.OW / p.BW; p.tiles_y = g.OH / p.BH; p.tiles_n = (N + p.BNI - 1) / p.BNI;

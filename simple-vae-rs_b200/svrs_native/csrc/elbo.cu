@@ -104,18 +104,32 @@ __global__ void philox_normal_kernel(float* __restrict__ out, int B, int Wd, uin
 }
 
 // ---------------------------------------------------------------- ELBO forward reductions
-template <typename T>
-__device__ __forceinline__ float ssq_segment(const T* __restrict__ r, const T* __restrict__ t, long long n,
+// dtype-generic vector access (the branch is uniform; these kernels are HBM-bound)
+__device__ __forceinline__ float4 ld4_dt(const void* p, int dt, long long i4) {
+    return dt == SVRS_F32 ? ld4(reinterpret_cast<const float*>(p) + i4 * 4) : ld4(reinterpret_cast<const __nv_bfloat16*>(p) + i4 * 4);
+}
+__device__ __forceinline__ float ld1_dt(const void* p, int dt, long long i) {
+    return dt == SVRS_F32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st4_dt(void* p, int dt, long long i4, float4 v) {
+    if (dt == SVRS_F32) st4(reinterpret_cast<float*>(p) + i4 * 4, v); else st4(reinterpret_cast<__nv_bfloat16*>(p) + i4 * 4, v);
+}
+__device__ __forceinline__ void st1_dt(void* p, int dt, long long i, float v) {
+    if (dt == SVRS_F32) reinterpret_cast<float*>(p)[i] = v; else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// recon (dtype dtr) and target (dtype dtt) share a layout; each is read once
+__device__ __forceinline__ float ssq_segment(const void* __restrict__ r, int dtr, const void* __restrict__ t, int dtt, long long n,
                                              long long gtid, long long gsize) {
     float s = 0.f;
     long long nvec = n / 4;
     for (long long i = gtid; i < nvec; i += gsize) {
-        float4 a = ld4(r + i * 4), b = ld4(t + i * 4);
+        float4 a = ld4_dt(r, dtr, i), b = ld4_dt(t, dtt, i);
         float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
         s += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
     }
     for (long long i = nvec * 4 + gtid; i < n; i += gsize) {
-        float d = Cvt<T>::to_f(r[i]) - Cvt<T>::to_f(t[i]);
+        float d = ld1_dt(r, dtr, i) - ld1_dt(t, dtt, i);
         s += d * d;
     }
     return s;
@@ -123,7 +137,8 @@ __device__ __forceinline__ float ssq_segment(const T* __restrict__ r, const T* _
 
 struct ElboArgs {
     const void *rx, *x, *ry, *y;
-    int dtx, dty;
+    int dtx, dty;      // dtype of recon_x / recon_y
+    int dttx, dtty;    // dtype of the targets x / y
     long long nx, ny;
     const float *mu1, *lv1, *mu2, *lv2, *mu3, *lv3;
     long long ld1, ld2, ld3;
@@ -136,12 +151,10 @@ __global__ void __launch_bounds__(256) elbo_fwd_kernel(const __grid_constant__ E
     const long long gsize = (long long)gridDim.x * blockDim.x;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     if (a.nx > 0) {
-        s[0] = a.dtx == SVRS_F32 ? ssq_segment((const float*)a.rx, (const float*)a.x, a.nx, gtid, gsize)
-                                 : ssq_segment((const __nv_bfloat16*)a.rx, (const __nv_bfloat16*)a.x, a.nx, gtid, gsize);
+        s[0] = ssq_segment(a.rx, a.dtx, a.x, a.dttx, a.nx, gtid, gsize);
     }
     if (a.ny > 0) {
-        s[1] = a.dty == SVRS_F32 ? ssq_segment((const float*)a.ry, (const float*)a.y, a.ny, gtid, gsize)
-                                 : ssq_segment((const __nv_bfloat16*)a.ry, (const __nv_bfloat16*)a.y, a.ny, gtid, gsize);
+        s[1] = ssq_segment(a.ry, a.dty, a.y, a.dtty, a.ny, gtid, gsize);
     }
     if (a.mu1) {
         const int wq = a.W1 / 4;
@@ -204,6 +217,8 @@ __global__ void elbo_finalize_kernel(const double* __restrict__ acc, long long n
 struct ElboBwdArgs {
     ElboArgs f;
     void *drx, *dry;
+    int dtdx, dtdy;    // dtype of d_recon_x / d_recon_y
+    int act;           // SVRS_ACT_SIGMOID: recon = sigmoid(pre) and d_recon_* receives the gradient wrt `pre`
     float *dmu1, *dlv1, *dmu2, *dlv2, *dmu3, *dlv3;
     long long dld1, dld2, dld3;
     const double* acc;
@@ -212,16 +227,21 @@ struct ElboBwdArgs {
     float* dgammas;
 };
 
-template <typename T>
-__device__ __forceinline__ void nll_bwd_segment(const T* __restrict__ r, const T* __restrict__ t, T* __restrict__ dr,
-                                                long long n, float coef, long long gtid, long long gsize) {
+__device__ __forceinline__ float nll_d(float r, float t, float coef, int act) {
+    float g = (r - t) * coef;
+    if (act == SVRS_ACT_SIGMOID) g = g * r * (1.f - r);      // chain through the decoder's final nn.Sigmoid (cond_vae.py:80,143)
+    return g;
+}
+__device__ __forceinline__ void nll_bwd_segment(const void* __restrict__ r, int dtr, const void* __restrict__ t, int dtt,
+                                                void* __restrict__ dr, int dtd, long long n, float coef, int act,
+                                                long long gtid, long long gsize) {
     long long nvec = n / 4;
     for (long long i = gtid; i < nvec; i += gsize) {
-        float4 a = ld4(r + i * 4), b = ld4(t + i * 4);
-        st4(dr + i * 4, make_float4((a.x - b.x) * coef, (a.y - b.y) * coef, (a.z - b.z) * coef, (a.w - b.w) * coef));
+        float4 a = ld4_dt(r, dtr, i), b = ld4_dt(t, dtt, i);
+        st4_dt(dr, dtd, i, make_float4(nll_d(a.x, b.x, coef, act), nll_d(a.y, b.y, coef, act), nll_d(a.z, b.z, coef, act), nll_d(a.w, b.w, coef, act)));
     }
     for (long long i = nvec * 4 + gtid; i < n; i += gsize)
-        dr[i] = Cvt<T>::from_f((Cvt<T>::to_f(r[i]) - Cvt<T>::to_f(t[i])) * coef);
+        st1_dt(dr, dtd, i, nll_d(ld1_dt(r, dtr, i), ld1_dt(t, dtt, i), coef, act));
 }
 
 __global__ void __launch_bounds__(256) elbo_bwd_kernel(const __grid_constant__ ElboBwdArgs a) {
@@ -238,13 +258,11 @@ __global__ void __launch_bounds__(256) elbo_bwd_kernel(const __grid_constant__ E
     }
     if (f.nx > 0 && a.drx) {
         float c = g_msex / (gx * gx);
-        if (f.dtx == SVRS_F32) nll_bwd_segment((const float*)f.rx, (const float*)f.x, (float*)a.drx, f.nx, c, gtid, gsize);
-        else nll_bwd_segment((const __nv_bfloat16*)f.rx, (const __nv_bfloat16*)f.x, (__nv_bfloat16*)a.drx, f.nx, c, gtid, gsize);
+        nll_bwd_segment(f.rx, f.dtx, f.x, f.dttx, a.drx, a.dtdx, f.nx, c, a.act, gtid, gsize);
     }
     if (f.ny > 0 && a.dry) {
         float c = g_msey / (gy * gy);
-        if (f.dty == SVRS_F32) nll_bwd_segment((const float*)f.ry, (const float*)f.y, (float*)a.dry, f.ny, c, gtid, gsize);
-        else nll_bwd_segment((const __nv_bfloat16*)f.ry, (const __nv_bfloat16*)f.y, (__nv_bfloat16*)a.dry, f.ny, c, gtid, gsize);
+        nll_bwd_segment(f.ry, f.dty, f.y, f.dtty, a.dry, a.dtdy, f.ny, c, a.act, gtid, gsize);
     }
     const float invB = 1.0f / (float)f.B;
     if (f.mu1 && a.dmu1 && a.dlv1) {
@@ -329,34 +347,35 @@ extern "C" int svrs_philox_normal(float* out, int B, int Wd, uint64_t seed, uint
     return check_launch("philox_normal");
 }
 
-static int fill_elbo_args(ElboArgs& a, const void* recon_x, const void* x, int dt_x, int64_t n_x,
-                          const void* recon_y, const void* y, int dt_y, int64_t n_y,
+static int fill_elbo_args(ElboArgs& a, const void* recon_x, const void* x, int dt_x, int dt_tx, int64_t n_x,
+                          const void* recon_y, const void* y, int dt_y, int dt_ty, int64_t n_y,
                           const float* mu1, const float* lv1, int64_t ld1, int W1,
                           const float* mu2, const float* lv2, int64_t ld2,
                           const float* mu3, const float* lv3, int64_t ld3, int W2, int B) {
     SVRS_CHECK_ARG(B > 0, "elbo: B must be > 0");
     SVRS_CHECK_ARG(n_x == 0 || (recon_x && x), "elbo: recon_x/x null");
     SVRS_CHECK_ARG(n_y == 0 || (recon_y && y), "elbo: recon_y/y null");
-    SVRS_CHECK_ARG((dt_x == SVRS_F32 || dt_x == SVRS_BF16) && (dt_y == SVRS_F32 || dt_y == SVRS_BF16), "elbo: bad dtype");
+    SVRS_CHECK_ARG((dt_x == SVRS_F32 || dt_x == SVRS_BF16) && (dt_y == SVRS_F32 || dt_y == SVRS_BF16) &&
+                   (dt_tx == SVRS_F32 || dt_tx == SVRS_BF16) && (dt_ty == SVRS_F32 || dt_ty == SVRS_BF16), "elbo: bad dtype");
     SVRS_CHECK_ARG(al16(recon_x) && al16(x) && al16(recon_y) && al16(y), "elbo: image pointers must be 16B aligned");
     if (mu1) SVRS_CHECK_ARG(lv1 && W1 % 4 == 0 && ld1 % 4 == 0 && al16(mu1) && al16(lv1), "elbo: kl1 needs W1,ld1 %% 4 == 0 and 16B alignment");
     if (mu2) SVRS_CHECK_ARG(lv2 && mu3 && lv3 && W2 % 4 == 0 && ld2 % 4 == 0 && ld3 % 4 == 0 && al16(mu2) && al16(lv2) && al16(mu3) && al16(lv3),
                             "elbo: kl23 needs W2,ld2,ld3 %% 4 == 0 and 16B alignment");
-    a.rx = recon_x; a.x = x; a.ry = recon_y; a.y = y; a.dtx = dt_x; a.dty = dt_y; a.nx = n_x; a.ny = n_y;
+    a.rx = recon_x; a.x = x; a.ry = recon_y; a.y = y; a.dtx = dt_x; a.dty = dt_y; a.dttx = dt_tx; a.dtty = dt_ty; a.nx = n_x; a.ny = n_y;
     a.mu1 = mu1; a.lv1 = lv1; a.mu2 = mu2; a.lv2 = lv2; a.mu3 = mu3; a.lv3 = lv3;
     a.ld1 = ld1; a.ld2 = ld2; a.ld3 = ld3; a.W1 = W1; a.W2 = W2; a.B = B;
     return 0;
 }
 
-extern "C" int svrs_elbo_fwd(const void* recon_x, const void* x, int dt_x, int64_t n_x,
-                             const void* recon_y, const void* y, int dt_y, int64_t n_y,
+extern "C" int svrs_elbo_fwd(const void* recon_x, const void* x, int dt_x, int dt_tx, int64_t n_x,
+                             const void* recon_y, const void* y, int dt_y, int dt_ty, int64_t n_y,
                              const float* mu1, const float* lv1, int64_t ld1, int W1,
                              const float* mu2, const float* lv2, int64_t ld2,
                              const float* mu3, const float* lv3, int64_t ld3, int W2,
                              int B, double* acc, void* stream) {
     SVRS_CHECK_ARG(acc, "elbo_fwd: acc null");
     ElboArgs a;
-    int rc = fill_elbo_args(a, recon_x, x, dt_x, n_x, recon_y, y, dt_y, n_y, mu1, lv1, ld1, W1, mu2, lv2, ld2, mu3, lv3, ld3, W2, B);
+    int rc = fill_elbo_args(a, recon_x, x, dt_x, dt_tx, n_x, recon_y, y, dt_y, dt_ty, n_y, mu1, lv1, ld1, W1, mu2, lv2, ld2, mu3, lv3, ld3, W2, B);
     if (rc) return rc;
     long long work = (n_x > n_y ? n_x : n_y) / 4;
     long long w2 = (long long)B * (W2 > W1 ? W2 : W1) / 4;
@@ -372,21 +391,23 @@ extern "C" int svrs_elbo_finalize(const double* acc, int64_t n_x, int64_t n_y, i
     return check_launch("elbo_finalize");
 }
 
-extern "C" int svrs_elbo_bwd(const void* recon_x, const void* x, int dt_x, int64_t n_x, void* d_recon_x,
-                             const void* recon_y, const void* y, int dt_y, int64_t n_y, void* d_recon_y,
+extern "C" int svrs_elbo_bwd(const void* recon_x, const void* x, int dt_x, int dt_tx, int64_t n_x, void* d_recon_x, int dt_dx,
+                             const void* recon_y, const void* y, int dt_y, int dt_ty, int64_t n_y, void* d_recon_y, int dt_dy,
                              const float* mu1, const float* lv1, int64_t ld1, int W1, float* d_mu1, float* d_lv1, int64_t dld1,
                              const float* mu2, const float* lv2, int64_t ld2, float* d_mu2, float* d_lv2, int64_t dld2,
                              const float* mu3, const float* lv3, int64_t ld3, int W2, float* d_mu3, float* d_lv3, int64_t dld3,
                              int B, const double* acc, const float* gammas, const float* gout, float* d_gammas,
-                             void* stream) {
+                             int act, void* stream) {
     SVRS_CHECK_ARG(acc && gammas && gout, "elbo_bwd: acc/gammas/gout null");
+    SVRS_CHECK_ARG((dt_dx == SVRS_F32 || dt_dx == SVRS_BF16) && (dt_dy == SVRS_F32 || dt_dy == SVRS_BF16) &&
+                   (act == SVRS_ACT_NONE || act == SVRS_ACT_SIGMOID), "elbo_bwd: bad gradient dtype / act");
     ElboBwdArgs a;
-    int rc = fill_elbo_args(a.f, recon_x, x, dt_x, n_x, recon_y, y, dt_y, n_y, mu1, lv1, ld1, W1, mu2, lv2, ld2, mu3, lv3, ld3, W2, B);
+    int rc = fill_elbo_args(a.f, recon_x, x, dt_x, dt_tx, n_x, recon_y, y, dt_y, dt_ty, n_y, mu1, lv1, ld1, W1, mu2, lv2, ld2, mu3, lv3, ld3, W2, B);
     if (rc) return rc;
     SVRS_CHECK_ARG(al16(d_recon_x) && al16(d_recon_y) && al16(d_mu1) && al16(d_lv1) && al16(d_mu2) && al16(d_lv2) && al16(d_mu3) && al16(d_lv3),
                    "elbo_bwd: gradient pointers must be 16B aligned");
     SVRS_CHECK_ARG(dld1 % 4 == 0 && dld2 % 4 == 0 && dld3 % 4 == 0, "elbo_bwd: gradient strides %% 4");
-    a.drx = d_recon_x; a.dry = d_recon_y;
+    a.drx = d_recon_x; a.dry = d_recon_y; a.dtdx = dt_dx; a.dtdy = dt_dy; a.act = act;
     a.dmu1 = d_mu1; a.dlv1 = d_lv1; a.dmu2 = d_mu2; a.dlv2 = d_lv2; a.dmu3 = d_mu3; a.dlv3 = d_lv3;
     a.dld1 = dld1; a.dld2 = dld2; a.dld3 = dld3;
     a.acc = acc; a.gammas = gammas; a.gout = gout; a.dgammas = d_gammas;

@@ -62,6 +62,127 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// adam_multi_kernel: the whole optimiser tail of the fused step in ONE launch over a device job table.
+//   * conv-weight jobs (d1 > 0): a CTA owns a 32 (d0) x 16 (d1) x kk tile of one layer.  The gradient is read in the layout
+//     the weight-gradient kernel left it in - torch [d0][d1][kk] (SIMT kernels) or the per-tap packed scratch
+//     [kk][d1][d0] (tcgen05 kernels' TMA-reduce epilogue) - transposed through shared memory, Adam runs on the torch-layout
+//     master weight / moments (coalesced runs of 16*kk floats), and the updated weight goes back through shared memory
+//     into BOTH compute-dtype packs [kk][d0][d1] and [kk][d1][d0] that the next step's fprop / dgrad kernels consume.
+//     This replaces unpack_multi + clip_adam + pack_multi (three passes over 82 MB each) by one.
+//   * plain jobs (d1 == 0): biases and BatchNorm affine parameters, d0 contiguous elements from `off`.
+// p / g / m / v are the flat buffers; a job addresses all four at the same element offset.
+// ------------------------------------------------------------------------------------------------------------------
+struct AdamJob {
+    long long off;      // element offset of the parameter in the flat buffers
+    void* p01;          // pack [kk][d0][d1] or NULL
+    void* p10;          // pack [kk][d1][d0] or NULL
+    int d0, d1, kk;
+    int layout;         // gradient layout: 0 torch [d0][d1][kk], 1 packed [kk][d1][d0]
+    int tile0;          // first global tile of this job
+    int tiles_b;        // tiles along d1 (conv jobs)
+};
+constexpr int AD_TA = 32, AD_TB = 16, AD_PLAIN = 2048, AD_MAX_JOBS = 512;
+
+__device__ __forceinline__ void split_kk_(int i, int kk, int& b, int& t) {
+    if (kk == 16) { b = i >> 4; t = i & 15; }
+    else if (kk == 9) { b = i / 9; t = i - 9 * b; }
+    else { b = i / kk; t = i - kk * b; }
+}
+
+template <typename TD>
+__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restrict__ jobs, int njobs,
+                                                          float* __restrict__ p, const float* __restrict__ g,
+                                                          float* __restrict__ m, float* __restrict__ v,
+                                                          const double* __restrict__ sumsq, float max_norm, float grad_scale,
+                                                          float lr, float b1, float b2, float eps,
+                                                          const long long* __restrict__ step_ptr) {
+    pdl_entry();
+    extern __shared__ float tile[];
+    __shared__ int s_tile0[AD_MAX_JOBS];
+    __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+    for (int i = threadIdx.x; i < njobs; i += blockDim.x) s_tile0[i] = jobs[i].tile0;
+    if (threadIdx.x == 0) {
+        float coef = grad_scale;
+        if (sumsq) {
+            float total = (float)sqrt(*sumsq) * grad_scale;
+            float c = max_norm / (total + 1e-6f);
+            coef = grad_scale * fminf(c, 1.0f);
+        }
+        double t = (double)(*step_ptr);
+        double bc1 = 1.0 - pow((double)b1, t);
+        double bc2 = 1.0 - pow((double)b2, t);
+        s_coef = coef;
+        s_step_size = (float)((double)lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_tile0[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const AdamJob jb = jobs[lo];
+    const int lt = blockIdx.x - jb.tile0;
+    const float coef = s_coef, step_size = s_step_size, bc2s = s_bc2_sqrt;
+    auto adam = [&](long long i, float gi) -> float {
+        gi *= coef;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float pn = p[i] - step_size * (mi / (sqrtf(vi) / bc2s + eps));
+        p[i] = pn;
+        return pn;
+    };
+    if (jb.d1 == 0) {                                   // plain range
+        const long long i0 = jb.off + (long long)lt * AD_PLAIN;
+        const long long i1 = jb.off + jb.d0 < i0 + AD_PLAIN ? jb.off + jb.d0 : i0 + AD_PLAIN;
+        for (long long i = i0 + threadIdx.x; i < i1; i += 256) adam(i, g[i]);
+        return;
+    }
+    const int a0 = (lt / jb.tiles_b) * AD_TA, b0 = (lt % jb.tiles_b) * AD_TB;
+    const int kk = jb.kk, d0 = jb.d0, d1 = jb.d1;
+    const int na = d0 - a0 < AD_TA ? d0 - a0 : AD_TA, nb = d1 - b0 < AD_TB ? d1 - b0 : AD_TB;
+    const int ROW = AD_TB * (kk + 1) + 1;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const float* gj = g + jb.off;
+    if (jb.layout == 1) {                               // packed [kk][d1][d0]: warps read 32 consecutive d0
+        if (lane < na)
+            for (int t = 0; t < kk; ++t)
+                for (int b = warp; b < nb; b += 8)
+                    tile[lane * ROW + b * (kk + 1) + t] = gj[((long long)t * d1 + b0 + b) * d0 + a0 + lane];
+        __syncthreads();
+    }
+    const int run = nb * kk;
+    for (int a = warp; a < na; a += 8) {                // torch layout: contiguous runs of nb*kk floats
+        const long long base = jb.off + ((long long)(a0 + a) * d1 + b0) * kk;
+        for (int i = lane; i < run; i += 32) {
+            int b, t;
+            split_kk_(i, kk, b, t);
+            float* slot = &tile[a * ROW + b * (kk + 1) + t];
+            const float gi = jb.layout == 1 ? *slot : g[base + i];
+            *slot = adam(base + i, gi);
+        }
+    }
+    __syncthreads();
+    TD* p01 = reinterpret_cast<TD*>(jb.p01);
+    TD* p10 = reinterpret_cast<TD*>(jb.p10);
+    if (p01) {                                          // [t][a][b]: half-warps write 16 consecutive b
+        const int tx = threadIdx.x % AD_TB, ty = threadIdx.x / AD_TB;
+        if (tx < nb)
+            for (int t = 0; t < kk; ++t)
+                for (int a = ty; a < na; a += 256 / AD_TB)
+                    p01[((long long)t * d0 + a0 + a) * d1 + b0 + tx] = Cvt<TD>::from_f(tile[a * ROW + tx * (kk + 1) + t]);
+    }
+    if (p10) {                                          // [t][b][a]: warps write 32 consecutive a
+        if (lane < na)
+            for (int t = 0; t < kk; ++t)
+                for (int b = warp; b < nb; b += 8)
+                    p10[((long long)t * d1 + b0 + b) * d0 + a0 + lane] = Cvt<TD>::from_f(tile[lane * ROW + b * (kk + 1) + t]);
+    }
+}
+
 __global__ void step_increment_kernel(long long* s) {
     pdl_entry(); *s += 1; }
 
@@ -95,4 +216,21 @@ extern "C" int svrs_step_increment(int64_t* step_ptr, void* stream) {
     SVRS_CHECK_ARG(step_ptr, "step_increment: null");
     SVRS_LAUNCH((step_increment_kernel), 1, 1, 0, (cudaStream_t)stream, (long long*)step_ptr);
     return check_launch("step_increment");
+}
+
+extern "C" int svrs_adam_job_bytes(void) { return (int)sizeof(svrs::AdamJob); }
+
+extern "C" int svrs_adam_multi(const void* jobs, int njobs, int total_tiles, int max_kk, float* p, const float* g, float* m, float* v,
+                               int pack_dtype, const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
+                               float beta2, float eps, const int64_t* step_ptr, void* stream) {
+    SVRS_CHECK_ARG(jobs && njobs > 0 && njobs <= svrs::AD_MAX_JOBS && total_tiles > 0 && max_kk > 0 && max_kk <= 16 && p && g && m && v && step_ptr,
+                   "adam_multi: bad args (at most %d jobs)", svrs::AD_MAX_JOBS);
+    size_t smem = (size_t)svrs::AD_TA * (svrs::AD_TB * (max_kk + 1) + 1) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pack_dtype == SVRS_F32)
+        SVRS_LAUNCH((adam_multi_kernel<float>), total_tiles, 256, smem, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr);
+    else if (pack_dtype == SVRS_BF16)
+        SVRS_LAUNCH((adam_multi_kernel<__nv_bfloat16>), total_tiles, 256, smem, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr);
+    else { set_error("adam_multi: bad pack dtype"); return SVRS_E_ARG; }
+    return check_launch("adam_multi");
 }

@@ -1,7 +1,18 @@
-// patch.cu - grid-mode patching of S x S tiles into P x P patches + per-patch per-channel min-max
-// normalisation (dataset.py:220-247,265-274; utils.py:4-23).  One CTA per patch; bit-exact fp32 arithmetic:
+// patch.cu - patch gather (grid mode or given crop origins) from S x S tiles + per-patch per-channel min-max
+// normalisation (dataset.py:205-247,265-274; utils.py:4-23).  Bit-exact fp32 arithmetic:
 // (x - min) / ((max - min) + 1e-5f), IEEE division.
+//
+// patch_tma_kernel: one CTA per patch.  The patch (all C channels) is fetched by ONE 3-D TMA box
+// (P columns x R rows x C channel planes of the tile tensor viewed as [T*C][S][S]) into shared memory, min/max are taken
+// from shared memory (the tile is read from HBM once), and up to three layouts are emitted from the same staged data:
+// NCHW fp32 (the reference's API layout), NHWC fp32 (NLL target of the fused step) and NHWC bf16 (operand of the first
+// conv layer).  Patches too large for shared memory (P = 256) are streamed as strips of R rows twice (the second
+// pass hits L2).  Crop origins: grid mode (index = tile * (S/P)^2 + row * (S/P) + col) or an explicit device array of
+// (tile, top, left) - the reference's random crop (dataset.py:205-216) with the draws made by the caller.
 #include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cuda.h>
+#include <string.h>
 
 namespace svrs {
 
@@ -10,6 +21,7 @@ constexpr int MAXC = 16;
 template <typename TS>
 __device__ __forceinline__ float load_src(const TS* p) { return (float)(*p); }
 
+// ---- fallback (no TMA constraints): one CTA per patch, plain loads, the tile region is read twice ----------------
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) grid_patch_kernel(const TS* __restrict__ tiles, TD* __restrict__ dst, int nhwc,
                                                           int C, int S, int P) {
@@ -60,16 +72,180 @@ __global__ void __launch_bounds__(256) grid_patch_kernel(const TS* __restrict__ 
     }
 }
 
+// ---- TMA gather ---------------------------------------------------------------------------------------------------
+struct alignas(64) PatchParams {
+    CUtensorMap map;            // tiles as (S, S, T*C), box (P, R, C)
+    const int* origins;         // [npatch][3] = (tile, top, left) or NULL (grid mode)
+    float* out_nchw;            // [npatch][C][P][P] or NULL
+    float* out_nhwc;            // [npatch][P][P][C] or NULL
+    __nv_bfloat16* out_nhwc_bf16;
+    int C, S, P, R, nstrips, per_side;
+};
+
+template <typename TS>
+__global__ void __launch_bounds__(256) patch_tma_kernel(const __grid_constant__ PatchParams p) {
+    pdl_entry();
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ float s_mn[MAXC], s_mx[MAXC];
+    __shared__ float red_mn[8], red_mx[8];
+    __shared__ __align__(8) uint64_t bar_storage;
+    const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+    const TS* sdata = reinterpret_cast<const TS*>(smem_raw + (sbase - smem_u32(smem_raw)));
+    const uint32_t bar = smem_u32(&bar_storage);
+    const int C = p.C, P = p.P, R = p.R;
+    const int pidx = blockIdx.x;
+    int tile, top, left;
+    if (p.origins) {
+        tile = p.origins[3 * pidx]; top = p.origins[3 * pidx + 1]; left = p.origins[3 * pidx + 2];
+    } else {
+        const int per_tile = p.per_side * p.per_side;
+        tile = pidx / per_tile;
+        const int q = pidx % per_tile;
+        top = (q / p.per_side) * P; left = (q % p.per_side) * P;
+    }
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&p.map);
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < MAXC) { s_mn[threadIdx.x] = INFINITY; s_mx[threadIdx.x] = -INFINITY; }
+    __syncthreads();
+    const uint32_t strip_bytes = (uint32_t)C * R * P * sizeof(TS);
+    const int strip_pix = R * P;
+    uint32_t phase = 0;
+    auto load_strip = [&](int s) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, strip_bytes);
+            tma_load_3d(sbase, &p.map, bar, left, top + s * R, tile * C);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+    };
+    // ---- pass 1: per-channel min / max
+    for (int s = 0; s < p.nstrips; ++s) {
+        if (s > 0) __syncthreads();            // every thread is done reading the previous strip
+        load_strip(s);
+        for (int c = 0; c < C; ++c) {
+            float mn = INFINITY, mx = -INFINITY;
+            const TS* cb = sdata + (size_t)c * strip_pix;
+            for (int i = threadIdx.x; i < strip_pix; i += 256) {
+                const float v = (float)cb[i];
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (threadIdx.x % 32 == 0) { red_mn[threadIdx.x / 32] = mn; red_mx[threadIdx.x / 32] = mx; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < 8; ++w) { mn = fminf(mn, red_mn[w]); mx = fmaxf(mx, red_mx[w]); }
+                s_mn[c] = fminf(s_mn[c], mn);
+                s_mx[c] = fmaxf(s_mx[c], mx);
+            }
+            __syncthreads();
+        }
+    }
+    // ---- pass 2: normalise + emit (single-strip patches are still resident in shared memory)
+    const long long npix = (long long)P * P;
+    for (int s = 0; s < p.nstrips; ++s) {
+        if (p.nstrips > 1) { __syncthreads(); load_strip(s); }
+        const long long pix0 = (long long)s * strip_pix;       // first pixel (row-major in the patch) of this strip
+        if (C == 4) {
+            const float mn0 = s_mn[0], mn1 = s_mn[1], mn2 = s_mn[2], mn3 = s_mn[3];
+            const float d0 = (s_mx[0] - mn0) + 1e-5f, d1 = (s_mx[1] - mn1) + 1e-5f, d2 = (s_mx[2] - mn2) + 1e-5f, d3 = (s_mx[3] - mn3) + 1e-5f;
+            for (int i = threadIdx.x; i < strip_pix; i += 256) {
+                float4 o;
+                o.x = __fdiv_rn((float)sdata[i] - mn0, d0);
+                o.y = __fdiv_rn((float)sdata[strip_pix + i] - mn1, d1);
+                o.z = __fdiv_rn((float)sdata[2 * strip_pix + i] - mn2, d2);
+                o.w = __fdiv_rn((float)sdata[3 * strip_pix + i] - mn3, d3);
+                const long long px = pix0 + i;
+                if (p.out_nchw) {
+                    float* q = p.out_nchw + (long long)pidx * 4 * npix + px;
+                    q[0] = o.x; q[npix] = o.y; q[2 * npix] = o.z; q[3 * npix] = o.w;
+                }
+                if (p.out_nhwc) st4(p.out_nhwc + ((long long)pidx * npix + px) * 4, o);
+                if (p.out_nhwc_bf16) st4(p.out_nhwc_bf16 + ((long long)pidx * npix + px) * 4, o);
+            }
+        } else {
+            for (int c = 0; c < C; ++c) {
+                const float mn = s_mn[c], den = (s_mx[c] - mn) + 1e-5f;
+                const TS* cb = sdata + (size_t)c * strip_pix;
+                for (int i = threadIdx.x; i < strip_pix; i += 256) {
+                    const float o = __fdiv_rn((float)cb[i] - mn, den);
+                    const long long px = pix0 + i;
+                    if (p.out_nchw) p.out_nchw[((long long)pidx * C + c) * npix + px] = o;
+                    if (p.out_nhwc) p.out_nhwc[((long long)pidx * npix + px) * C + c] = o;
+                    if (p.out_nhwc_bf16) p.out_nhwc_bf16[((long long)pidx * npix + px) * C + c] = __float2bfloat16_rn(o);
+                }
+            }
+        }
+    }
+}
+
+int make_plane_map_3d(CUtensorMap* m, const void* base, int elem_bytes, int S, long long planes, int box_w, int box_h, int box_c);
+
+static bool tma_patch_ok(int es, int C, int S, int P) {
+    return (S * es) % 16 == 0 && (P * es) % 16 == 0 && P <= 256 && C <= MAXC && P >= 8;
+}
+
 }  // namespace svrs
 
 using namespace svrs;
+
+extern "C" int svrs_patch_gather_normalize(const void* tiles, int src_is_i16, int T, int C, int S, int P,
+                                           const int32_t* origins, int npatch, float* out_nchw_f32, float* out_nhwc_f32,
+                                           void* out_nhwc_bf16, void* stream) {
+    SVRS_CHECK_ARG(tiles && T >= 0 && C > 0 && C <= MAXC && S > 0 && P > 0 && P <= S && npatch >= 0,
+                   "patch_gather_normalize: bad args (C <= 16, P <= S)");
+    SVRS_CHECK_ARG(origins || (S % P == 0 && npatch == T * (S / P) * (S / P)), "patch_gather_normalize: grid mode needs S %% P == 0 and npatch == T*(S/P)^2");
+    SVRS_CHECK_ARG(out_nchw_f32 || out_nhwc_f32 || out_nhwc_bf16, "patch_gather_normalize: no output");
+    const int es = src_is_i16 ? 2 : 4;
+    SVRS_CHECK_ARG(tma_patch_ok(es, C, S, P) && ((uintptr_t)tiles & 15) == 0,
+                   "patch_gather_normalize: needs 16-byte aligned tiles, S*elem and P*elem multiples of 16 bytes, 8 <= P <= 256 (S=%d P=%d)", S, P);
+    if (npatch == 0 || T == 0) return 0;
+    PatchParams p;
+    memset(&p, 0, sizeof(p));
+    // strip height: the largest power of two dividing P whose C planes fit in 96 KB
+    int R = P;
+    while ((long long)C * R * P * es > 96 * 1024 && R % 2 == 0) R /= 2;
+    SVRS_CHECK_ARG((long long)C * R * P * es <= 96 * 1024 && P % R == 0 && R <= 256, "patch_gather_normalize: patch does not tile into strips");
+    p.origins = origins;
+    p.out_nchw = out_nchw_f32; p.out_nhwc = out_nhwc_f32; p.out_nhwc_bf16 = reinterpret_cast<__nv_bfloat16*>(out_nhwc_bf16);
+    p.C = C; p.S = S; p.P = P; p.R = R; p.nstrips = P / R; p.per_side = S / P;
+    int rc = make_plane_map_3d(&p.map, tiles, es, S, (long long)T * C, P, R, C);
+    if (rc) return rc;
+    const size_t smem = (size_t)C * R * P * es + 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(patch_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(patch_tma_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 128);
+        if (e != cudaSuccess) { set_error("patch_gather_normalize: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
+        attr_set = true;
+    }
+    if (src_is_i16) SVRS_LAUNCH((patch_tma_kernel<short>), (unsigned)npatch, 256, smem, st, p);
+    else SVRS_LAUNCH((patch_tma_kernel<float>), (unsigned)npatch, 256, smem, st, p);
+    return check_launch("patch_tma_kernel");
+}
 
 extern "C" int svrs_grid_patch_normalize(const void* tiles, int src_is_i16, void* dst, int dst_dtype, int nhwc,
                                          int T, int C, int S, int P, void* stream) {
     SVRS_CHECK_ARG(tiles && dst && T >= 0 && C > 0 && C <= MAXC && S > 0 && P > 0 && S % P == 0,
                    "grid_patch_normalize: bad args (C <= 16, S %% P == 0)");
     if (T == 0) return 0;
-    unsigned blocks = (unsigned)(T * (S / P) * (S / P));
+    const int npatch = T * (S / P) * (S / P);
+    const bool tma = tma_patch_ok(src_is_i16 ? 2 : 4, C, S, P) && ((uintptr_t)tiles & 15) == 0 &&
+                     !(dst_dtype == SVRS_BF16 && !nhwc) && (dst_dtype == SVRS_F32 || dst_dtype == SVRS_BF16);
+    if (tma)
+        return svrs_patch_gather_normalize(tiles, src_is_i16, T, C, S, P, nullptr, npatch,
+                                           (dst_dtype == SVRS_F32 && !nhwc) ? (float*)dst : nullptr,
+                                           (dst_dtype == SVRS_F32 && nhwc) ? (float*)dst : nullptr,
+                                           dst_dtype == SVRS_BF16 ? dst : nullptr, stream);
+    unsigned blocks = (unsigned)npatch;
     cudaStream_t st = (cudaStream_t)stream;
     if (src_is_i16) {
         if (dst_dtype == SVRS_F32) SVRS_LAUNCH((grid_patch_kernel<short, float>), blocks, 256, 0, st, (const short*)tiles, (float*)dst, nhwc, C, S, P);

@@ -195,8 +195,38 @@ __device__ __forceinline__ void tc_mma_lohi(uint32_t d_tmem, uint32_t a_lo, uint
 // Specialised at compile time on (activation, bias) so the inner loop carries no per-element branches.
 constexpr int TC_EPI_WARPS = 8;
 
+// Optional extras of the shared epilogue (svrs_conv2d_fprop_ex):
+//   o2   - this thread's pixel in a second, fp32 output kept in the reference's NCHW-flat order (channel c at o2[c * hw]);
+//          the posterior / prior heads are written there straight from the fp32 accumulators (no bf16 rounding, no
+//          separate layout kernel).
+//   sbn  - CTA-shared float[2][EPI_BN_MAXC]: per-channel sum and sum of squares of the conv output (BatchNorm batch
+//          statistics taken from the fp32 accumulators instead of a separate read of the stored tensor).
+constexpr int EPI_BN_MAXC = 256;
+struct EpiRow {
+    float* o2;
+    int hw;
+    float* sbn;
+};
+
+// column sums over the 32 lanes of a warp (transpose-reduce butterfly, 31 shuffles): on return lane l holds
+// sum over lanes of v[l]
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int j = 0; j < s; ++j) {
+            const float send = up ? v[j] : v[j + s];
+            const float keep = up ? v[j + s] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
 template <int ACT, bool BIAS>
-__device__ __forceinline__ void epi_chunk8(const uint32_t* v, __nv_bfloat16* dst, const float* bias, int c, int Nc, bool vec_ok) {
+__device__ __forceinline__ void epi_chunk8(const uint32_t* v, __nv_bfloat16* dst, const float* bias, int c, int Nc, bool vec_ok,
+                                           float* o2, int hw) {
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -206,6 +236,12 @@ __device__ __forceinline__ void epi_chunk8(const uint32_t* v, __nv_bfloat16* dst
         else if (ACT == SVRS_ACT_HARDTANH7) x = fminf(fmaxf(x, -7.0f), 7.0f);
         f[e] = x;
     }
+    if (o2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (c + e < Nc) o2[(long long)(c + e) * hw] = f[e];
+    }
+    if (dst == nullptr) return;
     if (vec_ok) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
         __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
@@ -221,12 +257,14 @@ __device__ __forceinline__ void epi_chunk8(const uint32_t* v, __nv_bfloat16* dst
 }
 
 // taddr: TMEM address of (this warp's lane quarter, accumulator column 0); orow: output row pointer at channel c_base
+// (nullptr: no NHWC output); er: optional extras (second output / BatchNorm statistics), see EpiRow
 template <int ACT, bool BIAS>
 __device__ __forceinline__ void epi_rows(uint32_t taddr, int n_tile, int half, __nv_bfloat16* orow, const float* bias,
-                                         int c_base, int Nc, bool row_ok) {
+                                         int c_base, int Nc, bool row_ok, const EpiRow& er) {
     const bool vec_ok = (Nc % 8 == 0);
     const int chunks = (n_tile + 31) / 32;
     const int cbeg = half == 0 ? 0 : (chunks + 1) / 2, cend = half == 0 ? (chunks + 1) / 2 : chunks;
+    const int lane = threadIdx.x & 31;
     for (int ch = cbeg; ch < cend; ++ch) {
         const int c0 = ch * 32;
         uint32_t v[32];
@@ -237,22 +275,64 @@ __device__ __forceinline__ void epi_rows(uint32_t taddr, int n_tile, int half, _
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 const int c = c_base + c0 + j;
-                if (j < cols && c < Nc) epi_chunk8<ACT, BIAS>(v + j, orow + c0 + j, bias, c, Nc, vec_ok);
+                if (j < cols && c < Nc)
+                    epi_chunk8<ACT, BIAS>(v + j, orow ? orow + c0 + j : nullptr, bias, c, Nc, vec_ok, er.o2, er.hw);
+            }
+        }
+        if (er.sbn) {          // warp-uniform
+            float a[32], b[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = c_base + c0 + j;
+                float x = 0.f;
+                if (row_ok && j < cols && c < Nc) {
+                    x = __uint_as_float(v[j]);
+                    if (BIAS) x += __ldg(bias + c);
+                }
+                a[j] = x;
+                b[j] = x * x;
+            }
+            const float s1 = warp_colsum32(a, lane), s2 = warp_colsum32(b, lane);
+            const int c = c_base + c0 + lane;
+            if (lane < cols && c < Nc) {
+                atomicAdd(er.sbn + c, s1);
+                atomicAdd(er.sbn + EPI_BN_MAXC + c, s2);
             }
         }
     }
 }
 
 __device__ __forceinline__ void epi_dispatch(int act, uint32_t taddr, int n_tile, int half, __nv_bfloat16* orow, const float* bias,
-                                             int c_base, int Nc, bool row_ok) {
+                                             int c_base, int Nc, bool row_ok, const EpiRow& er) {
     if (bias) {
-        if (act == SVRS_ACT_SIGMOID) epi_rows<SVRS_ACT_SIGMOID, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok);
-        else if (act == SVRS_ACT_HARDTANH7) epi_rows<SVRS_ACT_HARDTANH7, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok);
-        else epi_rows<SVRS_ACT_NONE, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok);
+        if (act == SVRS_ACT_SIGMOID) epi_rows<SVRS_ACT_SIGMOID, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
+        else if (act == SVRS_ACT_HARDTANH7) epi_rows<SVRS_ACT_HARDTANH7, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
+        else epi_rows<SVRS_ACT_NONE, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
     } else {
-        epi_rows<SVRS_ACT_NONE, false>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok);
+        epi_rows<SVRS_ACT_NONE, false>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
     }
 }
+
+// BatchNorm statistics: zero the CTA's shared partial sums (all threads, before the first __syncthreads of the kernel) and
+// flush them (epilogue threads, after their tile loop) to one of the SVRS_BN_REPLICAS copies of the double[2C] scratch.
+__device__ __forceinline__ void epi_bn_zero(float* sbn) {
+    for (int i = threadIdx.x; i < 2 * EPI_BN_MAXC; i += blockDim.x) sbn[i] = 0.f;
+}
+__device__ __forceinline__ void epi_bn_flush(const float* sbn, double* sums, int C, int epi_tid, int epi_threads) {
+    named_bar_sync(3, epi_threads);
+    double* dst = sums + (size_t)(blockIdx.x % SVRS_BN_REPLICAS) * 2 * C;
+    for (int c = epi_tid; c < C; c += epi_threads) {
+        const float s1 = sbn[c], s2 = sbn[EPI_BN_MAXC + c];
+        if (s1 != 0.f || s2 != 0.f) { atomicAdd(dst + c, (double)s1); atomicAdd(dst + C + c, (double)s2); }
+    }
+}
+
+// extras of svrs_conv2d_fprop_ex / svrs_convT2d_fprop_ex (host side)
+struct ConvExtra {
+    float* out2 = nullptr;        // fp32 NCHW-flat second output
+    long long out2_ld = 0;
+    double* bn_sums = nullptr;    // BatchNorm statistics scratch
+};
 
 // host helpers (conv_tc.cu)
 int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sx, long long sy, long long sn,

@@ -62,8 +62,8 @@ def elbo_forward(recon_x, x, recon_y, y, mu1, lv1, mu2, lv2, mu3, lv3, gammas: t
     terms = torch.empty(5, device=dev, dtype=torch.float32)
     nx = recon_x.numel() if recon_x is not None else 0
     ny = recon_y.numel() if recon_y is not None else 0
-    lib.elbo_fwd(_p(recon_x), _p(x), _dt(recon_x) if nx else F32, nx,
-                 _p(recon_y), _p(y), _dt(recon_y) if ny else F32, ny,
+    lib.elbo_fwd(_p(recon_x), _p(x), _dt(recon_x) if nx else F32, _dt(x) if nx else F32, nx,
+                 _p(recon_y), _p(y), _dt(recon_y) if ny else F32, _dt(y) if ny else F32, ny,
                  _p(mu1), _p(lv1), mu1.stride(0) if mu1 is not None else 0, mu1.shape[1] if mu1 is not None else 0,
                  _p(mu2), _p(lv2), mu2.stride(0) if mu2 is not None else 0,
                  _p(mu3), _p(lv3), mu3.stride(0) if mu3 is not None else 0, mu2.shape[1] if mu2 is not None else 0,
@@ -105,12 +105,12 @@ class _CondLossFn(torch.autograd.Function):
         d_rx, d_ry = torch.empty_like(rx), torch.empty_like(ry)
         d = [torch.empty(t.shape, device=dev, dtype=torch.float32) for t in (m1, l1, m2, l2, m3, l3)]
         dgam = torch.empty(2, device=dev, dtype=torch.float32)
-        lib.elbo_bwd(_p(rx), _p(xx), _dt(rx), rx.numel(), _p(d_rx),
-                     _p(ry), _p(yy), _dt(ry), ry.numel(), _p(d_ry),
+        lib.elbo_bwd(_p(rx), _p(xx), _dt(rx), _dt(xx), rx.numel(), _p(d_rx), _dt(d_rx),
+                     _p(ry), _p(yy), _dt(ry), _dt(yy), ry.numel(), _p(d_ry), _dt(d_ry),
                      _p(m1), _p(l1), m1.stride(0), m1.shape[1], _p(d[0]), _p(d[1]), d[0].stride(0),
                      _p(m2), _p(l2), m2.stride(0), _p(d[2]), _p(d[3]), d[2].stride(0),
                      _p(m3), _p(l3), m3.stride(0), m2.shape[1], _p(d[4]), _p(d[5]), d[4].stride(0),
-                     ctx.B, _p(acc), _p(gam), _p(gout), _p(dgam), _st())
+                     ctx.B, _p(acc), _p(gam), _p(gout), _p(dgam), 0, _st())
         dgx = dgam[0].to(ctx.gdev[0])
         dgy = dgam[1].to(ctx.gdev[1])
         return d_rx, None, d_ry, None, d[0], d[1], d[2], d[3], d[4], d[5], dgx, dgy
@@ -145,12 +145,12 @@ class _BaseLossFn(torch.autograd.Function):
         d_rx = torch.empty_like(rx)
         dm, dl = (torch.empty(t.shape, device=dev, dtype=torch.float32) for t in (m1, l1))
         dgam = torch.empty(2, device=dev, dtype=torch.float32)
-        lib.elbo_bwd(_p(rx), _p(xx), _dt(rx), rx.numel(), _p(d_rx),
-                     None, None, F32, 0, None,
+        lib.elbo_bwd(_p(rx), _p(xx), _dt(rx), _dt(xx), rx.numel(), _p(d_rx), _dt(d_rx),
+                     None, None, F32, F32, 0, None, F32,
                      _p(m1), _p(l1), m1.stride(0), m1.shape[1], _p(dm), _p(dl), dm.stride(0),
                      None, None, 0, None, None, 0,
                      None, None, 0, 0, None, None, 0,
-                     ctx.B, _p(acc), _p(gam), _p(gout), _p(dgam), _st())
+                     ctx.B, _p(acc), _p(gam), _p(gout), _p(dgam), 0, _st())
         return d_rx, None, dm, dl, dgam[0].to(ctx.gdev)
 
 

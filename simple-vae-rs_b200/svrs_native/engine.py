@@ -17,9 +17,25 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
-from .lib import ACT_HARDTANH7, ACT_NONE, ACT_SIGMOID, BF16, F32, SvrsError, lib
+from .lib import ACT_HARDTANH7, ACT_NONE, ACT_SIGMOID, BF16, F32, SvrsError, SvrsUnsupported, lib
 
 BN_EPS_DEFAULT = 1e-5
+
+
+@dataclass
+class PatchBatch:
+    """A batch of normalised patches as the fused step consumes it: NHWC fp32 (the NLL target, and the conv operand in fp32
+    mode) plus the NHWC compute-dtype copy that feeds the first conv layer (the same tensor in fp32 mode).  Produced in one
+    launch by dataset.grid_patch_pair / svrs_patch_gather_normalize, or from a plain NCHW tensor by Runtime.patch_batch."""
+    f32: torch.Tensor
+    op: torch.Tensor
+
+    @property
+    def B(self) -> int:
+        return self.f32.shape[0]
+
+    def tensors(self):
+        return [self.f32] if self.op is self.f32 else [self.f32, self.op]
 
 
 def _dt(dtype: torch.dtype) -> int:
@@ -124,6 +140,9 @@ class ConvOp:
     act: int = ACT_NONE
     pack_f: Optional[torch.Tensor] = None   # KN pack for fprop
     pack_b: Optional[torch.Tensor] = None   # KN pack for dgrad
+    fuse_bn: Optional[bool] = None          # producer epilogue can take the BatchNorm statistics (None = not probed yet)
+    fuse_head: Optional[bool] = None        # epilogue can write the fp32 NCHW-flat head output
+    fuse_f32: Optional[bool] = None         # kernel can store fp32 from bf16 operands (sigmoid tail)
 
     @property
     def kk(self) -> int:
@@ -216,6 +235,15 @@ class Runtime:
         self.scratch_prezeroed = False   # the fused step zeroes all BatchNorm scratch once per step
         self.packs_dirty = True
         self._replayed = 0         # kernels re-issued by CUDA-graph replays (not seen by the library's own counter)
+        # fused-step gradient layout: the tcgen05 wgrad kernels accumulate their per-tap packed scratch DIRECTLY in the flat
+        # gradient buffer (at the parameter's offset) and svrs_adam_multi reads it there, so no gpack buffer / unpack pass
+        self.fused_grads = False
+        self.fuse_epilogues = os.environ.get("SVRS_FUSE_EPI", "1") != "0"   # BN statistics / head outputs in conv epilogues
+        # sync_bn (SURVEY 8.4 row e-ii): all-reduce the [sum, sum^2] / [sum dy, sum dy*xhat] scratch of every BatchNorm so
+        # the statistics are those of the GLOBAL batch (exact single-process parity of the data-parallel step)
+        self.sync_bn = False
+        self.pg = None
+        self.world = 1
         # Weight gradients are leaves of the backward pass: they run on a side stream, concurrently with the
         # dgrad -> BatchNorm chain of the main stream (most of them are small, latency-bound launches that leave SMs
         # idle).  SVRS_WGRAD_STREAM=0 keeps everything on one stream.
@@ -260,6 +288,7 @@ class Runtime:
                 for op in net.ops:
                     if isinstance(op, ConvOp):
                         op.pack_f = op.pack_b = None
+                        op.fuse_bn = op.fuse_head = op.fuse_f32 = None
             self.packs_dirty = True
 
     def ensure(self):
@@ -294,7 +323,8 @@ class Runtime:
         if with_scratch:
             self.zero_scratch()
         lib.fill_zero(_p(self.store.grad), self.store.grad.numel() * 4, _st())
-        lib.fill_zero(_p(self.store.gpack), self.store.gpack.numel() * 4, _st())
+        if not self.fused_grads:
+            lib.fill_zero(_p(self.store.gpack), self.store.gpack.numel() * 4, _st())
         self.launches += 2
 
     def branch(self, i: int):
@@ -403,6 +433,8 @@ class Runtime:
         """Add the per-tap packed weight-gradient scratch of every conv layer into the torch-layout flat gradient
         (one launch).  Must run after the last net_backward of a step and before anything reads store.grad."""
         self.join_wgrads()
+        if self.fused_grads:
+            return
         convs = [op for net in self.nets for op in net.ops if isinstance(op, ConvOp) and id(op) not in self._unpacked_early]
         self._unpacked_early = set()
         if not convs:
@@ -449,10 +481,11 @@ class Runtime:
         self.packs_dirty = False
 
     # -------------------------------------------------------------------------------------- layout glue
-    def to_nhwc(self, src: torch.Tensor, src_ld: int, n: int, c: int, h: int, w: int) -> torch.Tensor:
-        """NCHW-flat rows (fp32, row stride src_ld) -> NHWC compute-dtype tensor [n,h,w,c]."""
-        out = torch.empty((n, h, w, c), device=src.device, dtype=self.dtype)
-        lib.nchw_to_nhwc(_p(src), _dt(src.dtype), src_ld, _p(out), self.dt, n, c, h, w, _st())
+    def to_nhwc(self, src: torch.Tensor, src_ld: int, n: int, c: int, h: int, w: int, dtype=None) -> torch.Tensor:
+        """NCHW-flat rows (fp32, row stride src_ld) -> NHWC tensor [n,h,w,c] in the compute dtype (or `dtype`)."""
+        dtype = self.dtype if dtype is None else dtype
+        out = torch.empty((n, h, w, c), device=src.device, dtype=dtype)
+        lib.nchw_to_nhwc(_p(src), _dt(src.dtype), src_ld, _p(out), _dt(dtype), n, c, h, w, _st())
         self.launches += 1
         return out
 
@@ -472,24 +505,102 @@ class Runtime:
     def _dtype_of(t):
         return t.dtype
 
+    def cast(self, t: torch.Tensor, dtype) -> torch.Tensor:
+        if t.dtype == dtype:
+            return t
+        out = torch.empty(t.shape, device=t.device, dtype=dtype)
+        lib.cast(_p(t), _dt(t.dtype), _p(out), _dt(dtype), t.numel(), _st())
+        self.launches += 1
+        return out
+
+    def patch_batch(self, t) -> "PatchBatch":
+        """Accept either a PatchBatch (dataset.grid_patch_pair) or a plain NCHW tensor [B,C,P,P] (the reference's batch
+        layout) and return NHWC fp32 + NHWC compute-dtype operands."""
+        if isinstance(t, PatchBatch):
+            _require_cuda(t.f32, "patch batch")
+            if t.op.dtype != self.dtype:
+                return PatchBatch(t.f32, self.cast(t.f32, self.dtype))
+            return t
+        _require_cuda(t, "input batch")
+        t = t.contiguous().float()
+        b, c, h, w = t.shape
+        f32 = self.to_nhwc(t, c * h * w, b, c, h, w, torch.float32)
+        return PatchBatch(f32, self.cast(f32, self.dtype))
+
+    def _bn_allreduce(self, sums: torch.Tensor):
+        torch.distributed.all_reduce(sums, group=self.pg)
+
     # -------------------------------------------------------------------------------------- forward
-    def net_forward(self, net: Net, x: torch.Tensor, training: bool, save: bool, bn_updates: int = 1):
-        """x: NHWC [N,H,W,Cin] in the compute dtype.  Returns (out NHWC, tape)."""
+    def net_forward(self, net: Net, x: torch.Tensor, training: bool, save: bool, bn_updates: int = 1,
+                    head: Optional[Tuple[torch.Tensor, int]] = None, need_nhwc: bool = True, f32_out: bool = False):
+        """x: NHWC [N,H,W,Cin] in the compute dtype.  Returns (out NHWC, tape).
+        head = (dst, ld): the LAST conv also writes its result as fp32 NCHW-flat rows of dst (row stride ld) - from the
+        tcgen05 epilogue when that kernel takes the layer, else through svrs_nhwc_to_nchw; with need_nhwc=False the NHWC
+        result may be skipped (returned as None).  f32_out: the last conv stores fp32 (sigmoid tail -> NLL)."""
         st = _st()
         n, h, w, c = x.shape
         assert c == net.cin, f"{net.name}: expected {net.cin} channels, got {c}"
         tape = []
-        for op in net.ops:
+        last_conv = max(i for i, op in enumerate(net.ops) if isinstance(op, ConvOp))
+        fuse = self.fuse_epilogues and self.dtype == torch.bfloat16
+        pending_stats = None      # BNOp whose statistics the producing conv already accumulated
+        for i, op in enumerate(net.ops):
             if isinstance(op, ConvOp):
                 oh, ow = op.out_hw(h, w)
-                y = torch.empty((n, oh, ow, op.cout), device=x.device, dtype=self.dtype)
                 bias = op.mod.bias
-                if op.kind == "ct":
-                    lib.convT2d_fprop(_p(x), _p(op.pack_f), _p(op.pack_b), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout, op.act, st)
-                else:
-                    lib.conv2d_fprop(_p(x), _p(op.pack_f), _p(op.pack_b), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout,
-                                     3 if op.kind == "c3" else 4, op.act, st)
+                is_last = i == last_conv
+                nxt = net.ops[i + 1] if i + 1 < len(net.ops) else None
+                want_bn = fuse and training and isinstance(nxt, BNOp) and op.fuse_bn is not False
+                want_head = is_last and head is not None and fuse and op.fuse_head is not False and op.kind != "ct"
+                want_f32 = is_last and f32_out and self.dtype != torch.float32 and op.fuse_f32 is not False and op.kind != "ct"
+                out_dtype = torch.float32 if want_f32 else self.dtype
+                skip_nhwc = want_head and not need_nhwc
+                y = None if skip_nhwc else torch.empty((n, oh, ow, op.cout), device=x.device, dtype=out_dtype)
+                sums = None
+                if want_bn:
+                    sums = nxt.sums_f
+                    if not self.scratch_prezeroed:
+                        lib.fill_zero(_p(sums), 16 * nxt.mod.num_features * BN_REPLICAS, st)
+                done = False
+                if want_bn or want_head or want_f32:
+                    try:
+                        if op.kind == "ct":
+                            lib.convT2d_fprop_ex(_p(x), _p(op.pack_f), _p(op.pack_b), _p(bias), _p(y), self.dt, _p(sums),
+                                                 n, h, w, op.cin, op.cout, op.act, st)
+                        else:
+                            lib.conv2d_fprop_ex(_p(x), _p(op.pack_f), _p(op.pack_b), _p(bias), _p(y), self.dt, _dt(out_dtype),
+                                                _p(head[0]) if want_head else None, head[1] if want_head else 0, _p(sums),
+                                                n, h, w, op.cin, op.cout, 3 if op.kind == "c3" else 4, op.act, st)
+                        done = True
+                        if want_bn:
+                            op.fuse_bn = True
+                            pending_stats = nxt
+                        if want_head:
+                            op.fuse_head = True
+                        if want_f32:
+                            op.fuse_f32 = True
+                    except SvrsUnsupported:
+                        # remember which extra this layer's kernel lacks and fall through to the separate kernels
+                        if want_bn:
+                            op.fuse_bn = False
+                        if want_head:
+                            op.fuse_head = False
+                        if want_f32:
+                            op.fuse_f32 = False
+                        want_head = False
+                        if y is None or y.dtype != self.dtype:
+                            y = torch.empty((n, oh, ow, op.cout), device=x.device, dtype=self.dtype)
+                if not done:
+                    if op.kind == "ct":
+                        lib.convT2d_fprop(_p(x), _p(op.pack_f), _p(op.pack_b), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout, op.act, st)
+                    else:
+                        lib.conv2d_fprop(_p(x), _p(op.pack_f), _p(op.pack_b), _p(bias), _p(y), self.dt, n, h, w, op.cin, op.cout,
+                                         3 if op.kind == "c3" else 4, op.act, st)
                 self.launches += 1
+                if is_last and head is not None and not (done and want_head):
+                    self.to_nchw(y, head[0], head[1])
+                if is_last and f32_out and y is not None and y.dtype != torch.float32:
+                    y = self.cast(y, torch.float32)
                 if save:
                     tape.append((op, x, y if op.act != ACT_NONE else None))
                 x, h, w = y, oh, ow
@@ -503,13 +614,19 @@ class Runtime:
                 if training:
                     mean = torch.empty(cch, device=dev, dtype=torch.float32)
                     invstd = torch.empty(cch, device=dev, dtype=torch.float32)
-                    if not self.scratch_prezeroed:
-                        lib.fill_zero(_p(op.sums_f), 16 * cch * BN_REPLICAS, st)
-                    lib.bn_stats(_p(x), self.dt, m, cch, _p(op.sums_f), st)
+                    if pending_stats is not op:
+                        if not self.scratch_prezeroed:
+                            lib.fill_zero(_p(op.sums_f), 16 * cch * BN_REPLICAS, st)
+                        lib.bn_stats(_p(x), self.dt, m, cch, _p(op.sums_f), st)
+                    pending_stats = None
+                    m_stat = 0
+                    if self.sync_bn and self.world > 1:
+                        self._bn_allreduce(op.sums_f)
+                        m_stat = m * self.world
                     mom = 0.1 if bn.momentum is None else bn.momentum
                     track = bn.track_running_stats and bn.running_mean is not None
                     y = torch.empty_like(x) if save else x
-                    lib.bn_apply_train(_p(x), _p(y), self.dt, m, cch, _p(op.sums_f), _p(bn.weight), _p(bn.bias), bn.eps, mom,
+                    lib.bn_apply_train(_p(x), _p(y), self.dt, m, m_stat, cch, _p(op.sums_f), _p(bn.weight), _p(bn.bias), bn.eps, mom,
                                        _p(bn.running_mean) if track else None,
                                        _p(bn.running_var) if track else None,
                                        _p(bn.num_batches_tracked) if track else None, bn_updates, int(op.relu),
@@ -533,9 +650,10 @@ class Runtime:
         return x, tape
 
     # -------------------------------------------------------------------------------------- backward
-    def net_backward(self, net: Net, tape: list, dy: torch.Tensor, need_dx: bool) -> Optional[torch.Tensor]:
+    def net_backward(self, net: Net, tape: list, dy: torch.Tensor, need_dx: bool, act_done: bool = False) -> Optional[torch.Tensor]:
         """dy: NHWC grad wrt the net output (compute dtype; MAY be modified in place).  Accumulates parameter
-        gradients into the flat fp32 gradient buffer; returns dx (NHWC) if need_dx."""
+        gradients into the flat fp32 gradient buffer; returns dx (NHWC) if need_dx.  act_done: the backward of the
+        output activation (Sigmoid / Hardtanh) has already been applied to dy by the caller."""
         st = _st()
         store = self.store
         for idx in range(len(tape) - 1, -1, -1):
@@ -544,11 +662,11 @@ class Runtime:
             if isinstance(op, ConvOp):
                 _, x, yact = entry
                 n, h, w, _c = x.shape
-                if op.act != ACT_NONE:
+                if op.act != ACT_NONE and not (act_done and idx == len(tape) - 1):
                     lib.act_bwd(_p(yact), _p(dy), _p(dy), self.dt, op.act, dy.numel(), st)
                     self.launches += 1
                 dw = store.grad_ptr(op.mod.weight)
-                dwp = store.gpack_ptr(op.mod.weight)
+                dwp = dw if self.fused_grads else store.gpack_ptr(op.mod.weight)
                 db = store.grad_ptr(op.mod.bias) if op.mod.bias is not None else None
                 wst = self._wgrad_stream(x, dy)
                 if op.kind == "ct":
@@ -579,11 +697,22 @@ class Runtime:
                     lib.fill_zero(_p(op.sums_b), 16 * cch * BN_REPLICAS, st)
                 lib.bn_bwd_reduce(_p(x), _p(dy), self.dt, m, cch, _p(scale), _p(shift), _p(mean), _p(invstd),
                                   int(op.relu), _p(op.sums_b), st)
-                lib.bn_bwd_apply(_p(x), _p(dy), _p(dy), self.dt, m, cch, _p(scale), _p(shift), _p(mean), _p(invstd),
+                m_stat = 0
+                if self.sync_bn and self.world > 1:
+                    self._bn_allreduce(op.sums_b)
+                    m_stat = m * self.world
+                lib.bn_bwd_apply(_p(x), _p(dy), _p(dy), self.dt, m, m_stat, cch, _p(scale), _p(shift), _p(mean), _p(invstd),
                                  _p(bn.weight), int(op.relu), _p(op.sums_b),
                                  store.grad_ptr(bn.weight), store.grad_ptr(bn.bias), st)
                 self.launches += 3
         return dy if need_dx else None
+
+
+def _walk_conv_shapes(net: Net, n: int, h: int, w: int, out: dict):
+    for op in net.ops:
+        if isinstance(op, ConvOp):
+            out[id(op)] = (n, h, w)
+            h, w = op.out_hw(h, w)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -639,31 +768,37 @@ class CondEngine:
             raise SvrsError("latent widths must be multiples of 4")
         self.rng = RngState()
 
+    def conv_input_shapes(self, B: int) -> dict:
+        """id(ConvOp) -> (N, H, W) of the layer's input at batch B (the wgrad dispatch depends on the map size)."""
+        P, N, out = self.P, self.nets, {}
+        h8, h16 = P // 8, P // 16
+        for name, hw in (("encoder_y", P // 2), ("y_to_z", P // 2), ("encoder_x", P), ("decoder_y", h8), ("decoder_x", h8),
+                         ("u_to_z", h16), ("mu_u_y_to_z", h16), ("logvar_u_y_to_z", h16)):
+            _walk_conv_shapes(N[name], B, hw, hw, out)
+        return out
+
     # ---- forward ---------------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, y: torch.Tensor, eps_u: Optional[torch.Tensor], eps_z: Optional[torch.Tensor],
-                training: bool, save: bool, repack: bool = True):
-        """x [B,4,P,P], y [B,4,P/2,P/2] (NCHW, fp32, CUDA).  Returns (outs, ctx) where
-        outs = dict(x_hat, y_hat, enc_z [B,2Wz], enc_u [B,2Wu], mu3, lv3) all fp32 NCHW(-flat)."""
+    def forward(self, x, y, eps_u: Optional[torch.Tensor], eps_z: Optional[torch.Tensor],
+                training: bool, save: bool, repack: bool = True, fused_io: bool = False):
+        """x [B,4,P,P], y [B,4,P/2,P/2] (NCHW fp32 CUDA tensors, or PatchBatch objects).  Returns (outs, ctx) where
+        outs = dict(x_hat_nhwc, y_hat_nhwc (fp32 NHWC), enc_z [B,2Wz], enc_u [B,2Wu], mu3, lv3 (fp32 NCHW-flat)) plus, unless
+        fused_io, x_hat / y_hat in the reference's NCHW layout."""
         rt = self.rt
-        _require_cuda(x, "x")
-        _require_cuda(y, "y")
         rt.ensure()
         if repack:
             rt.packs_dirty = True
         rt.pack_weights()
-        P, B = self.P, x.shape[0]
-        assert x.shape[1:] == (4, P, P) and y.shape[1:] == (4, P // 2, P // 2) and y.shape[0] == B
-        x = x.contiguous().float()
-        y = y.contiguous().float()
-        dev = x.device
+        xb, yb = rt.patch_batch(x), rt.patch_batch(y)
+        P, B = self.P, xb.B
+        assert tuple(xb.f32.shape[1:]) == (P, P, 4) and tuple(yb.f32.shape[1:]) == (P // 2, P // 2, 4) and yb.B == B
+        dev = xb.f32.device
         f32 = dict(device=dev, dtype=torch.float32)
         h8, h16 = P // 8, P // 16
         Wz, Wu = self.Wz, self.Wu
         N = self.nets
         ctx = {}
 
-        y_nhwc = rt.to_nhwc(y, 4 * (P // 2) ** 2, B, 4, P // 2, P // 2)
-        x_nhwc = rt.to_nhwc(x, 4 * P * P, B, 4, P, P)
+        y_nhwc, x_nhwc = yb.op, xb.op
 
         enc_u = torch.empty((B, 2 * Wu), **f32)
         u = torch.empty((B, Wu), **f32)
@@ -671,23 +806,20 @@ class CondEngine:
         stack = torch.empty((B, 2 * Wz), **f32)          # torch.cat((y_enc, z), dim=1)  cond_vae.py:272
         mu3 = torch.empty((B, Wz), **f32)
         lv3 = torch.empty((B, Wz), **f32)
-        x_hat = torch.empty((B, 4, P, P), **f32)
-        y_hat = torch.empty((B, 4, P // 2, P // 2), **f32)
 
         # ---- phase 1: three independent encoders -------------------------------------------------------------------
+        # The posterior heads (mu || logvar) leave the conv stacks as fp32 NCHW-flat rows written by the conv epilogue
+        # (net_forward head=...): chunk / Flatten are addressing, mu / logvar are never rounded to bf16.
         with rt.branch(0):
             # q(u|y): encoder_y -> chunk -> reparameterize (RNG draw #1; Philox is counter-based, so the
             # draw order is a naming convention - stream ids 0 / 1 - not an execution order)
-            ey, ctx["t_ey"] = rt.net_forward(N["encoder_y"], y_nhwc, training, save)
-            rt.to_nchw(ey, enc_u, 2 * Wu)
+            _, ctx["t_ey"] = rt.net_forward(N["encoder_y"], y_nhwc, training, save, head=(enc_u, 2 * Wu), need_nhwc=False)
             reparam_fwd(rt, enc_u, eps_u, u, Wu, B, Wu, self.rng, 0)
         with rt.branch(1):
-            # y_to_z once (two BN running-stat updates)
-            yz, ctx["t_yz"] = rt.net_forward(N["y_to_z"], y_nhwc, training, save, bn_updates=2)
-            rt.to_nchw(yz, stack, 2 * Wz)                # left half of stack = y_enc flat
+            # y_to_z once (two BN running-stat updates); left half of stack = y_enc flat, NHWC copy feeds the prior heads
+            yz, ctx["t_yz"] = rt.net_forward(N["y_to_z"], y_nhwc, training, save, bn_updates=2, head=(stack, 2 * Wz))
         # q(z|x): encoder_x -> chunk -> reparameterize (draw #2); z lands in the right half of `stack`
-        ex, ctx["t_ex"] = rt.net_forward(N["encoder_x"], x_nhwc, training, save)
-        rt.to_nchw(ex, enc_z, 2 * Wz)
+        _, ctx["t_ex"] = rt.net_forward(N["encoder_x"], x_nhwc, training, save, head=(enc_z, 2 * Wz), need_nhwc=False)
         reparam_fwd(rt, enc_z, eps_z, stack.data_ptr() + 4 * Wz, 2 * Wz, B, Wz, self.rng, 1)
         rt.join(0, 1)
 
@@ -695,8 +827,7 @@ class CondEngine:
         with rt.branch(0):
             # decode_y(u): u viewed (Lu/64, P/8, P/8)
             u8 = rt.to_nhwc(u, Wu, B, self.cu, h8, h8)
-            yh, ctx["t_dy"] = rt.net_forward(N["decoder_y"], u8, training, save)
-            rt.to_nchw(yh, y_hat, 4 * (P // 2) ** 2)
+            yh, ctx["t_dy"] = rt.net_forward(N["decoder_y"], u8, training, save, f32_out=True)
         with rt.branch(1):
             # u_to_z on u re-viewed as (Lu/16, P/16, P/16)   cond_vae.py:168-175
             u16 = rt.to_nhwc(u, Wu, B, self.cu16, h16, h16)
@@ -710,26 +841,40 @@ class CondEngine:
             lib.copy2d(_p(uz), rt.dt, c16, joint.data_ptr() + es * c16, rt.dt, 2 * c16, rows, c16, 0, _st())
             rt.launches += 1
             with rt.branch(2):                           # the two prior heads only share their input
-                l3, ctx["t_lv"] = rt.net_forward(N["logvar_u_y_to_z"], joint, training, save)
-                rt.to_nchw(l3, lv3, Wz)
-            m3, ctx["t_mu"] = rt.net_forward(N["mu_u_y_to_z"], joint, training, save)
-            rt.to_nchw(m3, mu3, Wz)
+                _, ctx["t_lv"] = rt.net_forward(N["logvar_u_y_to_z"], joint, training, save, head=(lv3, Wz), need_nhwc=False)
+            _, ctx["t_mu"] = rt.net_forward(N["mu_u_y_to_z"], joint, training, save, head=(mu3, Wz), need_nhwc=False)
             rt.join(2)
         # decode_x(z, y): stack viewed (2L/64, P/8, P/8)
         s8 = rt.to_nhwc(stack, 2 * Wz, B, 2 * self.cz, h8, h8)
-        xh, ctx["t_dx"] = rt.net_forward(N["decoder_x"], s8, training, save)
-        rt.to_nchw(xh, x_hat, 4 * P * P)
+        xh, ctx["t_dx"] = rt.net_forward(N["decoder_x"], s8, training, save, f32_out=True)
         rt.join(0, 1)
 
+        outs = dict(x_hat_nhwc=xh, y_hat_nhwc=yh, enc_z=enc_z, enc_u=enc_u, mu3=mu3, lv3=lv3, xb=xb, yb=yb)
+        if not fused_io:
+            x_hat = torch.empty((B, 4, P, P), **f32)
+            y_hat = torch.empty((B, 4, P // 2, P // 2), **f32)
+            rt.to_nchw(xh, x_hat, 4 * P * P)
+            rt.to_nchw(yh, y_hat, 4 * (P // 2) ** 2)
+            outs.update(x_hat=x_hat, y_hat=y_hat)
         if save:
-            ctx.update(B=B, enc_u=enc_u, enc_z=enc_z, eps_u=eps_u, eps_z=eps_z, rng=RngState(**vars(self.rng)))
-        outs = dict(x_hat=x_hat, y_hat=y_hat, enc_z=enc_z, enc_u=enc_u, mu3=mu3, lv3=lv3)
+            ctx.update(B=B, enc_u=enc_u, enc_z=enc_z, eps_u=eps_u, eps_z=eps_z, rng=RngState(**vars(self.rng)),
+                       lv3=lv3, x_hat_nhwc=xh, y_hat_nhwc=yh)
         return outs, ctx
 
     # ---- backward --------------------------------------------------------------------------------
-    def backward(self, ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3):
-        """Gradients wrt the forward outputs (fp32, NCHW(-flat); None = zero; d_enc_* are MODIFIED in place).
-        Parameter gradients are accumulated into rt.store.grad (caller zeroes it)."""
+    def _image_grad(self, d_nchw: torch.Tensor, y_nhwc_f32: torch.Tensor, B: int, hw: int) -> torch.Tensor:
+        """Upstream gradient wrt a sigmoid output in the reference's NCHW fp32 layout -> gradient wrt the pre-activation,
+        NHWC in the compute dtype (autograd path; the fused step gets this straight from svrs_elbo_bwd)."""
+        rt = self.rt
+        g = rt.to_nhwc(d_nchw.contiguous().float(), 4 * hw * hw, B, 4, hw, hw, torch.float32)
+        lib.act_bwd(_p(y_nhwc_f32), _p(g), _p(g), F32, ACT_SIGMOID, g.numel(), _st())
+        rt.launches += 1
+        return rt.cast(g, rt.dtype)
+
+    def backward(self, ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3, fused_io: bool = False):
+        """Gradients wrt the forward outputs (fp32, NCHW(-flat); None = zero; d_enc_* and d_lv3 are MODIFIED in place).
+        fused_io: d_xhat / d_yhat are NHWC compute-dtype gradients wrt the decoders' PRE-sigmoid outputs (svrs_elbo_bwd with
+        act = SIGMOID).  Parameter gradients are accumulated into rt.store.grad (caller zeroes it)."""
         rt = self.rt
         N = self.nets
         P, B = self.P, ctx["B"]
@@ -750,16 +895,20 @@ class CondEngine:
         d_stack = d_u = d_yz = du16 = None
         with rt.branch(0):
             if d_yhat is not None:
-                g_y = rt.to_nhwc(d_yhat.contiguous(), 4 * (P // 2) ** 2, B, 4, P // 2, P // 2)
-                du8 = rt.net_backward(N["decoder_y"], ctx["t_dy"], g_y, True)
+                g_y = d_yhat if fused_io else self._image_grad(d_yhat, ctx["y_hat_nhwc"], B, P // 2)
+                du8 = rt.net_backward(N["decoder_y"], ctx["t_dy"], g_y, True, act_done=True)
                 d_u = torch.empty((B, Wu), **f32)
                 rt.to_nchw(du8, d_u, Wu)
         with rt.branch(1):
             d_joint = dj_lv = None
             with rt.branch(2):                           # the two prior heads run in parallel
                 if d_lv3 is not None:
-                    g_l = rt.to_nhwc(d_lv3.contiguous(), Wz, B, c16, h16, h16)
-                    dj_lv = rt.net_backward(N["logvar_u_y_to_z"], ctx["t_lv"], g_l, True)
+                    # Hardtanh(-7, 7) backward (cond_vae.py:230) on the NCHW-flat fp32 rows, from the saved OUTPUT
+                    d_lv3 = d_lv3.contiguous()
+                    lib.act_bwd(_p(ctx["lv3"]), _p(d_lv3), _p(d_lv3), F32, ACT_HARDTANH7, d_lv3.numel(), _st())
+                    rt.launches += 1
+                    g_l = rt.to_nhwc(d_lv3, Wz, B, c16, h16, h16)
+                    dj_lv = rt.net_backward(N["logvar_u_y_to_z"], ctx["t_lv"], g_l, True, act_done=True)
             if d_mu3 is not None:
                 g_h = rt.to_nhwc(d_mu3.contiguous(), Wz, B, c16, h16, h16)
                 d_joint = rt.net_backward(N["mu_u_y_to_z"], ctx["t_mu"], g_h, True)
@@ -779,8 +928,8 @@ class CondEngine:
                 rt.launches += 1
                 du16 = rt.net_backward(N["u_to_z"], ctx["t_uz"], d_uz, True)
         if d_xhat is not None:
-            g_x = rt.to_nhwc(d_xhat.contiguous(), 4 * P * P, B, 4, P, P)
-            ds8 = rt.net_backward(N["decoder_x"], ctx["t_dx"], g_x, True)
+            g_x = d_xhat if fused_io else self._image_grad(d_xhat, ctx["x_hat_nhwc"], B, P)
+            ds8 = rt.net_backward(N["decoder_x"], ctx["t_dx"], g_x, True, act_done=True)
             d_stack = torch.empty((B, 2 * Wz), **f32)
             rt.to_nchw(ds8, d_stack, 2 * Wz)
         rt.join(0, 1)
@@ -893,40 +1042,52 @@ class VaeEngine:
             raise SvrsError("latent width must be a multiple of 4")
         self.rng = RngState()
 
-    def forward(self, x, eps, training: bool, save: bool, repack: bool = True):
+    def conv_input_shapes(self, B: int) -> dict:
+        out = {}
+        _walk_conv_shapes(self.nets["encoder"], B, self.P, self.P, out)
+        _walk_conv_shapes(self.nets["decoder"], B, self.P // 4, self.P // 4, out)
+        return out
+
+    def forward(self, x, eps, training: bool, save: bool, repack: bool = True, fused_io: bool = False):
         rt = self.rt
-        _require_cuda(x, "x")
         rt.ensure()
         if repack:
             rt.packs_dirty = True
         rt.pack_weights()
-        P, B, Wd = self.P, x.shape[0], self.Wd
-        assert x.shape[1:] == (4, P, P)
-        x = x.contiguous().float()
-        f32 = dict(device=x.device, dtype=torch.float32)
+        xb = rt.patch_batch(x)
+        P, B, Wd = self.P, xb.B, self.Wd
+        assert tuple(xb.f32.shape[1:]) == (P, P, 4)
+        f32 = dict(device=xb.f32.device, dtype=torch.float32)
         ctx = {}
-        x_nhwc = rt.to_nhwc(x, 4 * P * P, B, 4, P, P)
-        e, ctx["t_e"] = rt.net_forward(self.nets["encoder"], x_nhwc, training, save)
         enc = torch.empty((B, 2 * Wd), **f32)
-        rt.to_nchw(e, enc, 2 * Wd)
+        _, ctx["t_e"] = rt.net_forward(self.nets["encoder"], xb.op, training, save, head=(enc, 2 * Wd), need_nhwc=False)
         z = torch.empty((B, Wd), **f32)
         reparam_fwd(rt, enc, eps, z, Wd, B, Wd, self.rng, 0)
         z4 = rt.to_nhwc(z, Wd, B, self.c, P // 4, P // 4)
-        d, ctx["t_d"] = rt.net_forward(self.nets["decoder"], z4, training, save)
-        x_hat = torch.empty((B, 4, P, P), **f32)
-        rt.to_nchw(d, x_hat, 4 * P * P)
+        d, ctx["t_d"] = rt.net_forward(self.nets["decoder"], z4, training, save, f32_out=True)
+        outs = dict(x_hat_nhwc=d, enc=enc, xb=xb)
+        if not fused_io:
+            x_hat = torch.empty((B, 4, P, P), **f32)
+            rt.to_nchw(d, x_hat, 4 * P * P)
+            outs["x_hat"] = x_hat
         if save:
-            ctx.update(B=B, enc=enc, eps=eps, rng=RngState(**vars(self.rng)))
-        return dict(x_hat=x_hat, enc=enc), ctx
+            ctx.update(B=B, enc=enc, eps=eps, rng=RngState(**vars(self.rng)), x_hat_nhwc=d)
+        return outs, ctx
 
-    def backward(self, ctx, d_xhat, d_enc):
+    def backward(self, ctx, d_xhat, d_enc, fused_io: bool = False):
         rt = self.rt
         P, B, Wd = self.P, ctx["B"], self.Wd
         f32 = dict(device=ctx["enc"].device, dtype=torch.float32)
         d_z = None
         if d_xhat is not None:
-            g = rt.to_nhwc(d_xhat.contiguous(), 4 * P * P, B, 4, P, P)
-            dz4 = rt.net_backward(self.nets["decoder"], ctx["t_d"], g, True)
+            if fused_io:
+                g = d_xhat
+            else:
+                g = rt.to_nhwc(d_xhat.contiguous().float(), 4 * P * P, B, 4, P, P, torch.float32)
+                lib.act_bwd(_p(ctx["x_hat_nhwc"]), _p(g), _p(g), F32, ACT_SIGMOID, g.numel(), _st())
+                rt.launches += 1
+                g = rt.cast(g, rt.dtype)
+            dz4 = rt.net_backward(self.nets["decoder"], ctx["t_d"], g, True, act_done=True)
             d_z = torch.empty((B, Wd), **f32)
             rt.to_nchw(dz4, d_z, Wd)
         if d_enc is None and d_z is not None:

@@ -31,6 +31,11 @@ class SvrsError(RuntimeError):
     pass
 
 
+class SvrsUnsupported(SvrsError):
+    """SVRS_E_UNSUPPORTED (-3): the kernel that takes this shape cannot provide a requested optional extra; nothing was
+    enqueued.  Callers use the separate kernels instead (never a CPU path)."""
+
+
 def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str]]]]:
     """-> {name: (return_type, [(ctype, argname), ...])} for every `svrs_*` prototype."""
     src = open(path).read()
@@ -89,7 +94,8 @@ class _Lib:
         if full not in self.protos:
             raise AttributeError(name)
         fn = getattr(self.load(), full)
-        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run", "svrs_pack_job_bytes", "svrs_launch_count"):
+        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run", "svrs_pack_job_bytes", "svrs_launch_count", "svrs_adam_job_bytes",
+                                                  "svrs_conv2d_wgrad_layout", "svrs_convT2d_wgrad_layout"):
             setattr(self, name, fn)
             return fn
 
@@ -111,6 +117,8 @@ class _Lib:
                 self.timing.append((_n, a, e0, e1, kernels))
             else:
                 rc = _fn(*a)
+            if rc == -3:
+                raise SvrsUnsupported(f"{_n}: {self.last_error()}")
             if rc != 0:
                 raise SvrsError(f"{_n} failed ({rc}): {self.last_error()}")
 

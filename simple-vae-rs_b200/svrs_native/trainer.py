@@ -12,13 +12,15 @@ gradient on the global batch (up to per-rank BatchNorm statistics).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 
 from .elbo import elbo_forward
-from .engine import CondEngine, VaeEngine, _p, _st
-from .lib import F32, lib
+from .engine import BNOp, CondEngine, ConvOp, PatchBatch, VaeEngine, _dt, _p, _st
+from .lib import ACT_SIGMOID, F32, lib
 from .parallel import upstream_grad_scales
 
 
@@ -38,7 +40,8 @@ class _AdamCfg:
 class _FusedBase:
     n_gammas = 2
 
-    def __init__(self, engine, optimizer=None, max_norm: float = 1.0, process_group=None, overlap: bool = True):
+    def __init__(self, engine, optimizer=None, max_norm: float = 1.0, process_group=None, overlap: bool = True,
+                 sync_bn: bool = False, world_override: Optional[int] = None):
         self.eng = engine
         self.rt = engine.rt
         self.cfg = _AdamCfg(max_norm=max_norm)
@@ -50,7 +53,16 @@ class _FusedBase:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
             self.rank = torch.distributed.get_rank(process_group)
+        if world_override is not None:          # world_override=1: a single-process step inside a distributed job
+            self.world = world_override
         self.overlap = overlap and self.world > 1
+        # sync_bn: BatchNorm statistics of the GLOBAL batch (per-layer all-reduce of the 2C sums, forward and backward) -
+        # exact single-process parity of the data-parallel step (SURVEY 8.4 row e-ii); default = per-rank statistics
+        self.sync_bn = bool(sync_bn) and self.world > 1
+        self.keep_grad = False                  # keep a copy of the (all-reduced) flat gradient of the last step (checks)
+        self.last_grad = None
+        self.fused_tail = os.environ.get("SVRS_FUSED_TAIL", "1") != "0"
+        self._adam_jobs = None
         self.m = self.v = None
         self._graphs: Dict[tuple, dict] = {}
         self._comm_stream = None
@@ -60,6 +72,7 @@ class _FusedBase:
     def _ensure_state(self):
         rt = self.rt
         rt.ensure()
+        rt.sync_bn, rt.pg, rt.world = self.sync_bn, self.pg, self.world
         store = rt.store
         if self.m is None or self.m.device != store.flat.device or self.m.numel() != store.flat.numel():
             dev = store.flat.device
@@ -75,10 +88,10 @@ class _FusedBase:
             self._load_gammas_from_model()
             self.eng.rng.step_ptr = self.step_ptr
             self._graphs.clear()
+            self._adam_jobs = None
             rt.packs_dirty = True
             if self.world > 1:
                 self._comm_stream = torch.cuda.Stream(device=dev)
-                import os
                 # off by default: neutral at 2 GPUs and harmful at 8 (6.3 vs 4.4 ms/step measured) - the NCCL kernels of the
                 # early all-reduce compete for SMs with five concurrent compute streams and every rank then waits
                 self._ar_overlap = os.environ.get("SVRS_AR_OVERLAP", "0") == "1"
@@ -101,18 +114,80 @@ class _FusedBase:
             getattr(self.eng.model, a).data.fill_(float(host[i]))
 
     # ---- optimizer tail ----------------------------------------------------------------------------
-    def _optim_tail(self):
+    def _adam_table(self, batch: int):
+        """Device job table of svrs_adam_multi: one conv job per conv / convT weight (gradient layout as the wgrad kernel
+        that takes the layer at this batch size leaves it) and one plain job per gap between them (biases, BatchNorm)."""
+        rt, eng = self.rt, self.eng
+        store = rt.store
+        key = (store.flat.data_ptr(), rt.dtype, batch)
+        if self._adam_jobs is not None and self._adam_jobs[0] == key:
+            return self._adam_jobs[1:]
+        rec = np.dtype([("off", "<i8"), ("p01", "<u8"), ("p10", "<u8"), ("d0", "<i4"), ("d1", "<i4"), ("kk", "<i4"),
+                        ("layout", "<i4"), ("tile0", "<i4"), ("tiles_b", "<i4")])
+        assert rec.itemsize == lib.adam_job_bytes()
+        shapes = eng.conv_input_shapes(batch)            # id(op) -> (N, H, W) of the layer's input at this batch
+        convs = sorted(((store.offsets[store._index[id(op.mod.weight)]], op) for net in rt.nets for op in net.ops
+                        if isinstance(op, ConvOp)), key=lambda t: t[0])
+        rows, tile0, cur = [], 0, 0
+
+        def plain(lo, hi):
+            nonlocal tile0
+            if hi > lo:
+                rows.append((lo, 0, 0, hi - lo, 0, 1, 0, tile0, 0))
+                tile0 += (hi - lo + 2047) // 2048
+
+        for off, op in convs:
+            plain(cur, off)
+            w = op.mod.weight
+            d0, d1 = w.shape[0], w.shape[1]
+            n, h, wd = shapes[id(op)]
+            if op.kind == "ct":
+                layout = lib.convT2d_wgrad_layout(rt.dt, n, h, wd, op.cin, op.cout)
+            else:
+                layout = lib.conv2d_wgrad_layout(rt.dt, n, h, wd, op.cin, op.cout, 3 if op.kind == "c3" else 4)
+            p01, p10 = (op.pack_f, op.pack_b) if op.kind == "ct" else (op.pack_b, op.pack_f)
+            tiles_b = (d1 + 15) // 16
+            rows.append((off, p01.data_ptr(), p10.data_ptr(), d0, d1, op.kk, int(layout), tile0, tiles_b))
+            tile0 += ((d0 + 31) // 32) * tiles_b
+            cur = off + w.numel()
+        plain(cur, store.total)
+        jobs = np.array(rows, dtype=rec)
+        dev_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).to(store.flat.device)
+        self._adam_jobs = (key, dev_jobs, len(rows), tile0)
+        return self._adam_jobs[1:]
+
+    def _optim_tail(self, batch: int):
         rt, cfg, st = self.rt, self.cfg, _st()
         store = rt.store
+        if self.keep_grad:
+            self.last_grad = store.grad.clone()
         lib.fill_zero(_p(self.normacc), 8, st)
         lib.sumsq(_p(store.grad), store.grad.numel(), _p(self.normacc), st)
-        lib.clip_adam(_p(store.flat), _p(store.grad), _p(self.m), _p(self.v), store.flat.numel(), _p(self.normacc),
-                      cfg.max_norm, 1.0, cfg.lr, cfg.b1, cfg.b2, cfg.eps, _p(self.step_ptr), st)
+        if rt.fused_grads:
+            jobs, njobs, tiles = self._adam_table(batch)
+            lib.adam_multi(_p(jobs), njobs, tiles, 16, _p(store.flat), _p(store.grad), _p(self.m), _p(self.v), rt.dt,
+                           _p(self.normacc), cfg.max_norm, 1.0, cfg.lr, cfg.b1, cfg.b2, cfg.eps, _p(self.step_ptr), st)
+        else:
+            lib.clip_adam(_p(store.flat), _p(store.grad), _p(self.m), _p(self.v), store.flat.numel(), _p(self.normacc),
+                          cfg.max_norm, 1.0, cfg.lr, cfg.b1, cfg.b2, cfg.eps, _p(self.step_ptr), st)
         lib.clip_adam(_p(self.gam), _p(self.dgam), _p(self.gam_m), _p(self.gam_v), self.n_gammas, None,
                       cfg.max_norm, 1.0, cfg.lr, cfg.b1, cfg.b2, cfg.eps, _p(self.step_ptr), st)
         rt.launches += 4
-        rt.packs_dirty = True
-        rt.pack_weights()
+        if not rt.fused_grads:
+            rt.packs_dirty = True
+            rt.pack_weights()
+
+    def _sync_bn_grad_fix(self):
+        """sync_bn: every rank computed dgamma / dbeta from the GLOBAL sums, so the SUM all-reduce would count them `world`
+        times - pre-scale them by 1/world."""
+        if not (self.sync_bn and self.world > 1):
+            return
+        store = self.rt.store
+        for net in self.rt.nets:
+            for op in net.ops:
+                if isinstance(op, BNOp):
+                    store.grad_view(op.mod.weight).mul_(1.0 / self.world)
+                    store.grad_view(op.mod.bias).mul_(1.0 / self.world)
 
     # ---- data-parallel gradient exchange ---------------------------------------------------------------
     # The flat fp32 gradient is SUM-all-reduced (NCCL).  With SVRS_AR_OVERLAP=1 the part that belongs to the nets whose
@@ -147,7 +222,8 @@ class _FusedBase:
                 comm.wait_stream(side)
         segs = self._net_segments(nets)
         with torch.cuda.stream(comm):
-            rt.unpack_nets(nets)
+            if not rt.fused_grads:
+                rt.unpack_nets(nets)
             for lo, hi in segs:
                 torch.distributed.all_reduce(rt.store.grad[lo:hi], group=self.pg)
         self._early_segs = segs
@@ -155,6 +231,7 @@ class _FusedBase:
     def _allreduce_all(self):
         if self.world == 1:
             return
+        self._sync_bn_grad_fix()
         store = self.rt.store
         early = getattr(self, "_early_segs", None)
         self._early_segs = None
@@ -177,42 +254,109 @@ class _FusedBase:
         raise NotImplementedError
 
     def step(self, *inputs, use_graph: bool = False) -> torch.Tensor:
-        """One optimisation step on device-resident inputs.  Returns the device tensor
+        """One optimisation step on device-resident inputs (NCHW tensors as the reference's loaders yield them, or
+        PatchBatch objects from dataset.grid_patch_pair).  Returns the device tensor
         [mse_x, kld_u, mse_y, kld_z, loss] (Cond) / [mse, kld, 0, 0, loss] (VAE) of THIS rank's batch."""
         self._ensure_state()
         self.cfg.read(self.optimizer)
         self.steps_done += 1
         if not use_graph:
             return self._step_impl(*inputs)
-        key = tuple((tuple(t.shape), t.dtype) for t in inputs) + (self.cfg.lr, self.rt.dtype)
+        flat, rebuild = _flatten_inputs(inputs)
+        key = tuple((tuple(t.shape), t.dtype) for t in flat) + (self.cfg.lr, self.rt.dtype, "step")
         g = self._graphs.get(key)
         if g is None:
             if self.steps_done == 1:
                 # first step runs eagerly (module loading, allocator warm-up); capture on the next one
                 return self._step_impl(*inputs)
-            static_in = [torch.empty_like(t) for t in inputs]
-            for s, t in zip(static_in, inputs):
-                s.copy_(t)
+            static_in = [torch.empty_like(t) for t in flat]
+            for s_, t in zip(static_in, flat):
+                s_.copy_(t)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             l0 = self.rt.launches
             with torch.cuda.graph(graph):
-                out = self._step_impl(*static_in)
+                out = self._step_impl(*rebuild(static_in))
             g = dict(graph=graph, inputs=static_in, out=out, launches=self.rt.launches - l0)
             self._graphs[key] = g
         else:
-            for s, t in zip(g["inputs"], inputs):
-                if s.data_ptr() != t.data_ptr():
-                    s.copy_(t, non_blocking=True)
+            for s_, t in zip(g["inputs"], flat):
+                if s_.data_ptr() != t.data_ptr():
+                    s_.copy_(t, non_blocking=True)
+            self.rt.add_replayed(g["launches"])
+        g["graph"].replay()
+        return g["out"]
+
+    def step_tiles(self, *tiles, patch_size: int, use_graph: bool = True) -> torch.Tensor:
+        """One optimisation step straight from device-resident tiles (grid mode): the patch gather + normalise kernels
+        (dataset.grid_patch_pair) are part of the captured graph.  tiles = (hr,) for the VAE, (hr, lr) for Cond_SRVAE."""
+        from dataset import grid_patch_pair
+        self._ensure_state()
+        self.cfg.read(self.optimizer)
+        self.steps_done += 1
+        sizes = [patch_size, patch_size // 2][:len(tiles)]
+
+        def run(ts):
+            return self._step_impl(*[grid_patch_pair(t, p, self.rt.dtype, rt=self.rt) for t, p in zip(ts, sizes)])
+
+        if not use_graph or self.steps_done == 1:
+            return run(tiles)
+        key = tuple((tuple(t.shape), t.dtype) for t in tiles) + (self.cfg.lr, self.rt.dtype, "tiles", patch_size)
+        g = self._graphs.get(key)
+        if g is None:
+            static_in = [t.clone() for t in tiles]
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            l0 = self.rt.launches
+            with torch.cuda.graph(graph):
+                out = run(static_in)
+            g = dict(graph=graph, inputs=static_in, out=out, launches=self.rt.launches - l0)
+            self._graphs[key] = g
+        else:
+            for s_, t in zip(g["inputs"], tiles):
+                if s_.data_ptr() != t.data_ptr():
+                    s_.copy_(t, non_blocking=True)
             self.rt.add_replayed(g["launches"])
         g["graph"].replay()
         return g["out"]
 
     def static_inputs(self, *like):
         """Device buffers a caller may fill directly (avoids the extra device copy before a replay)."""
-        key = tuple((tuple(t.shape), t.dtype) for t in like) + (self.cfg.lr, self.rt.dtype)
+        flat, _ = _flatten_inputs(like)
+        key = tuple((tuple(t.shape), t.dtype) for t in flat) + (self.cfg.lr, self.rt.dtype, "step")
         g = self._graphs.get(key)
         return None if g is None else g["inputs"]
+
+
+def _flatten_inputs(inputs):
+    """(tensors | PatchBatch | None ...) -> flat tensor list + a function that rebuilds the argument tuple from a list of
+    same-shaped tensors (CUDA-graph static inputs)."""
+    flat, spec = [], []
+    for a in inputs:
+        if isinstance(a, PatchBatch):
+            ts = a.tensors()
+            spec.append(("pb", len(ts)))
+            flat.extend(ts)
+        elif a is None:
+            spec.append(("none", 0))
+        else:
+            spec.append(("t", 1))
+            flat.append(a)
+
+    def rebuild(ts):
+        out, i = [], 0
+        for kind, n in spec:
+            if kind == "pb":
+                out.append(PatchBatch(ts[i], ts[i + n - 1]))
+                i += n
+            elif kind == "none":
+                out.append(None)
+            else:
+                out.append(ts[i])
+                i += 1
+        return tuple(out)
+
+    return flat, rebuild
 
 
 class FusedCondTrainer(_FusedBase):
@@ -225,42 +369,47 @@ class FusedCondTrainer(_FusedBase):
 
     def _step_impl(self, x, y, eps_u=None, eps_z=None):
         eng, rt, st = self.eng, self.rt, _st()
-        B = x.shape[0]
         Wz, Wu = eng.Wz, eng.Wu
         lib.step_increment(_p(self.step_ptr), st)
+        rt.fused_grads = self.fused_tail
         rt.zero_grads(with_scratch=True)
         rt.scratch_prezeroed = True
         try:
-            outs, ctx = eng.forward(x, y, eps_u, eps_z, training=True, save=True, repack=False)
+            outs, ctx = eng.forward(x, y, eps_u, eps_z, training=True, save=True, repack=False, fused_io=True)
         finally:
             rt.scratch_prezeroed = False
+        xb, yb = outs["xb"], outs["yb"]
+        B = xb.B
         enc_u, enc_z = outs["enc_u"], outs["enc_z"]
-        x_hat, y_hat, mu3, lv3 = outs["x_hat"], outs["y_hat"], outs["mu3"], outs["lv3"]
-        xf, yf = x.contiguous().float(), y.contiguous().float()
+        x_hat, y_hat, mu3, lv3 = outs["x_hat_nhwc"], outs["y_hat_nhwc"], outs["mu3"], outs["lv3"]
         mu_u, lv_u = enc_u[:, :Wu], enc_u[:, Wu:]
         mu_z, lv_z = enc_z[:, :Wz], enc_z[:, Wz:]
-        terms, acc = elbo_forward(x_hat, xf, y_hat, yf, mu_u, lv_u, mu_z, lv_z, mu3, lv3, self.gam, B)
-        d_xhat, d_yhat = torch.empty_like(x_hat), torch.empty_like(y_hat)
+        # ELBO on NHWC operands: reconstruction (fp32, straight from the sigmoid tail) vs the fp32 NHWC target
+        terms, acc = elbo_forward(x_hat, xb.f32, y_hat, yb.f32, mu_u, lv_u, mu_z, lv_z, mu3, lv3, self.gam, B)
+        # gradients wrt the decoders' PRE-sigmoid outputs, NHWC in the compute dtype (no layout / activation kernels)
+        d_xhat = torch.empty(x_hat.shape, device=x_hat.device, dtype=rt.dtype)
+        d_yhat = torch.empty(y_hat.shape, device=y_hat.device, dtype=rt.dtype)
         d_enc_u, d_enc_z = torch.empty_like(enc_u), torch.empty_like(enc_z)
         d_mu3, d_lv3 = torch.empty_like(mu3), torch.empty_like(lv3)
-        lib.elbo_bwd(_p(x_hat), _p(xf), F32, x_hat.numel(), _p(d_xhat),
-                     _p(y_hat), _p(yf), F32, y_hat.numel(), _p(d_yhat),
+        lib.elbo_bwd(_p(x_hat), _p(xb.f32), F32, F32, x_hat.numel(), _p(d_xhat), rt.dt,
+                     _p(y_hat), _p(yb.f32), F32, F32, y_hat.numel(), _p(d_yhat), rt.dt,
                      _p(mu_u), _p(lv_u), 2 * Wu, Wu, d_enc_u.data_ptr(), d_enc_u.data_ptr() + 4 * Wu, 2 * Wu,
                      _p(mu_z), _p(lv_z), 2 * Wz, d_enc_z.data_ptr(), d_enc_z.data_ptr() + 4 * Wz, 2 * Wz,
                      _p(mu3), _p(lv3), Wz, Wz, _p(d_mu3), _p(d_lv3), Wz,
-                     B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), st)
+                     B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), ACT_SIGMOID, st)
         rt.launches += 3
         rt.scratch_prezeroed = True
         self._early_segs = None
         if self.world > 1 and getattr(self, "_ar_overlap", False):
             rt.after_phase1 = self._early_allreduce      # only while the fused step's backward runs
         try:
-            eng.backward(ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3)
+            eng.backward(ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3, fused_io=True)
         finally:
             rt.scratch_prezeroed = False
             rt.after_phase1 = None
         self._allreduce_all()
-        self._optim_tail()
+        self._optim_tail(B)
+        rt.fused_grads = False
         return terms
 
 
@@ -276,31 +425,35 @@ class FusedVaeTrainer(_FusedBase):
 
     def _step_impl(self, x, eps=None):
         eng, rt, st = self.eng, self.rt, _st()
-        B, Wd = x.shape[0], eng.Wd
+        Wd = eng.Wd
         lib.step_increment(_p(self.step_ptr), st)
+        rt.fused_grads = self.fused_tail
         rt.zero_grads(with_scratch=True)
         rt.scratch_prezeroed = True
         try:
-            outs, ctx = eng.forward(x, eps, training=True, save=True, repack=False)
+            outs, ctx = eng.forward(x, eps, training=True, save=True, repack=False, fused_io=True)
         finally:
             rt.scratch_prezeroed = False
-        enc, x_hat = outs["enc"], outs["x_hat"]
-        xf = x.contiguous().float()
+        xb = outs["xb"]
+        B = xb.B
+        enc, x_hat = outs["enc"], outs["x_hat_nhwc"]
         mu, lv = enc[:, :Wd], enc[:, Wd:]
-        terms, acc = elbo_forward(x_hat, xf, None, None, mu, lv, None, None, None, None, self.gam, B)
-        d_xhat, d_enc = torch.empty_like(x_hat), torch.empty_like(enc)
-        lib.elbo_bwd(_p(x_hat), _p(xf), F32, x_hat.numel(), _p(d_xhat),
-                     None, None, F32, 0, None,
+        terms, acc = elbo_forward(x_hat, xb.f32, None, None, mu, lv, None, None, None, None, self.gam, B)
+        d_xhat = torch.empty(x_hat.shape, device=x_hat.device, dtype=rt.dtype)
+        d_enc = torch.empty_like(enc)
+        lib.elbo_bwd(_p(x_hat), _p(xb.f32), F32, F32, x_hat.numel(), _p(d_xhat), rt.dt,
+                     None, None, F32, F32, 0, None, F32,
                      _p(mu), _p(lv), 2 * Wd, Wd, d_enc.data_ptr(), d_enc.data_ptr() + 4 * Wd, 2 * Wd,
                      None, None, 0, None, None, 0,
                      None, None, 0, 0, None, None, 0,
-                     B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), st)
+                     B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), ACT_SIGMOID, st)
         rt.launches += 3
         rt.scratch_prezeroed = True
         try:
-            eng.backward(ctx, d_xhat, d_enc)
+            eng.backward(ctx, d_xhat, d_enc, fused_io=True)
         finally:
             rt.scratch_prezeroed = False
         self._allreduce_all()
-        self._optim_tail()
+        self._optim_tail(B)
+        rt.fused_grads = False
         return terms

@@ -27,9 +27,9 @@ for M, C in ((524288, 64), (131072, 128), (32768, 256), (131072, 64), (8192, 512
     mb = M * C * 2 / 1e6
     t = timeit(lambda: lib.bn_stats(x.data_ptr(), BF16, M, C, sums.data_ptr(), st()))
     print(f"M={M:7d} C={C:4d}  bn_stats      {t:7.1f} us  {mb / t * 1e3 / 1e3:6.2f} TB/s")
-    t = timeit(lambda: lib.bn_apply(x.data_ptr(), y.data_ptr(), BF16, M, C, sc.data_ptr(), sh.data_ptr(), 1, st()))
+    t = timeit(lambda: lib.bn_apply(x.data_ptr(), y.data_ptr(), BF16, M, 0, C, sc.data_ptr(), sh.data_ptr(), 1, st()))
     print(f"M={M:7d} C={C:4d}  bn_apply      {t:7.1f} us  {2 * mb / t * 1e3 / 1e3:6.2f} TB/s")
-    t = timeit(lambda: lib.bn_bwd_reduce(x.data_ptr(), dy.data_ptr(), BF16, M, C, sc.data_ptr(), sh.data_ptr(), mu.data_ptr(), iv.data_ptr(), 1, sums.data_ptr(), st()))
+    t = timeit(lambda: lib.bn_bwd_reduce(x.data_ptr(), dy.data_ptr(), BF16, M, 0, C, sc.data_ptr(), sh.data_ptr(), mu.data_ptr(), iv.data_ptr(), 1, sums.data_ptr(), st()))
     print(f"M={M:7d} C={C:4d}  bn_bwd_reduce {t:7.1f} us  {2 * mb / t * 1e3 / 1e3:6.2f} TB/s")
-    t = timeit(lambda: lib.bn_bwd_apply(x.data_ptr(), dy.data_ptr(), y.data_ptr(), BF16, M, C, sc.data_ptr(), sh.data_ptr(), mu.data_ptr(), iv.data_ptr(), gam.data_ptr(), 1, sums.data_ptr(), dg.data_ptr(), db.data_ptr(), st()))
+    t = timeit(lambda: lib.bn_bwd_apply(x.data_ptr(), dy.data_ptr(), y.data_ptr(), BF16, M, 0, C, sc.data_ptr(), sh.data_ptr(), mu.data_ptr(), iv.data_ptr(), gam.data_ptr(), 1, sums.data_ptr(), dg.data_ptr(), db.data_ptr(), st()))
     print(f"M={M:7d} C={C:4d}  bn_bwd_apply  {t:7.1f} us  {3 * mb / t * 1e3 / 1e3:6.2f} TB/s")
