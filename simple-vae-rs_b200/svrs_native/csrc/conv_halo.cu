@@ -57,7 +57,7 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t saddr, int mode) {
 }
 
 // KSUB = cw / 16 = MMAs (K = 16) per tap and chunk
-template <int KSUB>
+template <int KSUB, bool EXTRA>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_constant__ HaloParams p) {
     pdl_entry();
     constexpr uint32_t ROWB = 32u * KSUB;                 // bytes of one pixel's channel chunk
@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
     const uint32_t tmem_slot = bar_base + 8u * (2 * HL_HALO_SLOTS + 2 * HL_W_SLOTS + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    __shared__ float s_bn[2 * EPI_BN_MAXC];
-    if (p.bn_sums) epi_bn_zero(s_bn);
+    __shared__ float s_bn[EXTRA ? 2 * EPI_BN_MAXC : 1];
+    if (EXTRA && p.bn_sums) epi_bn_zero(s_bn);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.in_map);
@@ -212,16 +212,19 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv3_halo_kernel(const __grid_
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
             EpiRow er;
-            er.o2 = p.out2 ? p.out2 + (long long)n * p.out2_ld + (long long)(ty * 16 + iy) * p.OW + (tx * 8 + ix) : nullptr;
-            er.hw = p.OH * p.OW;
-            er.sbn = p.bn_sums ? s_bn : nullptr;
-            epi_dispatch(p.act, taddr, p.n_tile, half, p.out ? orow : nullptr, p.bias, c_base, p.Nc, true, er);
+            er.o2 = nullptr; er.hw = 0; er.sbn = nullptr;
+            if (EXTRA) {
+                er.o2 = p.out2 ? p.out2 + (long long)n * p.out2_ld + (long long)(ty * 16 + iy) * p.OW + (tx * 8 + ix) : nullptr;
+                er.hw = p.OH * p.OW;
+                er.sbn = p.bn_sums ? s_bn : nullptr;
+            }
+            epi_dispatch<EXTRA>(p.act, taddr, p.n_tile, half, (!EXTRA || p.out) ? orow : nullptr, p.bias, c_base, p.Nc, true, er);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        if (p.bn_sums) epi_bn_flush(s_bn, p.bn_sums, p.Nc, threadIdx.x - 64, 32 * TC_EPI_WARPS);
+        if (EXTRA && p.bn_sums) epi_bn_flush(s_bn, p.bn_sums, p.Nc, threadIdx.x - 64, 32 * TC_EPI_WARPS);
     }
 
     tc_fence_before();
@@ -253,7 +256,7 @@ struct alignas(64) HaloTParams {
     double* bn_sums;                    // optional BatchNorm statistics scratch (SVRS_BN_REPLICAS x double[2*Nc])
 };
 
-template <int KSUB>
+template <int KSUB, bool EXTRA>
 __global__ void __launch_bounds__(HL_THREADS, 1) convT_halo_kernel(const __grid_constant__ HaloTParams p) {
     pdl_trigger();
     constexpr uint32_t ROWB = 32u * KSUB;
@@ -273,8 +276,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) convT_halo_kernel(const __grid_
     const uint32_t tmem_slot = bar_base + 8u * (2 * HL_HALO_SLOTS + 2 * HL_W_SLOTS + 4);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    __shared__ float s_bn[2 * EPI_BN_MAXC];
-    if (p.bn_sums) epi_bn_zero(s_bn);
+    __shared__ float s_bn[EXTRA ? 2 * EPI_BN_MAXC : 1];
+    if (EXTRA && p.bn_sums) epi_bn_zero(s_bn);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.in_map);
@@ -376,17 +379,17 @@ __global__ void __launch_bounds__(HL_THREADS, 1) convT_halo_kernel(const __grid_
 #pragma unroll 1
             EpiRow er;
             er.o2 = nullptr; er.hw = 0;
-            er.sbn = p.bn_sums ? s_bn : nullptr;
+            er.sbn = (EXTRA && p.bn_sums) ? s_bn : nullptr;
             for (int par = 0; par < 4; ++par) {
                 const uint32_t taddr = tmem_base + acc * 256u + (uint32_t)(par * p.n_tile) + ((uint32_t)(q * 32) << 16);
-                epi_dispatch(p.act, taddr, p.n_tile, half, p.out + p.out_off[par] + pix, p.bias, c_base, p.Nc, true, er);
+                epi_dispatch<EXTRA>(p.act, taddr, p.n_tile, half, p.out + p.out_off[par] + pix, p.bias, c_base, p.Nc, true, er);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        if (p.bn_sums) epi_bn_flush(s_bn, p.bn_sums, p.Nc, threadIdx.x - 64, 32 * TC_EPI_WARPS);
+        if (EXTRA && p.bn_sums) epi_bn_flush(s_bn, p.bn_sums, p.Nc, threadIdx.x - 64, 32 * TC_EPI_WARPS);
     }
 
     tc_fence_before();
@@ -417,9 +420,10 @@ int launch_convT_halo(const void* in, const void* w_nk, const float* bias, void*
                       const ConvExtra& ex, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(convT_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(convT_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(convT_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
+        cudaError_t e = cudaSuccess;
+#define SET_T(K, X) if (e == cudaSuccess) e = cudaFuncSetAttribute(convT_halo_kernel<K, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES)
+        SET_T(4, false); SET_T(2, false); SET_T(1, false); SET_T(4, true); SET_T(2, true); SET_T(1, true);
+#undef SET_T
         if (e != cudaSuccess) { set_error("convT_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
         attr_set = true;
     }
@@ -454,9 +458,11 @@ int launch_convT_halo(const void* in, const void* w_nk, const float* bias, void*
     long long total = (long long)p.tiles_x * p.tiles_y * N * p.n_tiles;
     int grid = (int)(total < num_sms() ? total : num_sms());
     if (grid < 1) return 0;
-    if (p.cw == 64) SVRS_LAUNCH((convT_halo_kernel<4>), grid, HL_THREADS, HL_SMEM_BYTES, st, p);
-    else if (p.cw == 32) SVRS_LAUNCH((convT_halo_kernel<2>), grid, HL_THREADS, HL_SMEM_BYTES, st, p);
-    else SVRS_LAUNCH((convT_halo_kernel<1>), grid, HL_THREADS, HL_SMEM_BYTES, st, p);
+    const bool extra = ex.bn_sums != nullptr;
+#define GO_T(K) do { if (extra) SVRS_LAUNCH((convT_halo_kernel<K, true>), grid, HL_THREADS, HL_SMEM_BYTES, st, p); \
+                     else SVRS_LAUNCH((convT_halo_kernel<K, false>), grid, HL_THREADS, HL_SMEM_BYTES, st, p); } while (0)
+    if (p.cw == 64) GO_T(4); else if (p.cw == 32) GO_T(2); else GO_T(1);
+#undef GO_T
     return check_launch("convT_halo_kernel");
 }
 
@@ -464,9 +470,10 @@ int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* b
                       int act, const ConvExtra& ex, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES);
+        cudaError_t e = cudaSuccess;
+#define SET_C(K, X) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_halo_kernel<K, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_BYTES)
+        SET_C(4, false); SET_C(2, false); SET_C(1, false); SET_C(4, true); SET_C(2, true); SET_C(1, true);
+#undef SET_C
         if (e != cudaSuccess) { set_error("conv3_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
         attr_set = true;
     }
@@ -498,9 +505,11 @@ int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* b
     long long total = (long long)p.tiles_x * p.tiles_y * N * p.n_tiles;
     int grid = (int)(total < num_sms() ? total : num_sms());
     if (grid < 1) return 0;
-    if (p.cw == 64) SVRS_LAUNCH((conv3_halo_kernel<4>), grid, HL_THREADS, HL_SMEM_BYTES, st, p);
-    else if (p.cw == 32) SVRS_LAUNCH((conv3_halo_kernel<2>), grid, HL_THREADS, HL_SMEM_BYTES, st, p);
-    else SVRS_LAUNCH((conv3_halo_kernel<1>), grid, HL_THREADS, HL_SMEM_BYTES, st, p);
+    const bool extra = ex.bn_sums != nullptr || ex.out2 != nullptr;
+#define GO_C(K) do { if (extra) SVRS_LAUNCH((conv3_halo_kernel<K, true>), grid, HL_THREADS, HL_SMEM_BYTES, st, p); \
+                     else SVRS_LAUNCH((conv3_halo_kernel<K, false>), grid, HL_THREADS, HL_SMEM_BYTES, st, p); } while (0)
+    if (p.cw == 64) GO_C(4); else if (p.cw == 32) GO_C(2); else GO_C(1);
+#undef GO_C
     return check_launch("conv3_halo_kernel");
 }
 

@@ -64,6 +64,7 @@ struct alignas(64) TcParams {
 };
 
 // ------------------------------------------------------------------------------------------ kernel
+template <bool EXTRA>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     pdl_entry();
     extern __shared__ uint8_t smem_raw[];
@@ -78,8 +79,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    __shared__ float s_bn[2 * EPI_BN_MAXC];
-    if (p.bn_sums) epi_bn_zero(s_bn);
+    __shared__ float s_bn[EXTRA ? 2 * EPI_BN_MAXC : 1];
+    if (EXTRA && p.bn_sums) epi_bn_zero(s_bn);
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) prefetch_tmap(&p.in_maps[i]);
@@ -198,16 +199,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
             EpiRow er;
-            er.o2 = p.out2 ? p.out2 + (long long)n * p.out2_ld + (long long)(ty * p.BH + iy) * p.OW + (tx * p.BW + ix) : nullptr;
-            er.hw = p.OH * p.OW;
-            er.sbn = p.bn_sums ? s_bn : nullptr;
-            epi_dispatch(p.act, taddr, p.n_tile, half, p.out ? orow : nullptr, p.bias, c_base, p.Nc, n < p.N, er);
+            er.o2 = nullptr; er.hw = 0; er.sbn = nullptr;
+            if (EXTRA) {
+                er.o2 = p.out2 ? p.out2 + (long long)n * p.out2_ld + (long long)(ty * p.BH + iy) * p.OW + (tx * p.BW + ix) : nullptr;
+                er.hw = p.OH * p.OW;
+                er.sbn = p.bn_sums ? s_bn : nullptr;
+            }
+            epi_dispatch<EXTRA>(p.act, taddr, p.n_tile, half, (!EXTRA || p.out) ? orow : nullptr, p.bias, c_base, p.Nc, n < p.N, er);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        if (p.bn_sums) epi_bn_flush(s_bn, p.bn_sums, p.Nc, threadIdx.x - 64, 32 * TC_EPI_WARPS);
+        if (EXTRA && p.bn_sums) epi_bn_flush(s_bn, p.bn_sums, p.Nc, threadIdx.x - 64, 32 * TC_EPI_WARPS);
     }
 
     tc_fence_before();
@@ -332,11 +336,16 @@ int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias
                    int act, const ConvExtra& ex, cudaStream_t st) {
     if (ex.bn_sums && Cw > EPI_BN_MAXC) { set_error("conv_tc: fused BatchNorm statistics need Cout <= %d", EPI_BN_MAXC); return SVRS_E_UNSUPPORTED; }
     if (ex.out2 && form == 3) { set_error("conv_tc: NCHW second output is not available for the transposed form"); return SVRS_E_UNSUPPORTED; }
+    if ((ex.out2 || ex.bn_sums) && (act == SVRS_ACT_SIGMOID || (act == SVRS_ACT_HARDTANH7 && !bias))) {
+        set_error("conv_tc: epilogue extras support no activation or bias + Hardtanh only");
+        return SVRS_E_UNSUPPORTED;
+    }
     if (halo_supported(form, Cr, Cw, W, H)) return launch_conv3_halo(form, in, w_nk, bias, out, N, H, W, Cr, Cw, act, ex, st);
     if (form == 3 && convT_halo_supported(Cr, Cw, W, H)) return launch_convT_halo(in, w_nk, bias, out, N, H, W, Cr, Cw, act, ex, st);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
         attr_set = true;
     }
@@ -398,7 +407,8 @@ int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias
     long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles * p.nprob;
     int grid = (int)(total < num_sms() ? total : num_sms());
     if (grid < 1) return 0;
-    SVRS_LAUNCH((conv_tc_kernel), grid, TC_THREADS, TC_SMEM_BYTES, st, p);
+    if (ex.out2 || ex.bn_sums) SVRS_LAUNCH((conv_tc_kernel<true>), grid, TC_THREADS, TC_SMEM_BYTES, st, p);
+    else SVRS_LAUNCH((conv_tc_kernel<false>), grid, TC_THREADS, TC_SMEM_BYTES, st, p);
     return check_launch("conv_tc_kernel");
 }
 

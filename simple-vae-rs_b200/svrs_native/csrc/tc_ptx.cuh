@@ -66,13 +66,24 @@ __device__ __forceinline__ void colsum_tile8(const __nv_bfloat16* __restrict__ g
                                              int n0, int y0, int x0, int BW, int BH, int BNI, int N, int c0,
                                              int lane, int lanes, float* acc) {
     const int npix = BW * BH * BNI;
-    for (int i = lane; i < npix; i += lanes) {
-        const int bx = i % BW, by = (i / BW) % BH, n = n0 + i / (BW * BH);
-        if (n >= N) break;
-        const uint4 r = __ldg(reinterpret_cast<const uint4*>(g + (long long)n * sn + (long long)(y0 + by) * sy + (long long)(x0 + bx) * sx + c0));
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    // four independent 16-byte loads in flight per thread (the loop used to issue one at a time: on the weight-heavy 4x4
+    // layers the few CTAs that fold the bias gradient then finished 30 us after everyone else - SVRS_WG_PROF "drain" max)
+    for (int i0 = lane; i0 < npix; i0 += 4 * lanes) {
+        uint4 r[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[2 * j] += __uint_as_float(w[j] << 16); acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u); }
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * lanes;
+            const int bx = i % BW, by = (i / BW) % BH, n = n0 + i / (BW * BH);
+            r[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < npix && n < N)
+                r[u] = __ldg(reinterpret_cast<const uint4*>(g + (long long)n * sn + (long long)(y0 + by) * sy + (long long)(x0 + bx) * sx + c0));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t w[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[2 * j] += __uint_as_float(w[j] << 16); acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u); }
+        }
     }
 }
 // fold the pixel lanes through shared memory (csum: 128 x 8 floats) and add the CTA's sums to db; t = thread 0..127
@@ -224,7 +235,9 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     return v[0];
 }
 
-template <int ACT, bool BIAS>
+// EXTRA = false is the plain epilogue (bf16 NHWC stores only); the extras live in a separate instantiation so that the
+// common path carries none of their code (measured: folding them into one body cost every launch 1.5-3 us).
+template <int ACT, bool BIAS, bool EXTRA>
 __device__ __forceinline__ void epi_chunk8(const uint32_t* v, __nv_bfloat16* dst, const float* bias, int c, int Nc, bool vec_ok,
                                            float* o2, int hw) {
     float f[8];
@@ -236,12 +249,14 @@ __device__ __forceinline__ void epi_chunk8(const uint32_t* v, __nv_bfloat16* dst
         else if (ACT == SVRS_ACT_HARDTANH7) x = fminf(fmaxf(x, -7.0f), 7.0f);
         f[e] = x;
     }
-    if (o2) {
+    if (EXTRA) {
+        if (o2) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if (c + e < Nc) o2[(long long)(c + e) * hw] = f[e];
+            for (int e = 0; e < 8; ++e)
+                if (c + e < Nc) o2[(long long)(c + e) * hw] = f[e];
+        }
+        if (dst == nullptr) return;
     }
-    if (dst == nullptr) return;
     if (vec_ok) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
         __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
@@ -257,14 +272,13 @@ __device__ __forceinline__ void epi_chunk8(const uint32_t* v, __nv_bfloat16* dst
 }
 
 // taddr: TMEM address of (this warp's lane quarter, accumulator column 0); orow: output row pointer at channel c_base
-// (nullptr: no NHWC output); er: optional extras (second output / BatchNorm statistics), see EpiRow
-template <int ACT, bool BIAS>
+// (nullptr, EXTRA only: no NHWC output); er: optional extras (second output / BatchNorm statistics), see EpiRow
+template <int ACT, bool BIAS, bool EXTRA>
 __device__ __forceinline__ void epi_rows(uint32_t taddr, int n_tile, int half, __nv_bfloat16* orow, const float* bias,
                                          int c_base, int Nc, bool row_ok, const EpiRow& er) {
     const bool vec_ok = (Nc % 8 == 0);
     const int chunks = (n_tile + 31) / 32;
     const int cbeg = half == 0 ? 0 : (chunks + 1) / 2, cend = half == 0 ? (chunks + 1) / 2 : chunks;
-    const int lane = threadIdx.x & 31;
     for (int ch = cbeg; ch < cend; ++ch) {
         const int c0 = ch * 32;
         uint32_t v[32];
@@ -275,12 +289,16 @@ __device__ __forceinline__ void epi_rows(uint32_t taddr, int n_tile, int half, _
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 const int c = c_base + c0 + j;
-                if (j < cols && c < Nc)
-                    epi_chunk8<ACT, BIAS>(v + j, orow ? orow + c0 + j : nullptr, bias, c, Nc, vec_ok, er.o2, er.hw);
+                if (j < cols && c < Nc) {
+                    if (EXTRA) epi_chunk8<ACT, BIAS, true>(v + j, orow ? orow + c0 + j : nullptr, bias, c, Nc, vec_ok, er.o2, er.hw);
+                    else epi_chunk8<ACT, BIAS, false>(v + j, orow + c0 + j, bias, c, Nc, vec_ok, nullptr, 0);
+                }
             }
         }
-        if (er.sbn) {          // warp-uniform
-            float a[32], b[32];
+        if (EXTRA && er.sbn) {          // warp-uniform
+            const int lane = threadIdx.x & 31;
+            float a[32];
+            // two passes over the chunk (sum, then sum of squares) so only v[] and one work array are live at a time
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int c = c_base + c0 + j;
@@ -290,9 +308,19 @@ __device__ __forceinline__ void epi_rows(uint32_t taddr, int n_tile, int half, _
                     if (BIAS) x += __ldg(bias + c);
                 }
                 a[j] = x;
-                b[j] = x * x;
             }
-            const float s1 = warp_colsum32(a, lane), s2 = warp_colsum32(b, lane);
+            const float s1 = warp_colsum32(a, lane);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = c_base + c0 + j;
+                float x = 0.f;
+                if (row_ok && j < cols && c < Nc) {
+                    x = __uint_as_float(v[j]);
+                    if (BIAS) x += __ldg(bias + c);
+                }
+                a[j] = x * x;
+            }
+            const float s2 = warp_colsum32(a, lane);
             const int c = c_base + c0 + lane;
             if (lane < cols && c < Nc) {
                 atomicAdd(er.sbn + c, s1);
@@ -302,14 +330,23 @@ __device__ __forceinline__ void epi_rows(uint32_t taddr, int n_tile, int half, _
     }
 }
 
+// EXTRA kernels (heads with an fp32 NCHW-flat second output, BatchNorm producers) are separate instantiations of the conv
+// kernels; the plain kernels carry none of that code, shared memory or register pressure.
+template <bool EXTRA>
 __device__ __forceinline__ void epi_dispatch(int act, uint32_t taddr, int n_tile, int half, __nv_bfloat16* orow, const float* bias,
                                              int c_base, int Nc, bool row_ok, const EpiRow& er) {
+    if (EXTRA) {        // heads (o2: no activation or bias + Hardtanh) and BatchNorm producers (no activation)
+        if (act == SVRS_ACT_HARDTANH7) epi_rows<SVRS_ACT_HARDTANH7, true, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
+        else if (bias) epi_rows<SVRS_ACT_NONE, true, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
+        else epi_rows<SVRS_ACT_NONE, false, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
+        return;
+    }
     if (bias) {
-        if (act == SVRS_ACT_SIGMOID) epi_rows<SVRS_ACT_SIGMOID, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
-        else if (act == SVRS_ACT_HARDTANH7) epi_rows<SVRS_ACT_HARDTANH7, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
-        else epi_rows<SVRS_ACT_NONE, true>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
+        if (act == SVRS_ACT_SIGMOID) epi_rows<SVRS_ACT_SIGMOID, true, false>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
+        else if (act == SVRS_ACT_HARDTANH7) epi_rows<SVRS_ACT_HARDTANH7, true, false>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
+        else epi_rows<SVRS_ACT_NONE, true, false>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
     } else {
-        epi_rows<SVRS_ACT_NONE, false>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
+        epi_rows<SVRS_ACT_NONE, false, false>(taddr, n_tile, half, orow, bias, c_base, Nc, row_ok, er);
     }
 }
 

@@ -126,12 +126,12 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad3_halo_kernel(const __grid
     } else if (nsteps > 0) {
         const int q = warp % 4;
         const int m = q * 32 + lane;
-        if (p.db && bj == 0) {           // one CTA per (pixel split, 64-channel tile of G)
+        if (p.db) {           // the b-chunk CTAs of a (pixel split, 64-channel tile of G) share the column sums: chunk bj takes every b_chunks-th step
             __shared__ float csum[128][8];
             const int t = threadIdx.x - 64, cq = t % 8, cl = t / 8;
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const long long sx = p.Ca, sy = (long long)p.OW * p.Ca, sn = (long long)p.OH * p.OW * p.Ca;
-            for (int kstep = k_begin; kstep < k_end; ++kstep) {
+            for (int kstep = k_begin + bj; kstep < k_end; kstep += p.b_chunks) {
                 int pt = kstep;
                 const int tx = pt % p.tiles_x; pt /= p.tiles_x;
                 const int ty = pt % p.tiles_y;

@@ -19,11 +19,15 @@
 
 namespace svrs {
 
-constexpr int WG_STAGES = 3;
-constexpr int WG_X_BYTES = 128 * 128 * 2;  // one M-block: 128 rows (box channels) x 128 pixels
-constexpr int WG_G_BYTES = 128 * 128 * 2;  // up to 128 channels of G x 128 pixels
-constexpr int WG_STAGE_BYTES = WG_X_BYTES + WG_G_BYTES;
-constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+// Shared memory: a ring of X slots (one M-block each: 128 box-channel rows x 128 pixels) and a ring of G slots (up to 128
+// channels x 128 pixels).  The G tile of a pixel step is loaded ONCE and stays resident while all M-blocks of the CTA's
+// group consume it (it used to travel with every X block: (group + 1) instead of 2 * group boxes per step - these layers
+// are bound by the SM's L2 ingest).
+constexpr int WG_XSLOTS = 4;
+constexpr int WG_GSLOTS = 2;
+constexpr int WG_X_BYTES = 128 * 128 * 2;
+constexpr int WG_G_BYTES = 128 * 128 * 2;
+constexpr int WG_SMEM_BYTES = WG_XSLOTS * WG_X_BYTES + WG_GSLOTS * WG_G_BYTES + 1024 + 256;
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_GROUP = 16;
 
@@ -54,11 +58,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + WG_STAGES * WG_STAGE_BYTES;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (WG_STAGES + s); };
-    const uint32_t done_bar = bar_base + 8u * (2 * WG_STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * WG_STAGES + 1);
+    const uint32_t g_base = smem_base + WG_XSLOTS * WG_X_BYTES;
+    const uint32_t bar_base = g_base + WG_GSLOTS * WG_G_BYTES;
+    auto xfull = [&](int s) { return bar_base + 8u * s; };
+    auto xempty = [&](int s) { return bar_base + 8u * (WG_XSLOTS + s); };
+    auto gfull = [&](int s) { return bar_base + 8u * (2 * WG_XSLOTS + s); };
+    auto gempty = [&](int s) { return bar_base + 8u * (2 * WG_XSLOTS + WG_GSLOTS + s); };
+    const uint32_t done_bar = bar_base + 8u * (2 * WG_XSLOTS + 2 * WG_GSLOTS);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * WG_XSLOTS + 2 * WG_GSLOTS + 1);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     long long* prof = p.prof ? p.prof + 8ll * blockIdx.x : nullptr;
@@ -68,7 +75,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         for (int i = 0; i < 4; ++i) prefetch_tmap(&p.x_maps[i]);
         prefetch_tmap(&p.g_map);
         if (p.packed) prefetch_tmap(&p.dw_map);
-        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < WG_XSLOTS; ++s) { mbar_init(xfull(s), 1); mbar_init(xempty(s), 1); }
+        for (int s = 0; s < WG_GSLOTS; ++s) { mbar_init(gfull(s), 1); mbar_init(gempty(s), 1); }
         mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -100,28 +108,31 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+            uint32_t xs = 0, xph = 0, gs = 0, gph = 0;
             for (int kstep = k_begin; kstep < k_end; ++kstep) {
                 int pt = kstep;
                 const int tx = pt % p.tiles_x; pt /= p.tiles_x;
                 const int ty = pt % p.tiles_y;
                 const int tn = pt / p.tiles_y;
                 const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = tn * p.BNI;
+                mbar_wait(gempty(gs), gph ^ 1u);
+                const uint32_t sg = g_base + gs * WG_G_BYTES;
+                mbar_expect_tx(gfull(gs), (uint32_t)g_boxes * g_box);
+                for (int gbx = 0; gbx < g_boxes; ++gbx)
+                    tma_load_4d(sg + gbx * g_box, &p.g_map, gfull(gs), nt * p.n_tile + gbx * p.cwg, x0, y0, n0);
+                if (++gs == WG_GSLOTS) { gs = 0; gph ^= 1u; }
                 for (int b = 0; b < nblk; ++b) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
-                    const uint32_t sg = sx + WG_X_BYTES;
-                    mbar_expect_tx(full_bar(stage), (uint32_t)p.bpb * x_box + (uint32_t)g_boxes * g_box);
+                    mbar_wait(xempty(xs), xph ^ 1u);
+                    const uint32_t sx = smem_base + xs * WG_X_BYTES;
+                    mbar_expect_tx(xfull(xs), (uint32_t)p.bpb * x_box);
                     for (int h = 0; h < p.bpb; ++h) {
                         int box = p.bpb * (blk0 + b) + h;
                         if (box >= p.nboxes) box = p.nboxes - 1;       // tail: duplicate (rows are ignored by the epilogue)
                         const WgTap tp = p.taps[box / p.cb_chunks];
                         const int cj = box % p.cb_chunks;
-                        tma_load_4d(sx + h * x_box, &p.x_maps[tp.map], full_bar(stage), cj * p.cwx, x0 + tp.dx, y0 + tp.dy, n0);
+                        tma_load_4d(sx + h * x_box, &p.x_maps[tp.map], xfull(xs), cj * p.cwx, x0 + tp.dx, y0 + tp.dy, n0);
                     }
-                    for (int gbx = 0; gbx < g_boxes; ++gbx)
-                        tma_load_4d(sg + gbx * g_box, &p.g_map, full_bar(stage), nt * p.n_tile + gbx * p.cwg, x0, y0, n0);
-                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                    if (++xs == WG_XSLOTS) { xs = 0; xph ^= 1u; }
                 }
             }
         }
@@ -133,33 +144,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             const uint32_t a_hi = desc_hi(16u * (uint32_t)p.cwx, p.cwx == 64 ? 2u : (p.cwx == 32 ? 4u : 6u));   // 8 pixel rows
             const uint32_t b_hi = desc_hi(16u * (uint32_t)p.cwg, p.cwg == 64 ? 2u : (p.cwg == 32 ? 4u : 6u));
             const uint32_t kadv_x16 = 2u * (uint32_t)p.cwx, kadv_g16 = 2u * (uint32_t)p.cwg;                    // 16 pixel rows, >> 4
-            uint32_t stage = 0, phase = 0;
+            uint32_t xs = 0, xph = 0, gs = 0, gph = 0;
             for (int kstep = 0; kstep < nsteps; ++kstep) {
+                mbar_wait(gfull(gs), gph);
+                const uint32_t b0 = desc_lo(g_base + gs * WG_G_BYTES, g_box);
                 for (int b = 0; b < nblk; ++b) {
-                    mbar_wait(full_bar(stage), phase);
+                    mbar_wait(xfull(xs), xph);
                     tc_fence_after();
                     if (prof && kstep == 0 && b == 0) prof[2] = clock64();
-                    const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
-                    const uint32_t a0 = desc_lo(sx, x_box), b0 = desc_lo(sx + WG_X_BYTES, g_box);
+                    const uint32_t a0 = desc_lo(smem_base + xs * WG_X_BYTES, x_box);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(b * p.n_tile);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)     // 8 x (K = 16 pixels)
                         tc_mma_lohi(d_tmem, a0 + kadv_x16 * k, a_hi, b0 + kadv_g16 * k, b_hi, idesc, k ? 1u : (uint32_t)(kstep != 0));
-                    tc_commit(empty_bar(stage));
+                    tc_commit(xempty(xs));
+                    if (b == nblk - 1) tc_commit(gempty(gs));      // every M-block of the group has consumed this G tile
                     if (kstep == nsteps - 1 && b == nblk - 1) { tc_commit(done_bar); if (prof) prof[3] = clock64(); }
-                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                    if (++xs == WG_XSLOTS) { xs = 0; xph ^= 1u; }
                 }
+                if (++gs == WG_GSLOTS) { gs = 0; gph ^= 1u; }
             }
         }
     } else if (nsteps > 0) {
         const int q = warp % 4;
         const int m = q * 32 + lane;
-        if (p.db && grp == 0) {          // one CTA per (pixel split, column tile) sums its G tiles while the MMAs run
+        if (p.db) {          // the CTAs of a (pixel split, column tile) share its G tiles' column sums: group g takes every ngroups-th step
             __shared__ float csum[128][8];
             const int cg = p.n_tile / 8, lanes = 128 / cg;
             const int t = threadIdx.x - 64, cq = t % cg, cl = t / cg;
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int kstep = k_begin; kstep < k_end; ++kstep) {
+            for (int kstep = k_begin + grp; kstep < k_end; kstep += p.ngroups) {
                 int pt = kstep;
                 const int tx = pt % p.tiles_x; pt /= p.tiles_x;
                 const int ty = pt % p.tiles_y;
@@ -295,7 +309,14 @@ static int wg_plan(const TapGeom& g, int KK, WgParams& p) {
     p.ntaps = pb.ntaps;
     p.nboxes = pb.ntaps * p.cb_chunks;
     p.nblocks = (p.nboxes + p.bpb - 1) / p.bpb;
-    p.group = 512 / p.n_tile;
+    // M-blocks per CTA: as many accumulator blocks as TMEM holds (512 / n_tile columns).  MEASURED (SVRS_WG_GROUP A/B,
+    // SVRS_WG_PROF): on the 4x4 / 8x8 maps the TMA-reduce epilogue (group x 64 KB per CTA at ~20 B/clk/SM, the chip's
+    // fp32 L2-reduction rate) is 2-4x longer than the MMA phase, yet ONE block per CTA (a quarter of the reduction traffic,
+    // same operand loads) was 1.5x SLOWER overall (wgrad_tc 1.04 -> 1.53 ms per step): twice the CTAs, each paying the
+    // ~2 us first-load latency, and multi-wave grids on the 1024->512 layers.
+    static const int group_env = [] { const char* e = getenv("SVRS_WG_GROUP"); return e ? atoi(e) : 0; }();
+    p.group = group_env > 0 ? group_env : 512 / p.n_tile;
+    if (p.group > 512 / p.n_tile) p.group = 512 / p.n_tile;
     if (p.group > WG_MAX_GROUP) p.group = WG_MAX_GROUP;
     if (p.group > p.nblocks) p.group = p.nblocks;
     p.ngroups = (p.nblocks + p.group - 1) / p.group;
