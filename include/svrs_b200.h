@@ -279,6 +279,38 @@ int svrs_patch_gather_normalize(const void* tiles, int src_is_i16, int T, int C,
                                 const int32_t* origins, int npatch, float* out_nchw_f32, float* out_nhwc_f32,
                                 void* out_nhwc_bf16, void* stream);
 
+/* ---- inference: Cond_SRVAE.sample (cond_vae.py:299-318) + the uncertainty statistics of BaseVAE.task
+ *      (models/base.py:305-313, 341) - BASELINE config 5, SURVEY 8.4 rows a14 / f4 (csrc/sample_stats.cu).
+ * svrs_sample_latents: the S posterior-predictive draws of each of B patches,
+ *      z(b, s) = mu3[b] + eps(b, s) * exp(0.5 * lv3[b])            (cond_vae.py:305-310)
+ *   written together with y_to_z(y) as the decoder_x input rows (torch.cat((y_enc, z), dim=1), cond_vae.py:272):
+ *      stack[(b*S + s)][0:Wz] = yflat[b][0:Wz] ; stack[(b*S + s)][Wz:2Wz] = z(b, s)        (fp32, NCHW-flat order)
+ *   mu3 / lv3 rows have stride ld3, yflat rows stride ldy.  eps [B*S][Wz] fp32 or NULL = on-device Philox4x32-10 with the
+ *   counter layout of svrs_reparam_fwd (row = sample_offset + b*S + s). */
+int svrs_sample_latents(const float* mu3, const float* lv3, int64_t ld3, const float* yflat, int64_t ldy,
+                        const float* eps, float* stack, int B, int S, int Wz, uint64_t seed, int stream_id,
+                        uint64_t sample_offset, const int64_t* step_ptr, void* stream);
+/* svrs_sample_tail_stats: the LAST decoder_x layer (nn.Conv2d(16, 4, 3, padding=1) + nn.Sigmoid, cond_vae.py:79-80) over
+ * the S draws of every patch, x [B*S][H][W][16] (dtype) -> x_hat(b, s) [4][H][W], with the per-pixel statistics of task()
+ * accumulated while the draws are produced (streaming Welford over s; partial ranges of s merged with Chan's formula), so
+ * the [S, 4, P, P] sample stack of models/base.py:303 never reaches HBM:
+ *      mean_nchw [B][4][H][W] = samples.mean(dim=0)                                   (base.py:307)
+ *      std_map   [B][H][W]    = samples.std(dim=0).mean(axis=0)   (unbiased)          (base.py:308)
+ *      mae_map   [B][H][W]    = (samples - target).abs().mean(dim=(0, 1))             (base.py:309)
+ *      mse_map   [B][H][W]    = (samples - target).pow(2).mean(dim=(0, 1))            (base.py:310)
+ *      bias_map  [B][H][W]    = (target - samples.mean(dim=0)).mean(dim=0)            (base.py:341)
+ *      sample0_nchw [B][4][H][W] = samples[0]                                          (base.py:318)
+ * w_kn = p10 pack [9][16][4] of the layer (dtype), bias fp32[4] or NULL, target_nhwc fp32 [B][H][W][4] or NULL (then only
+ * mean / std / sample0 are produced).  Every output pointer may be NULL.  splits in [1, S] (svrs_sample_tail_splits gives
+ * the default); scratch = svrs_sample_tail_scratch_floats(B, H, W, splits) floats.  Returns SVRS_E_UNSUPPORTED unless
+ * (Cin, Cout) == (16, 4). */
+int svrs_sample_tail_splits(int B, int S, int H, int W);
+int64_t svrs_sample_tail_scratch_floats(int B, int H, int W, int splits);
+int svrs_sample_tail_stats(const void* x, int dtype, const void* w_kn, const float* bias, const float* target_nhwc,
+                           int B, int S, int H, int W, int Cin, int Cout, int splits, float* scratch,
+                           float* mean_nchw, float* std_map, float* mae_map, float* mse_map, float* bias_map,
+                           float* sample0_nchw, void* stream);
+
 /* ---- backward of the fused epilogue activations from their OUTPUT y:
  *      sigmoid: dx = dy*y*(1-y) ; hardtanh(-7,7): dx = dy if -7 < y < 7 else 0.  In-place (dx == dy) allowed. */
 int svrs_act_bwd(const void* y, const void* dy, void* dx, int dtype, int act, int64_t n, void* stream);

@@ -61,6 +61,8 @@ class ModelCheckpoint(Callback):
         return False
 
     def _save(self, model, name):
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_rank() != 0:
+            return                                  # data parallel: the replicas are identical, rank 0 writes the file
         os.makedirs(self.save_path, exist_ok=True)
         torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, os.path.join(self.save_path, name))
 

@@ -187,59 +187,160 @@ class TilePrefetcher:
             free[slot] = ev
 
 
+def _dist_info():
+    """(rank, world) of the default process group, (0, 1) outside torch.distributed."""
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
 class GridPatchLoader:
     """Iterates tile batches and emits (y, x) patch batches produced on the device - the on-device equivalent
-    of DataLoader(Sen2VenDataset(crop="grid"), collate_fn=grid_collate)."""
+    of DataLoader(Sen2VenDataset(crop="grid"), collate_fn=grid_collate).
+
+    Data parallel (rank, world): every rank walks the SAME shuffled tile order (same seed) and takes its contiguous share
+    (svrs_native.parallel.shard_bounds) of each GLOBAL batch of `tiles_per_batch` tiles; a ragged last global batch that
+    cannot give every rank a tile is dropped, so all ranks run the same number of steps.  `sample_offset` of the batch most
+    recently yielded = global index of this rank's first patch inside the global batch (Philox eps keyed by global sample)."""
 
     def __init__(self, tiles: TileDataset, tiles_per_batch: int, patch_size: int, device="cuda", shuffle: bool = False,
-                 seed: int = 0):
+                 seed: int = 0, rank: int = 0, world: int = 1):
         self.ds, self.tpb, self.P, self.device, self.shuffle = tiles, tiles_per_batch, patch_size, torch.device(device), shuffle
         self._gen = torch.Generator().manual_seed(seed)
+        self.rank, self.world = rank, world
+        self.sample_offset = 0
+        self.global_batch = 0
+        if tiles_per_batch % world:
+            raise ValueError(f"GridPatchLoader: {tiles_per_batch} tiles per global batch do not split evenly over {world} ranks")
 
-    def __len__(self):
-        return (len(self.ds) + self.tpb - 1) // self.tpb
-
-    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+    def _global_batches(self):
         n = len(self.ds)
         order = torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
+        out = [order[i:i + self.tpb] for i in range(0, n, self.tpb)]
+        # equal shards on every rank (the KL terms are batch MEANS scaled by 1/world, SURVEY Q2): trim each global batch
+        # to a multiple of the world size
+        out = [b[:len(b) // self.world * self.world] for b in out]
+        return [b for b in out if len(b)]
+
+    def __len__(self):
+        n = len(self.ds)
+        full, tail = divmod(n, self.tpb)
+        return full + (1 if tail >= self.world else 0)
+
+    def _shard(self, idx):
+        from svrs_native.parallel import shard_bounds
+        lo, hi = shard_bounds(len(idx), self.rank, self.world)
+        per_tile = (self.ds.hr.shape[-1] // self.P) ** 2
+        return idx[lo:hi], lo * per_tile, len(idx) * per_tile
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        batches = [self._shard(idx) for idx in self._global_batches()]
         if self.ds.lr.is_cuda:
-            for i in range(0, n, self.tpb):
-                idx = order[i:i + self.tpb]
+            for idx, off, gb in batches:
+                self.sample_offset, self.global_batch = off, gb
                 yield grid_batch(self.ds.lr[idx.to(self.ds.lr.device)], self.ds.hr[idx.to(self.ds.hr.device)], self.P)
             return
+        if not batches:
+            return
+        full_len = len(batches[0][0])
 
-        def host_batches():
-            full = [order[i:i + self.tpb] for i in range(0, n, self.tpb)]
-            for idx in full:
-                lr_h, hr_h = self.ds.lr[idx], self.ds.hr[idx]
-                if len(idx) == self.tpb:                    # constant-shape batches go through pinned staging
-                    lr_h, hr_h = lr_h.pin_memory(), hr_h.pin_memory()
-                yield lr_h, hr_h
+        def host_batches(items):
+            for idx, _, _ in items:
+                yield self.ds.lr[idx].pin_memory(), self.ds.hr[idx].pin_memory()
 
-        tail = n % self.tpb
-        batches = list(host_batches()) if tail else None
-        if tail:                                            # ragged last batch: plain copy (shape differs from the buffers)
-            for lr_h, hr_h in TilePrefetcher(batches[:-1], self.device):
-                yield grid_batch(lr_h, hr_h, self.P)
-            lr_h, hr_h = batches[-1]
-            yield grid_batch(lr_h.to(self.device), hr_h.to(self.device), self.P)
-        else:
-            for lr_d, hr_d in TilePrefetcher(host_batches(), self.device):
-                yield grid_batch(lr_d, hr_d, self.P)
+        # constant-shape batches go through the pinned, double-buffered prefetcher; a ragged last batch is a plain copy
+        ragged = len(batches[-1][0]) != full_len
+        head = batches[:-1] if ragged else batches
+        for (idx, off, gb), (lr_d, hr_d) in zip(head, TilePrefetcher(host_batches(head), self.device)):
+            self.sample_offset, self.global_batch = off, gb
+            yield grid_batch(lr_d, hr_d, self.P)
+        if ragged:
+            idx, off, gb = batches[-1]
+            self.sample_offset, self.global_batch = off, gb
+            yield grid_batch(self.ds.lr[idx].to(self.device), self.ds.hr[idx].to(self.device), self.P)
 
 
-def init_dataloader(dataset: str, batch_size: int = 16, patch_size: int = 64, device="cuda", n_tiles: int = 64):
-    """Same entry point as the reference (dataset.py:13-47).  `synthetic` builds in-memory tiles and grid-patches
-    them on the device (batch_size counts PATCHES, as in the reference's grid mode); the Sen2Venus / flood
-    datasets need the reference's GeoTIFF readers, which are outside this build's scope."""
+class RandomCropLoader:
+    """On-device equivalent of the reference's DEFAULT loader, DataLoader(Sen2VenDataset(crop="random"), batch_size, shuffle)
+    (dataset.py:13-47, 140-218): every epoch visits each tile once, one random same-origin LR / HR crop per tile
+    (LR at (top, left), HR at (2*top, 2*left), dataset.py:205-216), `batch_size` crops per batch, each crop min-max
+    normalised per channel (utils.py:4-23).  The tile pool is resident in HBM (one upload); crops are gathered by TMA
+    (svrs_patch_gather_normalize), no CPU slicing and no H2D copy per step.
+
+    Data parallel: all ranks draw the SAME tile order and crop origins (same seed) for the global batch and keep their
+    contiguous share, so the union over ranks is exactly the single-process batch (`drop_last` semantics for a global
+    batch smaller than the world size)."""
+
+    def __init__(self, tiles: TileDataset, batch_size: int, patch_size: int, device="cuda", shuffle: bool = True, seed: int = 0,
+                 rank: int = 0, world: int = 1):
+        self.P, self.bs, self.device, self.shuffle = patch_size, batch_size, torch.device(device), shuffle
+        self.lr = tiles.lr.to(self.device).contiguous()
+        self.hr = tiles.hr.to(self.device).contiguous()
+        self._gen = torch.Generator().manual_seed(seed)
+        self.rank, self.world = rank, world
+        self.sample_offset = 0
+        self.global_batch = 0
+        if batch_size % world:
+            raise ValueError(f"RandomCropLoader: a global batch of {batch_size} crops does not split evenly over {world} ranks")
+
+    def _global_batches(self):
+        n = self.lr.shape[0]
+        order = torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
+        return [order[i:i + self.bs] for i in range(0, n, self.bs)]
+
+    def __len__(self):
+        full, tail = divmod(self.lr.shape[0], self.bs)
+        return full + (1 if tail >= self.world else 0)
+
+    def plan(self):
+        """One epoch as a list of (origins int32 [n_local, 3] = (tile, top, left) on the LR grid, sample_offset, global batch
+        size) - pure host logic (the draws), shared by __iter__ and the CPU tests."""
+        from svrs_native.parallel import shard_bounds
+        lr_size = self.lr.shape[-1]
+        out = []
+        for idx in self._global_batches():
+            o = random_crop_origins(len(idx), lr_size, self.P, self._gen)      # draws for the WHOLE global batch
+            o[:, 0] = idx.to(torch.int32)
+            n = len(idx) // self.world * self.world      # equal shards on every rank (see GridPatchLoader): trim AFTER the
+            if n == 0:                                   # draws, so the draws do not depend on the world size
+                continue
+            lo, hi = shard_bounds(n, self.rank, self.world)
+            out.append((o[lo:hi].contiguous(), lo, n))
+        return out
+
+    def __iter__(self):
+        for o, lo, n in self.plan():
+            self.sample_offset, self.global_batch = lo, n
+            (y, _), (x, _) = random_crop_batch(self.lr, self.hr, self.P, o, torch.float32)
+            yield y, x
+
+
+def init_dataloader(dataset: str, batch_size: int = 16, patch_size: int = 64, device="cuda", n_tiles: int = 64,
+                    crop: str = "random", seed: int = 0):
+    """Same entry point as the reference (dataset.py:13-47): returns (train_loader, val_loader), 80 / 20 split, batches
+    are (y, x) = (LR, HR) patch tensors.  `crop="random"` (the reference's only reachable mode, dataset.py:24): batch_size
+    counts crops, exactly as in the reference; `crop="grid"`: every tile yields its (256/P)^2 grid patches and batch_size
+    (in patches) is rounded DOWN to whole tiles (at least one).  Under torchrun the loaders shard every global batch by
+    rank (see the loader classes).  `synthetic` builds in-memory multispectral tiles; the Sen2Venus / flood datasets need
+    the reference's GeoTIFF readers (tifffile / polars, not installed here and outside the hot-path scope): decode tiles
+    with the reference's reader and wrap them in TileDataset + RandomCropLoader."""
     if dataset != "synthetic":
         raise NotImplementedError(
             f"dataset '{dataset}': GeoTIFF decoding (tifffile/polars) is outside the hot-path scope of svrs_b200; "
             "decode tiles with the reference's reader and wrap them in TileDataset, or use --dataset synthetic")
-    per_tile = (256 // patch_size) ** 2
-    tpb = max(1, batch_size // per_tile)
+    rank, world = _dist_info()
     lr, hr = synthetic_tiles(n_tiles)
     split = max(1, int(0.8 * n_tiles))
-    train = GridPatchLoader(TileDataset(lr[:split], hr[:split]), tpb, patch_size, device, shuffle=True)
-    val = GridPatchLoader(TileDataset(lr[split:], hr[split:]), tpb, patch_size, device)
+    tr_ds, va_ds = TileDataset(lr[:split], hr[:split]), TileDataset(lr[split:], hr[split:])
+    if crop == "random":
+        train = RandomCropLoader(tr_ds, batch_size, patch_size, device, shuffle=True, seed=seed, rank=rank, world=world)
+        val = RandomCropLoader(va_ds, batch_size, patch_size, device, shuffle=False, seed=seed + 1)   # validation is replicated
+        return train, val
+    if crop != "grid":
+        raise ValueError(f"crop must be 'random' or 'grid', got {crop!r}")
+    per_tile = (256 // patch_size) ** 2
+    tpb = max(1, batch_size // per_tile)
+    tpb = (tpb + world - 1) // world * world          # whole tiles on every rank
+    train = GridPatchLoader(tr_ds, tpb, patch_size, device, shuffle=True, seed=seed, rank=rank, world=world)
+    val = GridPatchLoader(va_ds, max(1, batch_size // per_tile), patch_size, device)
     return train, val

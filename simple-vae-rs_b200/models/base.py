@@ -125,8 +125,14 @@ class BaseVAE(nn.Module, metaclass=abc.ABCMeta):
         start_epoch = kwargs.get("start_epoch", 1)
         val_metrics_every = kwargs.get("val_metrics_every", float("inf"))
         first, _ = next(iter(train_loader))
+        # data parallel (torchrun, one process per GPU): the loaders shard every global batch by rank (dataset.py), the fused
+        # trainer SUM-all-reduces the gradients; logging / checkpoint files belong to rank 0, stop decisions are agreed on
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        rank = torch.distributed.get_rank() if dist_on else 0
+        world = torch.distributed.get_world_size() if dist_on else 1
+        self.rank, self.world = rank, world
         try:
-            self.wandb_run = wandb.init(
+            self.wandb_run = _NullRun() if rank != 0 else wandb.init(
                 project=self.__class__.__name__,
                 name=f"Latent-{self.latent_size}-Patch-{self.patch_size}-SLURM-{kwargs.get('slurm_job_id', 'local')}",
                 entity="ebardet-isae-supaero",
@@ -150,7 +156,7 @@ class BaseVAE(nn.Module, metaclass=abc.ABCMeta):
         for epoch in range(start_epoch, epochs + 1):
             self.current_epoch = epoch
             for cb in self.callbacks:
-                if cb.on_epoch_begin(epoch=epoch, optimizer=optimizer, device=device, model=self):
+                if self._agree(cb.on_epoch_begin(epoch=epoch, optimizer=optimizer, device=device, model=self), device):
                     print(f"Stopping training before epoch {epoch} due to {cb.__class__.__name__} condition.")
                     return
             self.train()
@@ -158,6 +164,8 @@ class BaseVAE(nn.Module, metaclass=abc.ABCMeta):
             train_loss = 0.0
             for batch in train_loader:
                 if fused is not None:
+                    # Philox eps is keyed by the GLOBAL sample index: this rank's first sample inside the global batch
+                    fused.eng.rng.sample_offset = getattr(train_loader, "sample_offset", rank * batch[0].shape[0])
                     loss, terms = self.fused_train_step(batch, device, fused)
                 else:
                     optimizer.zero_grad()
@@ -197,7 +205,7 @@ class BaseVAE(nn.Module, metaclass=abc.ABCMeta):
                 self.scheduler.step(val_loss)
             self.log(self.wandb_run, val_terms_dict, step=epoch)
             for cb in self.callbacks:
-                if cb.on_epoch_end(epoch=epoch, optimizer=optimizer, device=device, model=self, logs=val_terms_dict):
+                if self._agree(cb.on_epoch_end(epoch=epoch, optimizer=optimizer, device=device, model=self, logs=val_terms_dict), device):
                     print(f"Stopping training after epoch {epoch} due to {cb.__class__.__name__} condition.")
                     return
             print(f"Epoch {epoch}/{epochs}, Train Loss: {train_loss:.4f}, Val Loss: {val_loss:.4f}")
@@ -207,6 +215,15 @@ class BaseVAE(nn.Module, metaclass=abc.ABCMeta):
 
     def fused_train_step(self, batch, device, fused):
         raise NotImplementedError
+
+    def _agree(self, stop, device) -> bool:
+        """A callback's stop decision, made identical on every rank (any rank that wants to stop stops all)."""
+        stop = bool(stop)
+        if getattr(self, "world", 1) > 1:
+            t = torch.tensor([int(stop)], device=device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            stop = bool(int(t))
+        return stop
 
     # ------------------------------------------------------------------ abstract interface (base.py:187-291)
     @abc.abstractmethod
@@ -256,18 +273,28 @@ class BaseVAE(nn.Module, metaclass=abc.ABCMeta):
         results_dir = os.path.join("results", f"{self.slurm_job_id}_CRx{self.cr}")
         os.makedirs(results_dir, exist_ok=True)
         pred, target = self.get_task_data(val_loader)
-        with torch.no_grad():
-            draws = self.sample(pred, samples=samples)
-        diff = draws - target
-        stats = {
-            "mean": draws.mean(dim=0).cpu(),
-            "std": draws.std(dim=0).mean(dim=0).cpu(),
-            "mae": diff.abs().mean(dim=(0, 1)).cpu(),
-            "mse": diff.pow(2).mean(dim=(0, 1)).cpu(),
-            "mean_bias": (target - draws.mean(dim=0)).mean(dim=0).mean(dim=0).cpu(),
-            "target": target.cpu(),
-            "sample0": draws[0].cpu(),
-        }
+        if hasattr(self, "sample_stats"):
+            # fused path: the statistics are accumulated inside the decoder tail kernel while the draws
+            # are produced; the [S,4,P,P] sample stack of base.py:303 is never materialised
+            with torch.no_grad():
+                st = self.sample_stats(pred, samples=samples, target=target)
+            stats = {"mean": st["mean"][0].cpu(), "std": st["std"][0].cpu(), "mae": st["mae"][0].cpu(), "mse": st["mse"][0].cpu(),
+                     "mean_bias": st["mean_bias"][0].cpu(), "target": target.cpu(), "sample0": st["sample0"][0].cpu()}
+            mmse = stats["mse"].mean()          # == (samples - target).pow(2).mean()   (base.py:346)
+        else:
+            with torch.no_grad():
+                draws = self.sample(pred, samples=samples)
+            diff = draws - target
+            stats = {
+                "mean": draws.mean(dim=0).cpu(),
+                "std": draws.std(dim=0).mean(dim=0).cpu(),
+                "mae": diff.abs().mean(dim=(0, 1)).cpu(),
+                "mse": diff.pow(2).mean(dim=(0, 1)).cpu(),
+                "mean_bias": (target - draws.mean(dim=0)).mean(dim=0).mean(dim=0).cpu(),
+                "target": target.cpu(),
+                "sample0": draws[0].cpu(),
+            }
+            mmse = diff.pow(2).mean()
         torch.save(stats, os.path.join(results_dir, "error_mean_std_maps.pt"))
         try:
             import matplotlib
@@ -289,6 +316,5 @@ class BaseVAE(nn.Module, metaclass=abc.ABCMeta):
             plt.close()
         except Exception:
             pass
-        mmse = diff.pow(2).mean()
         print(f"MMSE: {mmse:.4f}")
         return stats

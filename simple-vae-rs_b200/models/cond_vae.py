@@ -95,7 +95,7 @@ class Cond_SRVAE(BaseVAE):
         enc = torch.cat((mu.float(), logvar.float()), dim=1).contiguous()
         z = torch.empty((B, Wd), device=mu.device, dtype=torch.float32)
         self._free_draws = getattr(self, "_free_draws", 0) + 1
-        reparam_fwd(eng.rt, enc, None, z, Wd, B, Wd, RngState(seed=eng.rng.seed + 7919 * self._free_draws), 3)
+        reparam_fwd(eng.rt, enc, None, z, Wd, B, Wd, RngState(seed=eng.rng.key() + 7919 * self._free_draws), 3)
         return z
 
     def _subnet(self, name, t, chw):
@@ -163,6 +163,12 @@ class Cond_SRVAE(BaseVAE):
     def sample(self, y, samples=1000, eps_u=None, eps_s=None) -> torch.Tensor:
         """cond_vae.py:299-318: `samples` decodes of one LR patch; y_to_z is computed once, eps on device."""
         return self._engine().sample(y, samples, eps_u, eps_s, training=self.training)
+
+    def sample_stats(self, y, samples=1000, target=None, eps_u=None, eps_s=None, splits=0):
+        """The per-pixel uncertainty statistics task() derives from `samples` posterior draws (models/base.py:305-313, 341)
+        for a batch of LR patches, accumulated in the decoder tail kernel (streaming Welford): the [S,4,P,P] draws are never
+        written to memory.  -> dict(mean [B,4,P,P], std, mae, mse, mean_bias [B,P,P], sample0 [B,4,P,P])."""
+        return self._engine().sample_stats(y, samples, target, eps_u, eps_s, training=self.training, splits=splits)
 
     def generation(self):
         """cond_vae.py:320-324."""

@@ -77,7 +77,7 @@ class VAE(BaseVAE):
         enc = torch.cat((mu.float(), logvar.float()), dim=1).contiguous()
         z = torch.empty((B, Wd), device=mu.device, dtype=torch.float32)
         self._free_draws = getattr(self, "_free_draws", 0) + 1
-        reparam_fwd(eng.rt, enc, None, z, Wd, B, Wd, RngState(seed=eng.rng.seed + 7919 * self._free_draws), 3)
+        reparam_fwd(eng.rt, enc, None, z, Wd, B, Wd, RngState(seed=eng.rng.key() + 7919 * self._free_draws), 3)
         return z
 
     def decode(self, z):

@@ -37,7 +37,7 @@ struct alignas(64) HaloParams {
     const float* bias;
     int N, OH, OW, tiles_x, tiles_y;
     int Nc, n_tile, n_tiles, kchunks;
-    int act, resident, base_off_mode;
+    int act, resident;
     int cw;                         // channels per chunk: 64 / 32 / 16 (SWIZZLE_128B / 64B / 32B rows of 2*cw bytes)
     int hy[9], hx[9], wtap[9];      // tap -> halo offset (dy+1, dx+1) and packed-weight tap index
     float* out2;                    // optional fp32 NCHW-flat second output (EpiRow), per-sample stride out2_ld
@@ -400,8 +400,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) convT_halo_kernel(const __grid_
     }
 }
 
-static int g_halo_mode = 1;   // 0 = off, 1 = on (base-offset field 0), 2 = on WITH base-offset field (hardware experiment: wrong)
-void set_halo_mode(int m) { g_halo_mode = m; }
+static int g_halo_mode = 1;   // 0 = off (per-tap TMA kernels), 1 = on
+void set_halo_mode(int m) { g_halo_mode = m != 0; }
 int get_halo_mode() { return g_halo_mode; }
 int make_w_map_pub(CUtensorMap* m, const void* base, int K, int Nc, int taps, int n_tile, int cw);
 
@@ -490,7 +490,6 @@ int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* b
     p.act = act;
     p.out2 = ex.out2; p.out2_ld = ex.out2_ld; p.bn_sums = ex.bn_sums;
     p.resident = (9 * p.kchunks * p.n_tile * 2 * p.cw <= HL_W_RESIDENT_MAX) ? 1 : 0;
-    p.base_off_mode = g_halo_mode == 2 ? 1 : 0;
     for (int ky = 0; ky < 3; ++ky)
         for (int kx = 0; kx < 3; ++kx) {
             int t = ky * 3 + kx;

@@ -73,16 +73,20 @@ __global__ void __launch_bounds__(256) grid_patch_kernel(const TS* __restrict__ 
 }
 
 // ---- TMA gather ---------------------------------------------------------------------------------------------------
+// TMA fact (measured, tools/dbg/crop_probe.py): the box start must be 16-byte aligned in GLOBAL memory, i.e. the innermost
+// coordinate times the element size must be a multiple of 16 (an odd `left` raises "illegal instruction"); outer coordinates
+// are free.  Random crops therefore fetch the aligned superset box [left & ~(16/es - 1), + P + 16/es) and skip the first
+// left % (16/es) columns of every shared-memory row; columns past the tile edge are zero-filled by TMA and never read.
 struct alignas(64) PatchParams {
-    CUtensorMap map;            // tiles as (S, S, T*C), box (P, R, C)
+    CUtensorMap map;            // tiles as (S, S, T*C), box (PW, R, C); PW = P (grid mode) or P + 16/es (random crops)
     const int* origins;         // [npatch][3] = (tile, top, left) or NULL (grid mode)
     float* out_nchw;            // [npatch][C][P][P] or NULL
     float* out_nhwc;            // [npatch][P][P][C] or NULL
     __nv_bfloat16* out_nhwc_bf16;
-    int C, S, P, R, nstrips, per_side;
+    int C, S, P, R, nstrips, per_side, PW, amask;
 };
 
-template <typename TS>
+template <typename TS, bool PADDED>
 __global__ void __launch_bounds__(256) patch_tma_kernel(const __grid_constant__ PatchParams p) {
     pdl_entry();
     extern __shared__ uint8_t smem_raw[];
@@ -110,13 +114,19 @@ __global__ void __launch_bounds__(256) patch_tma_kernel(const __grid_constant__ 
     }
     if (threadIdx.x < MAXC) { s_mn[threadIdx.x] = INFINITY; s_mx[threadIdx.x] = -INFINITY; }
     __syncthreads();
-    const uint32_t strip_bytes = (uint32_t)C * R * P * sizeof(TS);
+    const int PW = PADDED ? p.PW : P;                      // shared-memory row pitch (elements)
+    const int left_al = PADDED ? (left & ~p.amask) : left;
+    const int coff = left - left_al;                       // first wanted column inside a staged row
+    const uint32_t strip_bytes = (uint32_t)C * R * PW * sizeof(TS);
     const int strip_pix = R * P;
+    const int plane = R * PW;                              // staged elements per channel
+    // staged index of patch pixel i (row-major inside the strip)
+    auto sidx = [&](int i) { return PADDED ? (i / P) * PW + (i % P) + coff : i; };
     uint32_t phase = 0;
     auto load_strip = [&](int s) {
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar, strip_bytes);
-            tma_load_3d(sbase, &p.map, bar, left, top + s * R, tile * C);
+            tma_load_3d(sbase, &p.map, bar, left_al, top + s * R, tile * C);
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -127,9 +137,9 @@ __global__ void __launch_bounds__(256) patch_tma_kernel(const __grid_constant__ 
         load_strip(s);
         for (int c = 0; c < C; ++c) {
             float mn = INFINITY, mx = -INFINITY;
-            const TS* cb = sdata + (size_t)c * strip_pix;
+            const TS* cb = sdata + (size_t)c * plane;
             for (int i = threadIdx.x; i < strip_pix; i += 256) {
-                const float v = (float)cb[i];
+                const float v = (float)cb[sidx(i)];
                 mn = fminf(mn, v);
                 mx = fmaxf(mx, v);
             }
@@ -158,10 +168,11 @@ __global__ void __launch_bounds__(256) patch_tma_kernel(const __grid_constant__ 
             const float d0 = (s_mx[0] - mn0) + 1e-5f, d1 = (s_mx[1] - mn1) + 1e-5f, d2 = (s_mx[2] - mn2) + 1e-5f, d3 = (s_mx[3] - mn3) + 1e-5f;
             for (int i = threadIdx.x; i < strip_pix; i += 256) {
                 float4 o;
-                o.x = __fdiv_rn((float)sdata[i] - mn0, d0);
-                o.y = __fdiv_rn((float)sdata[strip_pix + i] - mn1, d1);
-                o.z = __fdiv_rn((float)sdata[2 * strip_pix + i] - mn2, d2);
-                o.w = __fdiv_rn((float)sdata[3 * strip_pix + i] - mn3, d3);
+                const int si = sidx(i);
+                o.x = __fdiv_rn((float)sdata[si] - mn0, d0);
+                o.y = __fdiv_rn((float)sdata[plane + si] - mn1, d1);
+                o.z = __fdiv_rn((float)sdata[2 * plane + si] - mn2, d2);
+                o.w = __fdiv_rn((float)sdata[3 * plane + si] - mn3, d3);
                 const long long px = pix0 + i;
                 if (p.out_nchw) {
                     float* q = p.out_nchw + (long long)pidx * 4 * npix + px;
@@ -173,9 +184,9 @@ __global__ void __launch_bounds__(256) patch_tma_kernel(const __grid_constant__ 
         } else {
             for (int c = 0; c < C; ++c) {
                 const float mn = s_mn[c], den = (s_mx[c] - mn) + 1e-5f;
-                const TS* cb = sdata + (size_t)c * strip_pix;
+                const TS* cb = sdata + (size_t)c * plane;
                 for (int i = threadIdx.x; i < strip_pix; i += 256) {
-                    const float o = __fdiv_rn((float)cb[i] - mn, den);
+                    const float o = __fdiv_rn((float)cb[sidx(i)] - mn, den);
                     const long long px = pix0 + i;
                     if (p.out_nchw) p.out_nchw[((long long)pidx * C + c) * npix + px] = o;
                     if (p.out_nhwc) p.out_nhwc[((long long)pidx * npix + px) * C + c] = o;
@@ -209,26 +220,37 @@ extern "C" int svrs_patch_gather_normalize(const void* tiles, int src_is_i16, in
     if (npatch == 0 || T == 0) return 0;
     PatchParams p;
     memset(&p, 0, sizeof(p));
+    // random crops: aligned superset box (see PatchParams); grid mode origins are multiples of P, already aligned
+    const bool padded = origins != nullptr;
+    const int PW = padded ? P + 16 / es : P;
+    SVRS_CHECK_ARG(PW <= 256, "patch_gather_normalize: random crops need P <= %d", 256 - 16 / es);
     // strip height: the largest power of two dividing P whose C planes fit in 96 KB
     int R = P;
-    while ((long long)C * R * P * es > 96 * 1024 && R % 2 == 0) R /= 2;
-    SVRS_CHECK_ARG((long long)C * R * P * es <= 96 * 1024 && P % R == 0 && R <= 256, "patch_gather_normalize: patch does not tile into strips");
+    while ((long long)C * R * PW * es > 96 * 1024 && R % 2 == 0) R /= 2;
+    SVRS_CHECK_ARG((long long)C * R * PW * es <= 96 * 1024 && P % R == 0 && R <= 256, "patch_gather_normalize: patch does not tile into strips");
     p.origins = origins;
     p.out_nchw = out_nchw_f32; p.out_nhwc = out_nhwc_f32; p.out_nhwc_bf16 = reinterpret_cast<__nv_bfloat16*>(out_nhwc_bf16);
-    p.C = C; p.S = S; p.P = P; p.R = R; p.nstrips = P / R; p.per_side = S / P;
-    int rc = make_plane_map_3d(&p.map, tiles, es, S, (long long)T * C, P, R, C);
+    p.C = C; p.S = S; p.P = P; p.R = R; p.nstrips = P / R; p.per_side = S / P; p.PW = PW; p.amask = 16 / es - 1;
+    int rc = make_plane_map_3d(&p.map, tiles, es, S, (long long)T * C, PW, R, C);
     if (rc) return rc;
-    const size_t smem = (size_t)C * R * P * es + 128;
+    const size_t smem = (size_t)C * R * PW * es + 128;
     cudaStream_t st = (cudaStream_t)stream;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(patch_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 128);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(patch_tma_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 128);
+        cudaError_t e = cudaFuncSetAttribute(patch_tma_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(patch_tma_kernel<short, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(patch_tma_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(patch_tma_kernel<short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 128);
         if (e != cudaSuccess) { set_error("patch_gather_normalize: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SVRS_E_CUDA; }
         attr_set = true;
     }
-    if (src_is_i16) SVRS_LAUNCH((patch_tma_kernel<short>), (unsigned)npatch, 256, smem, st, p);
-    else SVRS_LAUNCH((patch_tma_kernel<float>), (unsigned)npatch, 256, smem, st, p);
+    if (padded) {
+        if (src_is_i16) SVRS_LAUNCH((patch_tma_kernel<short, true>), (unsigned)npatch, 256, smem, st, p);
+        else SVRS_LAUNCH((patch_tma_kernel<float, true>), (unsigned)npatch, 256, smem, st, p);
+    } else {
+        if (src_is_i16) SVRS_LAUNCH((patch_tma_kernel<short, false>), (unsigned)npatch, 256, smem, st, p);
+        else SVRS_LAUNCH((patch_tma_kernel<float, false>), (unsigned)npatch, 256, smem, st, p);
+    }
     return check_launch("patch_tma_kernel");
 }
 

@@ -94,8 +94,8 @@ class ParamStore:
         if self.flat is None or not self.params:
             return self.flat is not None
         base = self.flat.data_ptr()
-        for i in (0, len(self.params) // 2, len(self.params) - 1):
-            if self.params[i].data.data_ptr() != base + 4 * self.offsets[i]:
+        for p, off in zip(self.params, self.offsets):       # every parameter: a stand-alone block forward, .to() or
+            if p.data.data_ptr() != base + 4 * off:          # load_state_dict(assign=True) may have re-pointed any of them
                 return False
         return True
 
@@ -720,21 +720,45 @@ def _walk_conv_shapes(net: Net, n: int, h: int, w: int, out: dict):
 # ------------------------------------------------------------------------------------------------
 @dataclass
 class RngState:
-    seed: int = 0
+    """Philox4x32-10 addressing of the reparameterisation noise: key = seed, counter = (element index of the GLOBAL sample,
+    stream id, step).  seed None = derived from torch.initial_seed() at first use (torch.manual_seed then selects the noise,
+    as it does for the reference's torch.randn_like)."""
+    seed: Optional[int] = None
     sample_offset: int = 0          # global index of this rank's first sample (partition-invariant eps)
     step_ptr: Optional[torch.Tensor] = None   # device int64 step counter (Philox counter word 3)
+    sid_base: int = 0               # added to the stream ids (the non-fused path draws from its own streams)
+
+    def key(self) -> int:
+        if self.seed is None:
+            self.seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        return self.seed
 
 
 def reparam_fwd(rt: Runtime, enc, eps, z, z_ld, b, wd, rng: RngState, stream_id: int, eps_out=None):
     lib.reparam_fwd(_p(enc), _p(eps), z if isinstance(z, int) else _p(z), z_ld, _p(eps_out), b, wd,
-                    rng.seed, stream_id, rng.sample_offset, _p(rng.step_ptr), _st())
+                    rng.key(), stream_id + rng.sid_base, rng.sample_offset, _p(rng.step_ptr), _st())
     rt.launches += 1
 
 
 def reparam_bwd(rt: Runtime, enc, eps, dz, dz_ld, denc, b, wd, rng: RngState, stream_id: int):
     lib.reparam_bwd(_p(enc), _p(eps), dz if isinstance(dz, int) else _p(dz), dz_ld, _p(denc), b, wd,
-                    rng.seed, stream_id, rng.sample_offset, _p(rng.step_ptr), _st())
+                    rng.key(), stream_id + rng.sid_base, rng.sample_offset, _p(rng.step_ptr), _st())
     rt.launches += 1
+
+
+class _OwnNoise:
+    """Noise of every forward that is NOT driven by the fused trainer (model(x, y) under autograd, validation, evaluate(),
+    sample()): the engine keeps its own device counter, advanced once per call that draws eps on the device, so two
+    consecutive calls never see the same noise (the reference draws fresh torch.randn_like every call, cond_vae.py:261-265)."""
+
+    def __init__(self):
+        self.step = None
+
+    def tick(self, base: RngState, device) -> RngState:
+        if self.step is None or self.step.device != device:
+            self.step = torch.zeros(1, device=device, dtype=torch.int64)
+        lib.step_increment(_p(self.step), _st())
+        return RngState(seed=base.key(), sample_offset=base.sample_offset, step_ptr=self.step, sid_base=8)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -767,6 +791,7 @@ class CondEngine:
         if self.Wz % 4 or self.Wu % 4:
             raise SvrsError("latent widths must be multiples of 4")
         self.rng = RngState()
+        self._own = _OwnNoise()
 
     def conv_input_shapes(self, B: int) -> dict:
         """id(ConvOp) -> (N, H, W) of the layer's input at batch B (the wgrad dispatch depends on the map size)."""
@@ -799,6 +824,15 @@ class CondEngine:
         ctx = {}
 
         y_nhwc, x_nhwc = yb.op, xb.op
+        # noise: the fused trainer owns rng.step_ptr (one tick per optimisation step, eps recomputed in backward); every other
+        # caller draws from the engine's own counter and, when a backward may follow, keeps the eps it drew
+        rng = self.rng
+        eps_u_out = eps_z_out = None
+        if not fused_io and (eps_u is None or eps_z is None):
+            rng = self._own.tick(self.rng, dev)
+            if save:
+                eps_u_out = torch.empty((B, Wu), **f32) if eps_u is None else None
+                eps_z_out = torch.empty((B, Wz), **f32) if eps_z is None else None
 
         enc_u = torch.empty((B, 2 * Wu), **f32)
         u = torch.empty((B, Wu), **f32)
@@ -814,13 +848,13 @@ class CondEngine:
             # q(u|y): encoder_y -> chunk -> reparameterize (RNG draw #1; Philox is counter-based, so the
             # draw order is a naming convention - stream ids 0 / 1 - not an execution order)
             _, ctx["t_ey"] = rt.net_forward(N["encoder_y"], y_nhwc, training, save, head=(enc_u, 2 * Wu), need_nhwc=False)
-            reparam_fwd(rt, enc_u, eps_u, u, Wu, B, Wu, self.rng, 0)
+            reparam_fwd(rt, enc_u, eps_u, u, Wu, B, Wu, rng, 0, eps_out=eps_u_out)
         with rt.branch(1):
             # y_to_z once (two BN running-stat updates); left half of stack = y_enc flat, NHWC copy feeds the prior heads
             yz, ctx["t_yz"] = rt.net_forward(N["y_to_z"], y_nhwc, training, save, bn_updates=2, head=(stack, 2 * Wz))
         # q(z|x): encoder_x -> chunk -> reparameterize (draw #2); z lands in the right half of `stack`
         _, ctx["t_ex"] = rt.net_forward(N["encoder_x"], x_nhwc, training, save, head=(enc_z, 2 * Wz), need_nhwc=False)
-        reparam_fwd(rt, enc_z, eps_z, stack.data_ptr() + 4 * Wz, 2 * Wz, B, Wz, self.rng, 1)
+        reparam_fwd(rt, enc_z, eps_z, stack.data_ptr() + 4 * Wz, 2 * Wz, B, Wz, rng, 1, eps_out=eps_z_out)
         rt.join(0, 1)
 
         # ---- phase 2: decoder_y | prior heads | decoder_x -----------------------------------------------------------
@@ -857,7 +891,8 @@ class CondEngine:
             rt.to_nchw(yh, y_hat, 4 * (P // 2) ** 2)
             outs.update(x_hat=x_hat, y_hat=y_hat)
         if save:
-            ctx.update(B=B, enc_u=enc_u, enc_z=enc_z, eps_u=eps_u, eps_z=eps_z, rng=RngState(**vars(self.rng)),
+            ctx.update(B=B, enc_u=enc_u, enc_z=enc_z, eps_u=eps_u if eps_u_out is None else eps_u_out,
+                       eps_z=eps_z if eps_z_out is None else eps_z_out, rng=RngState(**vars(rng)),
                        lv3=lv3, x_hat_nhwc=xh, y_hat_nhwc=yh)
         return outs, ctx
 
@@ -971,58 +1006,119 @@ class CondEngine:
         rt.finish_grads()
 
     # ---- inference: Cond_SRVAE.sample (cond_vae.py:299-318) ---------------------------------------
-    def sample(self, y: torch.Tensor, samples: int, eps_u=None, eps_s=None, training: bool = False):
-        """S posterior-predictive decodes of ONE LR patch y [1,4,P/2,P/2] -> [S,4,P,P].
-        y_to_z(y) is identical for every sample, so it is computed once and broadcast (the reference
-        recomputes it on S expanded copies)."""
+    def _sample_decoder_input(self, y, samples: int, eps_u, eps_s, training: bool):
+        """Everything of sample() up to the decoder_x input, for B LR patches at once: encode_y -> u -> z_cond -> the S
+        draws z(b, s) (svrs_sample_latents: one launch, Philox on device unless eps_s [B*S, Wz] is injected) -> NHWC rows
+        [y_enc(b) | z(b, s)], row index b*S + s.  y_to_z(y) is identical for every draw of a patch, so it is computed once
+        per patch and broadcast (the reference recomputes it on S expanded copies)."""
         rt = self.rt
-        _require_cuda(y, "y")
         rt.ensure()
         rt.packs_dirty = True
         rt.pack_weights()
         P = self.P
-        if y.ndim == 3:
-            y = y.unsqueeze(0)
-        assert y.shape == (1, 4, P // 2, P // 2), "sample() takes a single LR patch"
-        y = y.contiguous().float()
-        dev = y.device
+        yb = rt.patch_batch(y)
+        B = yb.B
+        assert tuple(yb.f32.shape[1:]) == (P // 2, P // 2, 4)
+        dev = yb.f32.device
         f32 = dict(device=dev, dtype=torch.float32)
         h8, h16 = P // 8, P // 16
         Wz, Wu, c16, S = self.Wz, self.Wu, self.c16, samples
         N = self.nets
-        y_nhwc = rt.to_nhwc(y, 4 * (P // 2) ** 2, 1, 4, P // 2, P // 2)
-        ey, _ = rt.net_forward(N["encoder_y"], y_nhwc, training, False)
-        enc_u = torch.empty((1, 2 * Wu), **f32)
-        rt.to_nchw(ey, enc_u, 2 * Wu)
-        u = torch.empty((1, Wu), **f32)
-        reparam_fwd(rt, enc_u, eps_u, u, Wu, 1, Wu, self.rng, 0)
-        yz, _ = rt.net_forward(N["y_to_z"], y_nhwc, training, False, bn_updates=2)
-        u16 = rt.to_nhwc(u, Wu, 1, self.cu16, h16, h16)
+        y_nhwc = yb.op
+        rng = self._own.tick(self.rng, dev) if (eps_u is None or eps_s is None) else self.rng
+        enc_u = torch.empty((B, 2 * Wu), **f32)
+        rt.net_forward(N["encoder_y"], y_nhwc, training, False, head=(enc_u, 2 * Wu), need_nhwc=False)
+        u = torch.empty((B, Wu), **f32)
+        reparam_fwd(rt, enc_u, eps_u, u, Wu, B, Wu, rng, 0)
+        yflat = torch.empty((B, Wz), **f32)
+        yz, _ = rt.net_forward(N["y_to_z"], y_nhwc, training, False, bn_updates=2, head=(yflat, Wz))
+        u16 = rt.to_nhwc(u, Wu, B, self.cu16, h16, h16)
         uz, _ = rt.net_forward(N["u_to_z"], u16, training, False)
-        joint = torch.empty((1, h16, h16, 2 * c16), device=dev, dtype=rt.dtype)
-        rows = h16 * h16
+        joint = torch.empty((B, h16, h16, 2 * c16), device=dev, dtype=rt.dtype)
+        rows = B * h16 * h16
         es = joint.element_size()
         rt.copy2d(yz, c16, joint, 2 * c16, rows, c16)
         lib.copy2d(_p(uz), rt.dt, c16, joint.data_ptr() + es * c16, rt.dt, 2 * c16, rows, c16, 0, _st())
-        m3, _ = rt.net_forward(N["mu_u_y_to_z"], joint, training, False)
-        l3, _ = rt.net_forward(N["logvar_u_y_to_z"], joint, training, False)
-        # enc3 rows = [mu3 | lv3] replicated S times so the reparam kernel can treat samples as batch rows
-        enc3 = torch.empty((S, 2 * Wz), **f32)
-        one = torch.empty((1, 2 * Wz), **f32)
-        rt.to_nchw(m3, one, 2 * Wz)
-        lib.nhwc_to_nchw(_p(l3), rt.dt, one.data_ptr() + 4 * Wz, F32, 2 * Wz, 1, c16, h16, h16, 0, _st())
-        lib.copy2d(_p(one), F32, 0, _p(enc3), F32, 2 * Wz, S, 2 * Wz, 0, _st())
-        stack = torch.empty((S, 2 * Wz), **f32)
-        yflat = torch.empty((1, Wz), **f32)
-        rt.to_nchw(yz, yflat, Wz)
-        lib.copy2d(_p(yflat), F32, 0, _p(stack), F32, 2 * Wz, S, Wz, 0, _st())
-        reparam_fwd(rt, enc3, eps_s, stack.data_ptr() + 4 * Wz, 2 * Wz, S, Wz, self.rng, 2)
-        rt.launches += 3
-        s8 = rt.to_nhwc(stack, 2 * Wz, S, 2 * self.cz, h8, h8)
-        xh, _ = rt.net_forward(N["decoder_x"], s8, training, False)
-        out = torch.empty((S, 4, P, P), **f32)
+        rt.launches += 1
+        mu3 = torch.empty((B, Wz), **f32)
+        lv3 = torch.empty((B, Wz), **f32)
+        rt.net_forward(N["mu_u_y_to_z"], joint, training, False, head=(mu3, Wz), need_nhwc=False)
+        rt.net_forward(N["logvar_u_y_to_z"], joint, training, False, head=(lv3, Wz), need_nhwc=False)
+        stack = torch.empty((B * S, 2 * Wz), **f32)
+        lib.sample_latents(_p(mu3), _p(lv3), Wz, _p(yflat), Wz, _p(eps_s), _p(stack), B, S, Wz, rng.key(), 2 + rng.sid_base,
+                           rng.sample_offset, _p(rng.step_ptr), _st())
+        rt.launches += 1
+        return rt.to_nhwc(stack, 2 * Wz, B * S, 2 * self.cz, h8, h8), B
+
+    def sample(self, y: torch.Tensor, samples: int, eps_u=None, eps_s=None, training: bool = False):
+        """S posterior-predictive decodes of ONE LR patch y [1,4,P/2,P/2] -> [S,4,P,P] (cond_vae.py:299-318)."""
+        rt = self.rt
+        _require_cuda(y, "y")
+        P = self.P
+        if y.ndim == 3:
+            y = y.unsqueeze(0)
+        assert y.shape == (1, 4, P // 2, P // 2), "sample() takes a single LR patch"
+        s8, _ = self._sample_decoder_input(y.contiguous().float(), samples, eps_u, eps_s, training)
+        xh, _ = rt.net_forward(self.nets["decoder_x"], s8, training, False, f32_out=True)
+        out = torch.empty((samples, 4, P, P), device=y.device, dtype=torch.float32)
         rt.to_nchw(xh, out, 4 * P * P)
         return out
+
+    def sample_stats(self, y, samples: int, target=None, eps_u=None, eps_s=None, training: bool = False,
+                     splits: int = 0) -> Dict[str, torch.Tensor]:
+        """The uncertainty maps of BaseVAE.task (models/base.py:305-313, 341) for B LR patches at once, WITHOUT materialising
+        the [S,4,P,P] draws: decoder_x runs up to its last layer on all B*S rows and svrs_sample_tail_stats applies the
+        final 16->4 conv + Sigmoid per draw while accumulating streaming Welford statistics over s (also
+        BASELINE config 5's kernel).  y: [B,4,P/2,P/2] NCHW tensor or a PatchBatch; target: [B,4,P,P] NCHW, a PatchBatch, or
+        None.  Returns fp32 tensors: mean [B,4,P,P], std / mae / mse / mean_bias [B,P,P], sample0 [B,4,P,P] (first draw).
+        Train-mode BatchNorm (--test never calls eval()) is batch dependent, so B > 1 then runs patch by patch."""
+        rt = self.rt
+        P = self.P
+        if isinstance(y, torch.Tensor):
+            _require_cuda(y, "y")
+            if y.ndim == 3:
+                y = y.unsqueeze(0)
+        B_in = y.B if isinstance(y, PatchBatch) else y.shape[0]
+        if training and B_in > 1:
+            parts = []
+            for b in range(B_in):
+                yb = PatchBatch(y.f32[b:b + 1], y.op[b:b + 1]) if isinstance(y, PatchBatch) else y[b:b + 1]
+                tb = None
+                if target is not None:
+                    tb = PatchBatch(target.f32[b:b + 1], target.op[b:b + 1]) if isinstance(target, PatchBatch) else target[b:b + 1]
+                parts.append(self.sample_stats(yb, samples, tb, None if eps_u is None else eps_u[b:b + 1],
+                                               None if eps_s is None else eps_s[b * samples:(b + 1) * samples], True, splits))
+            return {k: torch.cat([p_[k] for p_ in parts]) for k in parts[0]}
+        s8, B = self._sample_decoder_input(y, samples, eps_u, eps_s, training)
+        dec = self.nets["decoder_x"]
+        last = dec.ops[-1]
+        body = Net(dec.name, dec.ops[:-1])
+        x16, _ = rt.net_forward(body, s8, training, False)
+        dev = x16.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        tgt = None
+        if target is not None:
+            tgt = rt.patch_batch(target).f32
+            assert tuple(tgt.shape) == (B, P, P, 4)
+        S = samples
+        if splits <= 0:
+            splits = int(lib.sample_tail_splits(B, S, P, P))
+        scratch = torch.empty(int(lib.sample_tail_scratch_floats(B, P, P, splits)), **f32)
+        out = dict(mean=torch.empty((B, 4, P, P), **f32), std=torch.empty((B, P, P), **f32),
+                   sample0=torch.empty((B, 4, P, P), **f32))
+        if tgt is not None:
+            out.update(mae=torch.empty((B, P, P), **f32), mse=torch.empty((B, P, P), **f32),
+                       mean_bias=torch.empty((B, P, P), **f32))
+        lib.sample_tail_stats(_p(x16), rt.dt, _p(last.pack_f), _p(last.mod.bias), _p(tgt), B, S, P, P, last.cin, last.cout,
+                              splits, _p(scratch), _p(out["mean"]), _p(out["std"]), _p(out.get("mae")), _p(out.get("mse")),
+                              _p(out.get("mean_bias")), _p(out["sample0"]), _st())
+        rt.launches += 2
+        return out
+
+    def sample_stats_batch(self, yb, samples: int) -> torch.Tensor:
+        """bench.py's config-5 step: the statistics of `samples` draws for every LR patch of a tile batch; returns the
+        [B,P,P] std map (the other maps are produced as well)."""
+        return self.sample_stats(yb, samples)["std"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1041,6 +1137,7 @@ class VaeEngine:
         if self.Wd % 4:
             raise SvrsError("latent width must be a multiple of 4")
         self.rng = RngState()
+        self._own = _OwnNoise()
 
     def conv_input_shapes(self, B: int) -> dict:
         out = {}
@@ -1062,7 +1159,11 @@ class VaeEngine:
         enc = torch.empty((B, 2 * Wd), **f32)
         _, ctx["t_e"] = rt.net_forward(self.nets["encoder"], xb.op, training, save, head=(enc, 2 * Wd), need_nhwc=False)
         z = torch.empty((B, Wd), **f32)
-        reparam_fwd(rt, enc, eps, z, Wd, B, Wd, self.rng, 0)
+        rng, eps_out = self.rng, None
+        if not fused_io and eps is None:
+            rng = self._own.tick(self.rng, enc.device)
+            eps_out = torch.empty((B, Wd), **f32) if save else None
+        reparam_fwd(rt, enc, eps, z, Wd, B, Wd, rng, 0, eps_out=eps_out)
         z4 = rt.to_nhwc(z, Wd, B, self.c, P // 4, P // 4)
         d, ctx["t_d"] = rt.net_forward(self.nets["decoder"], z4, training, save, f32_out=True)
         outs = dict(x_hat_nhwc=d, enc=enc, xb=xb)
@@ -1071,7 +1172,7 @@ class VaeEngine:
             rt.to_nchw(d, x_hat, 4 * P * P)
             outs["x_hat"] = x_hat
         if save:
-            ctx.update(B=B, enc=enc, eps=eps, rng=RngState(**vars(self.rng)), x_hat_nhwc=d)
+            ctx.update(B=B, enc=enc, eps=eps if eps_out is None else eps_out, rng=RngState(**vars(rng)), x_hat_nhwc=d)
         return outs, ctx
 
     def backward(self, ctx, d_xhat, d_enc, fused_io: bool = False):

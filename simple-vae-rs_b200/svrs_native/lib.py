@@ -95,7 +95,7 @@ class _Lib:
             raise AttributeError(name)
         fn = getattr(self.load(), full)
         if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run", "svrs_pack_job_bytes", "svrs_launch_count", "svrs_adam_job_bytes",
-                                                  "svrs_conv2d_wgrad_layout", "svrs_convT2d_wgrad_layout"):
+                                                  "svrs_conv2d_wgrad_layout", "svrs_convT2d_wgrad_layout", "svrs_sample_tail_splits"):
             setattr(self, name, fn)
             return fn
 

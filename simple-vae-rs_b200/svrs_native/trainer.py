@@ -24,6 +24,24 @@ from .lib import ACT_SIGMOID, F32, lib
 from .parallel import upstream_grad_scales
 
 
+class _Nvtx:
+    """NVTX ranges around the phases of the fused step (SVRS_NVTX=1): forward / elbo / backward / allreduce / optimizer show
+    up as named ranges in nsys / ncu --nvtx timelines.  Host-side markers only; no effect on the enqueued work."""
+    on = os.environ.get("SVRS_NVTX", "0") == "1"
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_push("svrs/" + self.name)
+
+    def __exit__(self, *exc):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class _AdamCfg:
     def __init__(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
         self.lr, self.b1, self.b2, self.eps, self.max_norm = lr, betas[0], betas[1], eps, max_norm
@@ -64,6 +82,7 @@ class _FusedBase:
         self.fused_tail = os.environ.get("SVRS_FUSED_TAIL", "1") != "0"
         self._adam_jobs = None
         self.m = self.v = None
+        self._flat_ptr = None
         self._graphs: Dict[tuple, dict] = {}
         self._comm_stream = None
         self.steps_done = 0
@@ -74,7 +93,16 @@ class _FusedBase:
         rt.ensure()
         rt.sync_bn, rt.pg, rt.world = self.sync_bn, self.pg, self.world
         store = rt.store
-        if self.m is None or self.m.device != store.flat.device or self.m.numel() != store.flat.numel():
+        fresh = self.m is None or self.m.device != store.flat.device or self.m.numel() != store.flat.numel()
+        if not fresh and self._flat_ptr != store.flat.data_ptr():
+            # the parameter store was re-flattened on the same device (a stand-alone block forward, load_state_dict(assign=True)
+            # ...): captured graphs, job tables and packs point at freed buffers - drop them, keep the optimiser state
+            self._flat_ptr = store.flat.data_ptr()
+            self._graphs.clear()
+            self._adam_jobs = None
+            rt.packs_dirty = True
+        if fresh:
+            self._flat_ptr = store.flat.data_ptr()
             dev = store.flat.device
             self.m = torch.zeros_like(store.flat)
             self.v = torch.zeros_like(store.flat)
@@ -120,8 +148,11 @@ class _FusedBase:
         rt, eng = self.rt, self.eng
         store = rt.store
         key = (store.flat.data_ptr(), rt.dtype, batch)
-        if self._adam_jobs is not None and self._adam_jobs[0] == key:
-            return self._adam_jobs[1:]
+        if self._adam_jobs is None:
+            self._adam_jobs = {}
+        hit = self._adam_jobs.get(key)       # one table per batch size: captured graphs keep pointing at theirs
+        if hit is not None:
+            return hit
         rec = np.dtype([("off", "<i8"), ("p01", "<u8"), ("p10", "<u8"), ("d0", "<i4"), ("d1", "<i4"), ("kk", "<i4"),
                         ("layout", "<i4"), ("tile0", "<i4"), ("tiles_b", "<i4")])
         assert rec.itemsize == lib.adam_job_bytes()
@@ -153,8 +184,8 @@ class _FusedBase:
         plain(cur, store.total)
         jobs = np.array(rows, dtype=rec)
         dev_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).to(store.flat.device)
-        self._adam_jobs = (key, dev_jobs, len(rows), tile0)
-        return self._adam_jobs[1:]
+        self._adam_jobs[key] = (dev_jobs, len(rows), tile0)
+        return self._adam_jobs[key]
 
     def _optim_tail(self, batch: int):
         rt, cfg, st = self.rt, self.cfg, _st()
@@ -272,6 +303,8 @@ class _FusedBase:
             static_in = [torch.empty_like(t) for t in flat]
             for s_, t in zip(static_in, flat):
                 s_.copy_(t)
+            if self.fused_tail:
+                self._adam_table(int(flat[0].shape[0]))     # host -> device table upload must not happen under capture
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             l0 = self.rt.launches
@@ -305,6 +338,8 @@ class _FusedBase:
         g = self._graphs.get(key)
         if g is None:
             static_in = [t.clone() for t in tiles]
+            if self.fused_tail:
+                self._adam_table(int(tiles[0].shape[0]) * (tiles[0].shape[-1] // patch_size) ** 2)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             l0 = self.rt.launches
@@ -375,7 +410,8 @@ class FusedCondTrainer(_FusedBase):
         rt.zero_grads(with_scratch=True)
         rt.scratch_prezeroed = True
         try:
-            outs, ctx = eng.forward(x, y, eps_u, eps_z, training=True, save=True, repack=False, fused_io=True)
+            with _Nvtx("forward"):
+                outs, ctx = eng.forward(x, y, eps_u, eps_z, training=True, save=True, repack=False, fused_io=True)
         finally:
             rt.scratch_prezeroed = False
         xb, yb = outs["xb"], outs["yb"]
@@ -403,12 +439,15 @@ class FusedCondTrainer(_FusedBase):
         if self.world > 1 and getattr(self, "_ar_overlap", False):
             rt.after_phase1 = self._early_allreduce      # only while the fused step's backward runs
         try:
-            eng.backward(ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3, fused_io=True)
+            with _Nvtx("backward"):
+                eng.backward(ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3, fused_io=True)
         finally:
             rt.scratch_prezeroed = False
             rt.after_phase1 = None
-        self._allreduce_all()
-        self._optim_tail(B)
+        with _Nvtx("allreduce"):
+            self._allreduce_all()
+        with _Nvtx("optimizer"):
+            self._optim_tail(B)
         rt.fused_grads = False
         return terms
 
@@ -431,7 +470,8 @@ class FusedVaeTrainer(_FusedBase):
         rt.zero_grads(with_scratch=True)
         rt.scratch_prezeroed = True
         try:
-            outs, ctx = eng.forward(x, eps, training=True, save=True, repack=False, fused_io=True)
+            with _Nvtx("forward"):
+                outs, ctx = eng.forward(x, eps, training=True, save=True, repack=False, fused_io=True)
         finally:
             rt.scratch_prezeroed = False
         xb = outs["xb"]
@@ -450,10 +490,13 @@ class FusedVaeTrainer(_FusedBase):
         rt.launches += 3
         rt.scratch_prezeroed = True
         try:
-            eng.backward(ctx, d_xhat, d_enc, fused_io=True)
+            with _Nvtx("backward"):
+                eng.backward(ctx, d_xhat, d_enc, fused_io=True)
         finally:
             rt.scratch_prezeroed = False
-        self._allreduce_all()
-        self._optim_tail(B)
+        with _Nvtx("allreduce"):
+            self._allreduce_all()
+        with _Nvtx("optimizer"):
+            self._optim_tail(B)
         rt.fused_grads = False
         return terms

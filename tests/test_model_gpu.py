@@ -347,3 +347,78 @@ def test_baseline_configs_2_and_4_bf16_matches_fp32(config):
         assert x == x and y == y, "non-finite ELBO term"
         tol = 5e-3 if i in kl_idx else 1e-3
         assert abs(x - y) <= tol * max(abs(x), 1e-6), (config, i, x, y)
+
+
+def test_noise_is_fresh_on_every_call_and_follows_torch_seed(golden_dir):
+    """outside the fused trainer the reparameterisation noise used to be frozen (step 0, seed 0).  The
+    reference draws fresh torch.randn_like on every call (cond_vae.py:261-265) under torch's global seed: two consecutive
+    model(x, y) calls must see different eps, validation batches too, and torch.manual_seed must select the sequence."""
+    fx = FX.load(golden_dir, "cond_cr2_p64_b2")
+    x, y = FX.inputs(fx)
+    x, y = x.to(DEV), y.to(DEV)
+
+    def run(seed):
+        torch.manual_seed(seed)
+        model, _ = FX.build(fx, device=DEV)
+        model.train()
+        a = model(x, y)
+        b = model(x, y)
+        model.eval()
+        with torch.no_grad():
+            c = model(x, y)
+            d = model(x, y)
+        return [t[0].detach().clone() for t in (a, b, c, d)], (a, model)
+
+    (a, b, c, d), (outs, model) = run(11)
+    assert not torch.equal(a, b) and not torch.equal(c, d), "identical noise on consecutive calls"
+    (a2, b2, _, _), _ = run(11)
+    assert torch.equal(a, a2) and torch.equal(b, b2), "same torch seed must reproduce the noise"
+    (a3, _, _, _), _ = run(12)
+    assert not torch.equal(a, a3), "torch.manual_seed must select the noise"
+    # backward after ANOTHER forward still uses the eps its own forward drew (saved, not recomputed from the counter)
+    from loss import cond_loss
+    torch.manual_seed(11)
+    m1, _ = FX.build(fx, device=DEV)
+    m1.train()
+    o1 = m1(x, y)
+    l1 = sum(cond_loss(o1[0], x, o1[1], y, o1[4], o1[5], o1[2], o1[3], o1[6], o1[7], m1.gammax, m1.gammay))
+    l1.backward()
+    g_ref = m1.encoder_x[6].weight.grad.clone()
+    torch.manual_seed(11)
+    m2, _ = FX.build(fx, device=DEV)
+    m2.train()
+    o2 = m2(x, y)
+    with torch.no_grad():
+        m2(x, y)                       # interleaved forward advances the engine's counter
+    l2 = sum(cond_loss(o2[0], x, o2[1], y, o2[4], o2[5], o2[2], o2[3], o2[6], o2[7], m2.gammax, m2.gammay))
+    l2.backward()
+    report("grad with an interleaved forward", m2.encoder_x[6].weight.grad, g_ref, 1e-5, atol=1e-7)
+
+
+def test_fit_on_the_random_crop_loader(monkeypatch, tmp_path):
+    """init_dataloader("synthetic") -> RandomCropLoader (the reference's default crop mode, dataset.py:24,205-216, on the
+    device) -> fit(): batch_size counts crops exactly, losses finite, parameters move."""
+    import models.base as base_module
+    import models
+    from dataset import init_dataloader
+
+    class DummyRun:
+        def log(self, *a, **k):
+            pass
+
+        def finish(self):
+            pass
+
+    monkeypatch.setattr(base_module.wandb, "init", lambda *a, **k: DummyRun())
+    monkeypatch.chdir(tmp_path)
+    train, val = init_dataloader("synthetic", batch_size=6, patch_size=64, device=DEV, n_tiles=20)
+    yb, xb = next(iter(train))
+    assert yb.shape == (6, 4, 32, 32) and xb.shape == (6, 4, 64, 64) and len(train) == 3
+    assert float(xb.min()) >= 0 and float(xb.max()) <= 1
+    model = models.Cond_SRVAE(2, patch_size=64).to(DEV)
+    w0 = model.encoder_x[6].weight.detach().clone()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    model.fit(train_loader=train, val_loader=val, device=DEV, optimizer=opt, epochs=2, start_epoch=1, val_metrics_every=1)
+    assert model.scheduler.last_epoch == 2
+    assert all(v == v for v in model.terms_dict.values())
+    assert not torch.equal(model.encoder_x[6].weight.detach(), w0)
