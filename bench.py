@@ -270,6 +270,18 @@ def ddp_check(dev, rank, world, pg=None):
     spread = (p_ddp - p0).abs().max()
     torch.distributed.all_reduce(spread, op=torch.distributed.ReduceOp.MAX, group=pg)
     res["param_spread"] = float(spread)
+    # the overlapped exchange (early all-reduce of the decoders' range on the bounded, high-priority communicator) against
+    # the single all-reduce after the backward pass: same shard, per-rank BatchNorm statistics, fp32
+    g_ov = []
+    for overlap in (True, False):
+        mo, tro = fresh(False, world)
+        tro.eng.rng.sample_offset = rank * B
+        tro.keep_grad = True
+        tro._ensure_state()
+        tro._ar_overlap = overlap
+        tro.step(X[rank * B:(rank + 1) * B], Y[rank * B:(rank + 1) * B])
+        g_ov.append(tro.last_grad.clone())
+    res["overlap_vs_plain_allreduce_grad_rel_err"] = float((g_ov[0] - g_ov[1]).norm() / g_ov[1].norm())
     if rank == 0:
         m1, tr1 = fresh(False, 1)
         tr1.keep_grad = True

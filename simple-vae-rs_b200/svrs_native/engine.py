@@ -72,19 +72,31 @@ def _require_cuda(t: torch.Tensor, what: str):
 class ParamStore:
     ALIGN = 4  # floats -> 16-byte aligned views
 
-    def __init__(self, module: nn.Module):
+    def __init__(self, module: nn.Module, late_prefixes: Tuple[str, ...] = ()):
+        """late_prefixes: parameter-name prefixes of the sub-networks whose backward pass finishes LAST (the encoders).  They
+        are laid out at the END of the flat buffers, so the gradients that are complete early (everything else) form one
+        contiguous range [0, early_end) that the data-parallel trainer can all-reduce while the late nets' backward is still
+        running, and the late range [early_end, total) plus the small tail (gamma gradients) is a second single call.
+        state_dict / named_parameters order is the module's own and unaffected."""
         self.module = module
-        self.params: List[nn.Parameter] = []
-        self.names: List[str] = []
-        for n, p in module.named_parameters():
-            self.names.append(n)
-            self.params.append(p)
+        named = list(module.named_parameters())
+        late = [i for i, (n, _) in enumerate(named) if n.startswith(tuple(late_prefixes))] if late_prefixes else []
+        order = [i for i in range(len(named)) if i not in set(late)] + late
+        self.params: List[nn.Parameter] = [named[i][1] for i in order]
+        self.names: List[str] = [named[i][0] for i in order]
         self.offsets: List[int] = []
         off = 0
-        for p in self.params:
+        self.early_end = None
+        n_early = len(order) - len(late)
+        for j, p in enumerate(self.params):
+            if j == n_early:
+                self.early_end = off
             self.offsets.append(off)
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.total = off
+        if self.early_end is None:
+            self.early_end = off
+        self.TAIL = 4            # floats after the parameters' gradients: scalar gradients that travel with the all-reduce
         self.flat: Optional[torch.Tensor] = None
         self.grad: Optional[torch.Tensor] = None
         self.gpack: Optional[torch.Tensor] = None
@@ -112,7 +124,9 @@ class ParamStore:
                 v.copy_(p.data.to(torch.float32))
                 p.data = v
         self.flat = flat
-        self.grad = torch.zeros_like(flat)
+        self.grad_full = torch.zeros(self.total + self.TAIL, device=dev, dtype=torch.float32)
+        self.grad = self.grad_full[:self.total]
+        self.tail = self.grad_full[self.total:]
         self.gpack = torch.zeros_like(flat)     # per-tap packed scratch for the tensor-core wgrad kernels
         return True
 
@@ -219,13 +233,14 @@ def plan_sequential(name: str, seq: nn.Sequential) -> Net:
 class Runtime:
     """Kernel-level forward/backward over Net plans; owns weight packs and scratch."""
 
-    def __init__(self, module: nn.Module, nets: Sequence[Net], compute_dtype: torch.dtype = torch.float32):
+    def __init__(self, module: nn.Module, nets: Sequence[Net], compute_dtype: torch.dtype = torch.float32,
+                 late_prefixes: Tuple[str, ...] = ()):
         lib.load()
         self.module = module
         self.nets = list(nets)
         self.dtype = compute_dtype
         self.dt = _dt(compute_dtype)
-        self.store = ParamStore(module)
+        self.store = ParamStore(module, late_prefixes)
         self._scratch: Optional[torch.Tensor] = None
         self._pack_jobs: Optional[torch.Tensor] = None
         self._pack_key = None
@@ -777,7 +792,8 @@ class CondEngine:
         self.Lu = model.latent_size_y
         names = ["encoder_y", "decoder_y", "encoder_x", "decoder_x", "y_to_z", "u_to_z", "mu_u_y_to_z", "logvar_u_y_to_z"]
         self.nets = {n: plan_sequential(n, getattr(model, n)) for n in names}
-        self.rt = Runtime(model, list(self.nets.values()), compute_dtype)
+        # backward phase 2 (CondEngine.backward) = the three encoders: their gradients are complete last
+        self.rt = Runtime(model, list(self.nets.values()), compute_dtype, late_prefixes=("encoder_y.", "encoder_x.", "y_to_z."))
         P = self.P
         assert P % 16 == 0, "patch_size must be a multiple of 16"
         self.cz = self.L // 64                   # channels of mu_z at (P/8)^2

@@ -111,7 +111,7 @@ class _FusedBase:
             self.gam = torch.ones(2, device=dev, dtype=torch.float32)
             self.gam_m = torch.zeros(2, device=dev, dtype=torch.float32)
             self.gam_v = torch.zeros(2, device=dev, dtype=torch.float32)
-            self.dgam = torch.zeros(2, device=dev, dtype=torch.float32)
+            self.dgam = store.tail[:2]       # gamma gradients live behind the flat gradient: one all-reduce carries both
             self.gout = torch.tensor(upstream_grad_scales(self.world), device=dev)
             self._load_gammas_from_model()
             self.eng.rng.step_ptr = self.step_ptr
@@ -119,10 +119,27 @@ class _FusedBase:
             self._adam_jobs = None
             rt.packs_dirty = True
             if self.world > 1:
-                self._comm_stream = torch.cuda.Stream(device=dev)
-                # off by default: neutral at 2 GPUs and harmful at 8 (6.3 vs 4.4 ms/step measured) - the NCCL kernels of the
-                # early all-reduce compete for SMs with five concurrent compute streams and every rank then waits
-                self._ar_overlap = os.environ.get("SVRS_AR_OVERLAP", "0") == "1"
+                self._setup_comm(dev)
+
+    def _setup_comm(self, dev):
+        """Gradient exchange plumbing.  The all-reduce of the nets whose backward finishes first (decoders, prior heads,
+        u_to_z: 18.4 M of the 20.6 M parameters) is issued while the encoders' backward pass is still running.  Round 1
+        found that harmful at 8 GPUs (6.3 vs 4.1 ms/step): NCCL's CTAs queued behind five compute streams whose persistent
+        CTAs hold ~200 KB of shared memory and all 512 TMEM columns per SM, and every rank waited for the slowest one.  Two
+        changes make the overlap pay: the reduction runs on its OWN communicator with a bounded CTA count
+        (ncclConfig maxCTAs = SVRS_NCCL_MAX_CTAS, default 8: ~5 % of the SMs) on a HIGH-PRIORITY stream, so its few CTAs
+        are scheduled ahead of queued compute CTAs as soon as any SM frees up.  SVRS_AR_OVERLAP=0 restores the single
+        all-reduce after the backward pass."""
+        self._ar_overlap = os.environ.get("SVRS_AR_OVERLAP", "1") == "1"
+        self._comm_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self._ar_pg = self.pg
+        max_ctas = int(os.environ.get("SVRS_NCCL_MAX_CTAS", "8"))
+        if self._ar_overlap and max_ctas > 0 and torch.distributed.get_backend(self.pg) == "nccl":
+            opts = torch.distributed.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            opts.config.max_ctas = max_ctas
+            opts.config.min_ctas = min(max_ctas, int(os.environ.get("SVRS_NCCL_MIN_CTAS", "1")))
+            ranks = torch.distributed.get_process_group_ranks(self.pg) if self.pg is not None else None
+            self._ar_pg = torch.distributed.new_group(ranks=ranks, backend="nccl", pg_options=opts)
 
     def _gamma_attrs(self):
         raise NotImplementedError
@@ -245,21 +262,27 @@ class _FusedBase:
         return [(lo, min(hi, store.total)) for lo, hi in merged]
 
     def _early_allreduce(self, nets):
+        """Called by CondEngine.backward when phase 1 (decoders, prior heads, u_to_z) is complete: their gradients are the
+        contiguous range [0, early_end) of the flat buffer (ParamStore lays the encoders out last) - ONE all-reduce on the
+        communication stream, overlapped with the encoders' backward pass."""
         rt = self.rt
+        store = rt.store
+        segs = self._net_segments(nets)
+        assert segs == [(0, store.early_end)], (segs, store.early_end)
         comm = self._comm_stream
         comm.wait_stream(torch.cuda.current_stream())
         if rt._side_busy:
             for side in rt.wgrad_streams():            # the wgrads queued so far are exactly those of `nets`
                 comm.wait_stream(side)
-        segs = self._net_segments(nets)
         with torch.cuda.stream(comm):
             if not rt.fused_grads:
                 rt.unpack_nets(nets)
-            for lo, hi in segs:
-                torch.distributed.all_reduce(rt.store.grad[lo:hi], group=self.pg)
+            torch.distributed.all_reduce(store.grad_full[:store.early_end], group=self._ar_pg)
         self._early_segs = segs
 
     def _allreduce_all(self):
+        """The rest of the exchange after the backward pass: the encoders' range plus the gamma gradients in the tail of the
+        same buffer (one call), or the whole buffer when nothing was reduced early."""
         if self.world == 1:
             return
         self._sync_bn_grad_fix()
@@ -267,15 +290,10 @@ class _FusedBase:
         early = getattr(self, "_early_segs", None)
         self._early_segs = None
         if not early:
-            torch.distributed.all_reduce(store.grad, group=self.pg)
+            torch.distributed.all_reduce(store.grad_full, group=self.pg)
         else:
-            lo0 = 0
-            for lo, hi in early + [(store.total, store.total)]:
-                if lo > lo0:
-                    torch.distributed.all_reduce(store.grad[lo0:lo], group=self.pg)
-                lo0 = hi
+            torch.distributed.all_reduce(store.grad_full[store.early_end:], group=self.pg)
             torch.cuda.current_stream().wait_stream(self._comm_stream)
-        torch.distributed.all_reduce(self.dgam, group=self.pg)
 
     # ---- public ------------------------------------------------------------------------------------
     def grad_norm(self) -> torch.Tensor:
@@ -436,7 +454,7 @@ class FusedCondTrainer(_FusedBase):
         rt.launches += 3
         rt.scratch_prezeroed = True
         self._early_segs = None
-        if self.world > 1 and getattr(self, "_ar_overlap", False):
+        if self.world > 1 and getattr(self, "_ar_overlap", False) and not self.sync_bn:
             rt.after_phase1 = self._early_allreduce      # only while the fused step's backward runs
         try:
             with _Nvtx("backward"):
