@@ -21,6 +21,11 @@ struct ConvArgs {
 
 constexpr int BK = 16;
 
+}  // namespace svrs
+#include "conv_narrow.cuh"   // bf16 narrow layers on mma.sync (needs ConvArgs)
+namespace svrs {
+extern int g_tc_enabled_narrow;   // follows svrs_set_tc_enabled: 0 keeps the narrow layers on the CUDA-core kernel (A/B tests)
+
 template <typename T, int BM, int BN>
 __global__ void __launch_bounds__(256) conv_taps_kernel(const __grid_constant__ ConvArgs a) {
     pdl_entry();
@@ -265,6 +270,10 @@ static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st, int out_dt
     long long M = (long long)g.N * g.OH * g.OW;
     if (M == 0) return 0;
     if (out_dtype < 0) out_dtype = dtype;
+    if (g_tc_enabled_narrow && narrow_mma_takes(g, dtype) && (out_dtype == SVRS_BF16 || out_dtype == SVRS_F32)) {
+        launch_narrow(a, out_dtype, st);
+        return check_launch("conv_narrow_mma_kernel");
+    }
     if (pixel_kernel_takes(g, dtype)) {
         dim3 grid((unsigned)((M + 255) / 256), 1, g.nprob);
         if (dtype == SVRS_F32 && out_dtype == SVRS_F32) launch_pixel<float, float>(a, grid, st);
@@ -587,7 +596,10 @@ __global__ void __launch_bounds__(512, 1) wgrad_narrow_kernel(const __grid_const
     const T* __restrict__ G = reinterpret_cast<const T*>(a.gmat) + pb.out_off;
     const T* __restrict__ X = reinterpret_cast<const T*>(a.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = warp * TPW;
+    // blockIdx.z selects a GROUP of taps: the taps of a layer are spread over several small CTAs (3-4 warps) instead of
+    // one 9..16-warp CTA per SM, so that 4-5 CTAs with DIFFERENT pixel ranges are resident per SM - the kernel was bound by
+    // the number of distinct loads in flight (one pixel stream per SM: 0.3 TB/s), not by FMA issue
+    const int t0 = (blockIdx.z * (blockDim.x >> 5) + warp) * TPW;
     Tap tp[TPW];
     bool tap_ok[TPW];
 #pragma unroll
@@ -676,12 +688,18 @@ static bool try_launch_wgrad_narrow(const WgradArgs& a, cudaStream_t st, int& rc
     if (disabled) return false;
     if (g.nprob != 1 || ohw % 32 != 0 || (long long)g.N * ohw >= (1ll << 31) || ntaps > 16) return false;
     const int groups = (int)((long long)g.N * ohw / 32);
-    const int warps = (Ca == 4 && Cb == 4) ? (ntaps + 3) / 4 : ntaps;
-    int grid = num_sms() * (warps >= 8 ? 1 : 16 / warps);          // ~16 resident warps per SM (100-120 registers each)
-    if (grid > groups) grid = groups;
-    if (Ca == 4 && Cb == 16) SVRS_LAUNCH((wgrad_narrow_kernel<T, 4, 16, 1>), grid, 32 * ntaps, 0, st, a);
-    else if (Ca == 16 && Cb == 4) SVRS_LAUNCH((wgrad_narrow_kernel<T, 16, 4, 1>), grid, 32 * ntaps, 0, st, a);
-    else if (Ca == 4 && Cb == 4) SVRS_LAUNCH((wgrad_narrow_kernel<T, 4, 4, 4>), grid, 32 * ((ntaps + 3) / 4), 0, st, a);
+    const int warps = (Ca == 4 && Cb == 4) ? (ntaps + 3) / 4 : ntaps;       // warps needed for all taps
+    // warps per CTA: 3 (nine taps) or 4 (sixteen taps / the 4x4 form); tap groups in grid.z
+    const int wpc = warps % 3 == 0 ? 3 : (warps >= 4 ? 4 : warps);
+    const int zg = (warps + wpc - 1) / wpc;
+    int per_sm = 65536 / (128 * 32 * wpc);                                  // CTAs per SM at 128 registers per thread
+    if (per_sm > 5) per_sm = 5;
+    int gx = (num_sms() * per_sm + zg - 1) / zg;
+    if (gx > groups) gx = groups;
+    dim3 grid(gx, 1, zg);
+    if (Ca == 4 && Cb == 16) SVRS_LAUNCH((wgrad_narrow_kernel<T, 4, 16, 1>), grid, 32 * wpc, 0, st, a);
+    else if (Ca == 16 && Cb == 4) SVRS_LAUNCH((wgrad_narrow_kernel<T, 16, 4, 1>), grid, 32 * wpc, 0, st, a);
+    else if (Ca == 4 && Cb == 4) SVRS_LAUNCH((wgrad_narrow_kernel<T, 4, 4, 4>), grid, 32 * wpc, 0, st, a);
     else return false;
     rc = check_launch("wgrad_narrow_kernel");
     return true;
@@ -799,6 +817,7 @@ int launch_wgrad_tc(const TapGeom& g, const void* gmat, const void* x, float* dw
 bool wgrad_halo_supported(const TapGeom& g, int KK);
 int launch_wgrad3_halo(const TapGeom& g, const void* gmat, const void* x, float* dw, int packed, float* db, cudaStream_t st);
 static int g_tc_enabled = 1;
+int g_tc_enabled_narrow = 1;
 static inline bool use_tc(const void* w_nk, int dtype, int K, int Nc, int OW, int OH) {
     // layers with both channel counts <= 16 are HBM-bound streaming ops: the per-pixel SIMT kernel beats a padded MMA
     return g_tc_enabled && w_nk != nullptr && !((K == 4 || Nc == 4) && K <= 16 && Nc <= 16) && tc_supported(dtype, K, Nc, OW, OH);
@@ -810,7 +829,7 @@ using namespace svrs;
 static bool dtype_ok(int d) { return d == SVRS_F32 || d == SVRS_BF16; }
 
 namespace svrs { void set_halo_mode(int m); }
-extern "C" void svrs_set_tc_enabled(int enabled) { svrs::g_tc_enabled = enabled; }
+extern "C" void svrs_set_tc_enabled(int enabled) { svrs::g_tc_enabled = enabled; svrs::g_tc_enabled_narrow = enabled; }
 extern "C" void svrs_set_halo_mode(int mode) { svrs::set_halo_mode(mode); }
 extern "C" int svrs_tc_would_run(int dtype, int K, int Nc, int OH, int OW) {
     return svrs::g_tc_enabled && svrs::tc_supported(dtype, K, Nc, OW, OH) ? 1 : 0;

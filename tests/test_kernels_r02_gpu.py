@@ -93,6 +93,8 @@ EX_CASES = [
     (2, 16, 16, 64, 128, 4),    # down_block conv4s2 -> BatchNorm (conv_tc)
     (2, 16, 16, 128, 128, 3),   # halo kernel
     (2, 32, 32, 16, 64, 4),     # 16-channel chunks
+    (2, 32, 32, 4, 16, 4),      # image-side down_block conv4s2 -> BatchNorm (narrow mma.sync kernel)
+    (3, 16, 16, 4, 16, 4),
 ]
 
 
