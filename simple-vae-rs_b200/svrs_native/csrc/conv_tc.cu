@@ -20,6 +20,7 @@
 //     for the MMA (weight rows beyond Nc are TMA zero fill) and masked at the store.
 //   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 #include "common.cuh"
+#include <stdlib.h>
 #include "taps.cuh"
 #include <cuda.h>
 #include <string.h>
@@ -368,11 +369,14 @@ int launch_conv_tc(int form, const void* in, const void* w_nk, const float* bias
     p.Nc = Cw;
     int npad = (Cw + 15) / 16 * 16;
     p.n_tile = npad <= 256 ? npad : 256;
-    // few pixel tiles (4x4 / 8x8 maps): trade MMA width for CTAs until the machine is reasonably full.  N = 128 still
-    // balances the ~58-cycle issue floor (64 cycles of tensor work per MMA); N = 64 only when even that leaves SMs idle.
+    // few pixel tiles (4x4 / 8x8 maps): trade MMA width for CTAs only while fewer than `want` CTAs would have work.
     {
         long long pix_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * g.nprob;
-        while (p.n_tile > 64 && p.n_tile % 32 == 0 && pix_tiles * ((Cw + p.n_tile - 1) / p.n_tile) < 96) p.n_tile /= 2;
+        // Measured (bench step, 128 patches): shrinking N for >= 96 CTAs cost 6.6 % of the whole step against >= 32 - on the
+        // 4x4 / 8x8 maps a CTA's time is dominated by the weight stream and the ~58-cycle MMA issue floor, so 64 CTAs issuing
+        // N = 128 / 256 MMAs beat 128 CTAs issuing N = 64 MMAs, and leave SMs to the kernels of the parallel streams.
+        static const int want = getenv("SVRS_TC_WANT_CTAS") ? atoi(getenv("SVRS_TC_WANT_CTAS")) : 32;
+        while (p.n_tile > 64 && p.n_tile % 32 == 0 && pix_tiles * ((Cw + p.n_tile - 1) / p.n_tile) < want) p.n_tile /= 2;
     }
     p.n_tiles = (Cw + p.n_tile - 1) / p.n_tile;
     p.cw = chunk_width(Cr);

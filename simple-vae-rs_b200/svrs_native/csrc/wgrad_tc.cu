@@ -322,7 +322,12 @@ static int wg_plan(const TapGeom& g, int KK, WgParams& p) {
     p.ngroups = (p.nblocks + p.group - 1) / p.group;
     p.ksteps_total = p.tiles_x * p.tiles_y * p.tiles_n;
     int base = p.ngroups * p.n_tiles;
-    int ksplit = (num_sms() + base / 2) / base;
+    // split-K over pixels until about HALF the SMs have a CTA.  MEASURED (SVRS_WG_TARGET_CTAS sweep on the bench step): a
+    // target of 148 CTAs costs 3 % of the whole step against 60-74 - every extra split pays another TMA-reduce epilogue
+    // (group x 64 KB through the L2 fp32 adder) and the weight gradients run on side streams next to the dgrad chain, so a
+    // grid that takes every SM only queues behind (or in front of) the kernel it is supposed to overlap with.
+    static const int target = getenv("SVRS_WG_TARGET_CTAS") ? atoi(getenv("SVRS_WG_TARGET_CTAS")) : num_sms() / 2;
+    int ksplit = (target + base / 2) / base;
     if (ksplit > p.ksteps_total) ksplit = p.ksteps_total;
     if (ksplit < 1) ksplit = 1;
     const int steps_per = (p.ksteps_total + ksplit - 1) / ksplit;
