@@ -14,6 +14,7 @@
 // 64->64 layers) or streamed through a 4-slot ring of (chunk, tap) slices.
 // Warp roles / TMEM double buffering / epilogue are those of conv_tc.cu.
 #include "common.cuh"
+#include <stdlib.h>
 #include "taps.cuh"
 #include <cuda.h>
 #include <string.h>
@@ -400,6 +401,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1) convT_halo_kernel(const __grid_
     }
 }
 
+// persistent-grid cap of the halo kernels (SVRS_HALO_MAX_CTAS, default = all SMs)
+static int halo_max_ctas() {
+    static const int v = getenv("SVRS_HALO_MAX_CTAS") ? atoi(getenv("SVRS_HALO_MAX_CTAS")) : num_sms();
+    return v < 1 ? 1 : v;
+}
 static int g_halo_mode = 1;   // 0 = off (per-tap TMA kernels), 1 = on
 void set_halo_mode(int m) { g_halo_mode = m != 0; }
 int get_halo_mode() { return g_halo_mode; }
@@ -456,7 +462,7 @@ int launch_convT_halo(const void* in, const void* w_nk, const float* bias, void*
     rc = make_w_map_pub(&p.w_map, w_nk, Cr, Cw, 16, p.n_tile, p.cw);
     if (rc) return rc;
     long long total = (long long)p.tiles_x * p.tiles_y * N * p.n_tiles;
-    int grid = (int)(total < num_sms() ? total : num_sms());
+    int grid = (int)(total < halo_max_ctas() ? total : halo_max_ctas());
     if (grid < 1) return 0;
     const bool extra = ex.bn_sums != nullptr;
 #define GO_T(K) do { if (extra) SVRS_LAUNCH((convT_halo_kernel<K, true>), grid, HL_THREADS, HL_SMEM_BYTES, st, p); \
@@ -502,7 +508,7 @@ int launch_conv3_halo(int form, const void* in, const void* w_nk, const float* b
     rc = make_w_map_pub(&p.w_map, w_nk, Cr, Cw, 9, p.n_tile, p.cw);
     if (rc) return rc;
     long long total = (long long)p.tiles_x * p.tiles_y * N * p.n_tiles;
-    int grid = (int)(total < num_sms() ? total : num_sms());
+    int grid = (int)(total < halo_max_ctas() ? total : halo_max_ctas());
     if (grid < 1) return 0;
     const bool extra = ex.bn_sums != nullptr || ex.out2 != nullptr;
 #define GO_C(K) do { if (extra) SVRS_LAUNCH((conv3_halo_kernel<K, true>), grid, HL_THREADS, HL_SMEM_BYTES, st, p); \

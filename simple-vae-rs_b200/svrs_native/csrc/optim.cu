@@ -91,7 +91,7 @@ __device__ __forceinline__ void split_kk_(int i, int kk, int& b, int& t) {
 }
 
 template <typename TD>
-__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restrict__ jobs, int njobs,
+__global__ void __launch_bounds__(256, 4) adam_multi_kernel(const AdamJob* __restrict__ jobs, int njobs,
                                                           float* __restrict__ p, const float* __restrict__ g,
                                                           float* __restrict__ m, float* __restrict__ v,
                                                           const double* __restrict__ sumsq, float max_norm, float grad_scale,
@@ -156,53 +156,136 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restri
     }
     const int run = nb * kk;
     const int E = na * run;
-    // torch layout: row a of the tile is a contiguous run of nb*kk floats.  Four independent elements per thread and trip
-    // (16 global loads in flight) - this phase is pure streaming of p / g / m / v.
-    for (int e0 = threadIdx.x; e0 < E; e0 += 4 * 256) {
-        float gi[4], mi[4], vi[4], pi[4];
-        long long idx[4];
-        int slot[4];
+    const long long row0 = jb.off + ((long long)a0 * d1 + b0) * kk;     // first element of tile row a = 0 (torch layout)
+    const long long rstride = (long long)d1 * kk;                        // distance between tile rows
+    // torch layout: row a of the tile is a contiguous run of nb*kk floats.  When the runs are 16-byte aligned (every conv
+    // layer of the models: kk = 9 | 16 with d1 % 4 == 0) p / g / m / v move as float4 - this phase is 28 of the kernel's 32
+    // bytes per parameter - two independent vectors per thread and trip (8 x 16-byte loads in flight).
+    if ((run & 3) == 0 && (rstride & 3) == 0 && (row0 & 3) == 0) {
+        const int run4 = run >> 2;
+        const int Q = na * run4;
+        for (int q0 = threadIdx.x; q0 < Q; q0 += 2 * 256) {
+            float4 gi[2], mi[2], vi[2], pi[2];
+            long long idx[2];
+            int slot[2], tt[2];
+            bool on[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int e = e0 + u * 256;
-            slot[u] = -1;
-            if (e < E) {
-                const int a = e / run, i = e - a * run;
-                int b, t;
-                split_kk_(i, kk, b, t);
-                slot[u] = a * ROW + b * (kk + 1) + t;
-                idx[u] = jb.off + ((long long)(a0 + a) * d1 + b0) * kk + i;
-                gi[u] = jb.layout == 1 ? tile[slot[u]] : g[idx[u]];
-                mi[u] = m[idx[u]]; vi[u] = v[idx[u]]; pi[u] = p[idx[u]];
+            for (int u = 0; u < 2; ++u) {
+                const int qq = q0 + u * 256;
+                on[u] = qq < Q;
+                slot[u] = 0; tt[u] = 0; idx[u] = row0;
+                if (on[u]) {
+                    const int a = qq / run4, i = (qq - a * run4) << 2;
+                    int b, t;
+                    split_kk_(i, kk, b, t);
+                    slot[u] = a * ROW + b * (kk + 1);
+                    tt[u] = t;
+                    idx[u] = row0 + (long long)a * rstride + i;
+                    mi[u] = *reinterpret_cast<const float4*>(m + idx[u]);
+                    vi[u] = *reinterpret_cast<const float4*>(v + idx[u]);
+                    pi[u] = *reinterpret_cast<const float4*>(p + idx[u]);
+                    if (jb.layout != 1) gi[u] = *reinterpret_cast<const float4*>(g + idx[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!on[u]) continue;
+                // shared-memory slots of the four consecutive (b, t) elements of this vector
+                int sl[4];
+                int sb = slot[u], st_ = tt[u];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sl[e] = sb + st_;
+                    if (++st_ == kk) { st_ = 0; sb += kk + 1; }
+                }
+                float ga[4];
+                if (jb.layout == 1) { ga[0] = tile[sl[0]]; ga[1] = tile[sl[1]]; ga[2] = tile[sl[2]]; ga[3] = tile[sl[3]]; }
+                else { ga[0] = gi[u].x; ga[1] = gi[u].y; ga[2] = gi[u].z; ga[3] = gi[u].w; }
+                float ma[4] = {mi[u].x, mi[u].y, mi[u].z, mi[u].w}, va[4] = {vi[u].x, vi[u].y, vi[u].z, vi[u].w};
+                float pa[4] = {pi[u].x, pi[u].y, pi[u].z, pi[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float gg = ga[e] * coef;
+                    ma[e] = b1 * ma[e] + (1.f - b1) * gg;
+                    va[e] = b2 * va[e] + (1.f - b2) * gg * gg;
+                    pa[e] = pa[e] - step_size * (ma[e] / (sqrtf(va[e]) / bc2s + eps));
+                    tile[sl[e]] = pa[e];
+                }
+                *reinterpret_cast<float4*>(m + idx[u]) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+                *reinterpret_cast<float4*>(v + idx[u]) = make_float4(va[0], va[1], va[2], va[3]);
+                *reinterpret_cast<float4*>(p + idx[u]) = make_float4(pa[0], pa[1], pa[2], pa[3]);
             }
         }
+    } else {
+        for (int e0 = threadIdx.x; e0 < E; e0 += 4 * 256) {
+            float gi[4], mi[4], vi[4], pi[4];
+            long long idx[4];
+            int slot[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (slot[u] >= 0) {
-                const float gg = gi[u] * coef;
-                const float mn = b1 * mi[u] + (1.f - b1) * gg;
-                const float vn = b2 * vi[u] + (1.f - b2) * gg * gg;
-                const float pn = pi[u] - step_size * (mn / (sqrtf(vn) / bc2s + eps));
-                m[idx[u]] = mn; v[idx[u]] = vn; p[idx[u]] = pn;
-                tile[slot[u]] = pn;
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 256;
+                slot[u] = -1;
+                if (e < E) {
+                    const int a = e / run, i = e - a * run;
+                    int b, t;
+                    split_kk_(i, kk, b, t);
+                    slot[u] = a * ROW + b * (kk + 1) + t;
+                    idx[u] = row0 + (long long)a * rstride + i;
+                    gi[u] = jb.layout == 1 ? tile[slot[u]] : g[idx[u]];
+                    mi[u] = m[idx[u]]; vi[u] = v[idx[u]]; pi[u] = p[idx[u]];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (slot[u] >= 0) {
+                    const float gg = gi[u] * coef;
+                    const float mn = b1 * mi[u] + (1.f - b1) * gg;
+                    const float vn = b2 * vi[u] + (1.f - b2) * gg * gg;
+                    const float pn = pi[u] - step_size * (mn / (sqrtf(vn) / bc2s + eps));
+                    m[idx[u]] = mn; v[idx[u]] = vn; p[idx[u]] = pn;
+                    tile[slot[u]] = pn;
+                }
             }
         }
     }
     __syncthreads();
     TD* p01 = reinterpret_cast<TD*>(jb.p01);
     TD* p10 = reinterpret_cast<TD*>(jb.p10);
-    if (p01) {                                          // [t][a][b]: half-warps write 16 consecutive b
-        const int tx = threadIdx.x % AD_TB, ty = threadIdx.x / AD_TB;
-        if (tx < nb)
-            for (int t = 0; t < kk; ++t)
-                for (int a = ty; a < na; a += 256 / AD_TB)
-                    p01[((long long)t * d0 + a0 + a) * d1 + b0 + tx] = Cvt<TD>::from_f(tile[a * ROW + tx * (kk + 1) + t]);
+    const bool pair = sizeof(TD) == 2 && (d0 & 1) == 0 && (d1 & 1) == 0;      // bf16 packs: two elements per 4-byte store
+    if (p01) {                                          // [t][a][b]: b fastest
+        if (pair) {
+            const int tx = threadIdx.x % (AD_TB / 2), ty = threadIdx.x / (AD_TB / 2);      // 8 lanes x 4 B = one 32-byte row
+            if (2 * tx < nb)
+                for (int t = 0; t < kk; ++t)
+                    for (int a = ty; a < na; a += 256 / (AD_TB / 2)) {
+                        const float* src = tile + a * ROW + 2 * tx * (kk + 1) + t;
+                        *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p01) + ((long long)t * d0 + a0 + a) * d1 + b0 + 2 * tx) =
+                            __floats2bfloat162_rn(src[0], src[kk + 1]);
+                    }
+        } else {
+            const int tx = threadIdx.x % AD_TB, ty = threadIdx.x / AD_TB;
+            if (tx < nb)
+                for (int t = 0; t < kk; ++t)
+                    for (int a = ty; a < na; a += 256 / AD_TB)
+                        p01[((long long)t * d0 + a0 + a) * d1 + b0 + tx] = Cvt<TD>::from_f(tile[a * ROW + tx * (kk + 1) + t]);
+        }
     }
-    if (p10) {                                          // [t][b][a]: warps write 32 consecutive a
-        if (lane < na)
-            for (int t = 0; t < kk; ++t)
-                for (int b = warp; b < nb; b += 8)
-                    p10[((long long)t * d1 + b0 + b) * d0 + a0 + lane] = Cvt<TD>::from_f(tile[lane * ROW + b * (kk + 1) + t]);
+    if (p10) {                                          // [t][b][a]: a fastest
+        if (pair) {
+            const int tx = threadIdx.x % (AD_TA / 2), ty = threadIdx.x / (AD_TA / 2);      // 16 lanes x 4 B = one 64-byte row
+            if (2 * tx < na)
+                for (int t = 0; t < kk; ++t)
+                    for (int b = ty; b < nb; b += 256 / (AD_TA / 2)) {
+                        const float* src = tile + 2 * tx * ROW + b * (kk + 1) + t;
+                        *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p10) + ((long long)t * d1 + b0 + b) * d0 + a0 + 2 * tx) =
+                            __floats2bfloat162_rn(src[0], src[ROW]);
+                    }
+        } else {
+            if (lane < na)
+                for (int t = 0; t < kk; ++t)
+                    for (int b = warp; b < nb; b += 8)
+                        p10[((long long)t * d1 + b0 + b) * d0 + a0 + lane] = Cvt<TD>::from_f(tile[lane * ROW + b * (kk + 1) + t]);
+        }
     }
 }
 
@@ -250,6 +333,12 @@ extern "C" int svrs_adam_multi(const void* jobs, int njobs, int total_tiles, int
                    "adam_multi: bad args (at most %d jobs)", svrs::AD_MAX_JOBS);
     size_t smem = (size_t)svrs::AD_TA * (svrs::AD_TB * (max_kk + 1) + 1) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_set = false;
+    if (!attr_set) {          // 4-6 CTAs of ~35 KB per SM: ask for the large shared-memory carve-out (the default gave 3)
+        cudaFuncSetAttribute(adam_multi_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(adam_multi_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
     if (pack_dtype == SVRS_F32)
         SVRS_LAUNCH((adam_multi_kernel<float>), total_tiles, 256, smem, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr);
     else if (pack_dtype == SVRS_BF16)

@@ -219,7 +219,8 @@ static void wh_plan(const TapGeom& g, WhParams& p) {
     p.ksteps_total = p.tiles_x * p.tiles_y * g.N;
     int base = p.a_tiles * p.b_chunks;
     static int ctas_target = 0;
-    if (!ctas_target) { const char* e = getenv("SVRS_WG_CTAS"); ctas_target = e ? atoi(e) : num_sms(); }
+    // about half the SMs (measured on the bench step, as for wgrad_tc: weight gradients run next to the dgrad chain)
+    if (!ctas_target) { const char* e = getenv("SVRS_WG_CTAS"); ctas_target = e ? atoi(e) : num_sms() / 2; }
     int ksplit = (ctas_target + base - 1) / base;
     if (ksplit > p.ksteps_total) ksplit = p.ksteps_total;
     if (ksplit < 1) ksplit = 1;
