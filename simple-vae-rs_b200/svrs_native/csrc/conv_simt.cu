@@ -312,6 +312,10 @@ struct WgradArgs {
     TapGeom g;         // prob[0].taps[t].w_off unused; tap id = t
 };
 
+}  // namespace svrs
+#include "wgrad_narrow.cuh"   // bf16 narrow weight gradients on mma.sync + movmatrix (needs WgradArgs)
+namespace svrs {
+
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_taps_kernel(const __grid_constant__ WgradArgs a) {
     pdl_entry();
@@ -923,6 +927,9 @@ extern "C" int svrs_conv2d_wgrad(const void* x, const void* dy, float* dw, float
         } else if (g_tc_enabled && N > 0 && wgrad_tc_supported(dtype, Cout, Cin, a.g.OW, a.g.OH)) {
             rc = launch_wgrad_tc(a.g, dy, x, dw_packed ? dw_packed : dw, dw_packed != nullptr, a.KK, fold_db ? db : nullptr, (cudaStream_t)stream);
             if (fold_db) db = nullptr;
+        } else if (g_tc_enabled_narrow && N > 0 && ksplit <= 0 && wgrad_narrow_mma_takes(a.g, dtype)) {
+            rc = launch_wgrad_narrow_mma(a, db, (cudaStream_t)stream);      // bias gradient folded in (one more MMA)
+            db = nullptr;
         } else
             rc = launch_wgrad(a, dtype, ksplit, (cudaStream_t)stream);
         if (rc) return rc;
