@@ -238,6 +238,34 @@ def gpu_reference_arm(wl, batch, dev, steps=10):
             "unit": wl["unit"], "variants": out, "best": best}
 
 
+def patch_gather_bandwidth(dev, pk, tiles=64, reps=10):
+    """The TMA patch gather + normalise (dataset.py:220-247,265-274 + utils.py:4-23) at BASELINE config 3's full tile batch
+    (64 HR tiles 256x256x4 fp32 -> 1024 patches, fp32 NHWC + bf16 NHWC emitted): algorithmic bytes = tiles read once + both
+    outputs written once; `reps` launches captured in one CUDA graph (no host launch gaps), CUDA-event timed."""
+    from dataset import grid_patch_pair, synthetic_tiles
+    _, hr = synthetic_tiles(tiles, 256, seed=7)
+    hr = hr.to(dev)
+    for _ in range(2):
+        grid_patch_pair(hr, 64, torch.bfloat16)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            out = grid_patch_pair(hr, 64, torch.bfloat16)
+    g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    nbytes = hr.numel() * (4 + 4 + 2)
+    return {"us_per_launch": round(us, 2), "launches": 1.0, "MB_per_launch": round(nbytes / 1e6, 3),
+            "achieved": round(nbytes / us / 1e3, 1), "frac": round(nbytes / us / 1e3 / pk["hbm"], 3),
+            "note": "64 tiles (config 3's whole tile batch), tiles larger than L2 together with the outputs: 168 MB per launch"}
+
+
 def ddp_check(dev, rank, world, pg=None):
     """Hardware parity of the data-parallel step (printed by rank 0 under `ddp_check`): every rank runs ONE fp32 fused
     step on its own shard of a small global batch (sync_bn on, so BatchNorm sees the global batch); rank 0 then repeats
@@ -380,7 +408,14 @@ def main():
         """One step from device-resident tiles: grid-patch gather + normalise (dual emit: fp32 targets and the
         compute-dtype NHWC operands of the first conv layers), then the fused step / the sample decode."""
         if is_sample:
-            yb = grid_patch_pair(lr, P // 2, dtype)
+            if use_graph and sample_graph:
+                sg = sample_graph[0]
+                if sg["lr"].data_ptr() != lr.data_ptr():
+                    sg["lr"].copy_(lr, non_blocking=True)
+                rt.add_replayed(sg["launches"])
+                sg["graph"].replay()
+                return sg["out"]
+            yb = grid_patch_pair(lr, P // 2, dtype, rt=rt)
             return eng.sample_stats_batch(yb, SAMPLES_PER_PATCH)
         if is_vae:
             return tr.step_tiles(hr, patch_size=P, use_graph=use_graph)
@@ -392,8 +427,21 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- warm-up
+    sample_graph = []
     for i in range(args.warmup):
         step_from_device(*dev_sets[i % n_sets])
+    if is_sample and use_graph:
+        # the inference step (patch gather -> encoders -> prior -> S draws -> decoder -> streaming statistics) as one CUDA
+        # graph, like the training step; the engine's device-side noise counter advances on every replay
+        torch.cuda.synchronize()
+        sg = {"lr": dev_sets[0][0].clone(), "graph": torch.cuda.CUDAGraph()}
+        l0g = rt.launches
+        with torch.cuda.graph(sg["graph"]):
+            sg["out"] = eng.sample_stats_batch(grid_patch_pair(sg["lr"], P // 2, dtype, rt=rt), SAMPLES_PER_PATCH)
+        sg["launches"] = rt.launches - l0g
+        sample_graph.append(sg)
+        for i in range(2):
+            step_from_device(*dev_sets[i % n_sets])
     barrier()
 
     # ---------------- timed region 1: device-resident inputs (value)
@@ -415,6 +463,10 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d2h_elems = out.numel()
     loss_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    # untimed warm-up of the host-fed path itself (copy stream, staging buffers, first asynchronous H2D / D2H): one fresh
+    # box showed a ~40 ms one-off inside the first pass through the prefetcher
+    for lr_d, hr_d in TilePrefetcher((host_sets[i % n_sets] for i in range(max(3, args.warmup))), dev):
+        loss_host.copy_(step_from_device(lr_d, hr_d), non_blocking=True)
     barrier()
     e2.record()
     # the package's own feed (dataset.TilePrefetcher): pinned host tiles -> device on a copy stream, double-buffered, so the
@@ -438,10 +490,15 @@ def main():
     # ---------------- roofline of the dominant kernel family (eager, per-launch CUDA events; not in the timed region)
     pk = peaks()
     roof, roof_hbm = None, None
-    if not args.no_profile and not is_sample:
+    if not args.no_profile:
         try:
             from svrs_native import profile as prof
-            roof, roof_hbm = prof.dominant_kernel_roofline(tr, dev_sets[0], pk, steps=2, dtype=dtype)
+            if is_sample:
+                roof, roof_hbm = prof.dominant_kernel_roofline(None, None, pk, steps=2, rt=rt,
+                                                               eager=lambda: step_from_device(*dev_sets[0]))
+            else:
+                roof, roof_hbm = prof.dominant_kernel_roofline(tr, dev_sets[0], pk, steps=2, dtype=dtype)
+            roof_hbm["kernels"]["patch_gather_normalize_64_tiles"] = patch_gather_bandwidth(dev, pk)
             # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (tools/ncu_traffic.py)
             for tname in ("traffic_r02.json", "traffic_r01.json"):
                 tpath = os.path.join(ROOT, "profiles", tname)
@@ -484,7 +541,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": wl["name"], "global_units_per_step": units_per_gpu * world, "parallelism": f"dp{world}",
-                       "cuda_graph": use_graph and not is_sample,
+                       "cuda_graph": use_graph,
                        "l2": f"inputs + activations + weights + Adam state per step far exceed the 126 MB L2 "
                              f"(~{6.24 * 3 * per_gpu * (P // 64) ** 2:.0f} MB of activations); {n_sets} tile sets rotated",
                        "tensor_roofline_units_per_s_per_gpu": pk["tf_sus"] * 1e12 / wl["flop"],

@@ -275,6 +275,8 @@ class Runtime:
         self.branch_streams = os.environ.get("SVRS_BRANCH_STREAMS", "1") != "0"
         self._branches: List[torch.cuda.Stream] = []
         self._branch_open: List[bool] = []
+        self._zero_stream: Optional[torch.cuda.Stream] = None
+        self._zero_pending = False
 
     # kernels of libsvrs_b200.so enqueued so far (bench.py's gpu_launches): the library counts every launch site itself
     # (svrs_launch_count); graph replays add the number of kernels captured in the graph.  The `+= n` bookkeeping at the
@@ -334,13 +336,29 @@ class Runtime:
         lib.fill_zero(_p(self._scratch), self._scratch.numel() * 8, _st())
         self.launches += 1
 
-    def zero_grads(self, with_scratch: bool = False):
+    def zero_grads(self, with_scratch: bool = False, deferred: bool = False):
+        """deferred: the 82 MB gradient fill is only needed by the first weight-gradient kernel of the backward pass, so the
+        fused step runs it on a side stream next to the forward pass; join_zero_grads() is the matching wait."""
         if with_scratch:
             self.zero_scratch()
-        lib.fill_zero(_p(self.store.grad), self.store.grad.numel() * 4, _st())
+        cur = torch.cuda.current_stream()
+        if deferred:
+            if self._zero_stream is None:
+                self._zero_stream = torch.cuda.Stream(device=self.device)
+            self._zero_stream.wait_stream(cur)
+            st = self._zero_stream.cuda_stream
+            self._zero_pending = True
+        else:
+            st = cur.cuda_stream
+        lib.fill_zero(_p(self.store.grad), self.store.grad.numel() * 4, st)
         if not self.fused_grads:
-            lib.fill_zero(_p(self.store.gpack), self.store.gpack.numel() * 4, _st())
+            lib.fill_zero(_p(self.store.gpack), self.store.gpack.numel() * 4, st)
         self.launches += 2
+
+    def join_zero_grads(self):
+        if self._zero_pending:
+            torch.cuda.current_stream().wait_stream(self._zero_stream)
+            self._zero_pending = False
 
     def branch(self, i: int):
         """Context manager: run the enclosed launches on branch stream `i`, forked from the current stream.

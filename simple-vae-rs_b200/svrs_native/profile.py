@@ -97,19 +97,25 @@ def _hbm_bytes(name, a):
     return 0
 
 
-def dominant_kernel_roofline(tr, inputs, pk, steps: int = 2, dtype=None):
+def dominant_kernel_roofline(tr, inputs, pk, steps: int = 2, dtype=None, eager=None, rt=None):
     """-> (roofline of the dominant tensor-core kernel family, roofline_hbm of the bandwidth-bound kernels), both timed per
-    launch with CUDA events in an eager single-stream pass at the bench batch."""
-    import dataset
+    launch with CUDA events in an eager single-stream pass at the bench batch.  tr = fused trainer (training workloads) or
+    None with `eager` (a callable running one eager step) and `rt` (the engine's Runtime) for the inference workload."""
+    if eager is None:
+        def eager():
+            lr, hr = inputs
+            P = tr.eng.P
+            if hasattr(tr.eng, "Wz"):
+                tr.step_tiles(hr, lr, patch_size=P, use_graph=False)
+            else:
+                tr.step_tiles(hr, patch_size=P, use_graph=False)
 
-    def eager():
-        lr, hr = inputs
-        P = tr.eng.P
-        if hasattr(tr.eng, "Wz"):
-            tr.step_tiles(hr, lr, patch_size=P, use_graph=False)
-        else:
-            tr.step_tiles(hr, patch_size=P, use_graph=False)
+    class _Holder:
+        pass
 
+    if tr is None:
+        tr = _Holder()
+        tr.rt = rt
     side, tr.rt.wgrad_side = tr.rt.wgrad_side, False      # per-call event brackets only see the current stream,
     br, tr.rt.branch_streams = tr.rt.branch_streams, False  # and kernels must not overlap while they are being timed
     pad, lib.timing_pad_cycles = lib.timing_pad_cycles, 100000

@@ -425,7 +425,7 @@ class FusedCondTrainer(_FusedBase):
         Wz, Wu = eng.Wz, eng.Wu
         lib.step_increment(_p(self.step_ptr), st)
         rt.fused_grads = self.fused_tail
-        rt.zero_grads(with_scratch=True)
+        rt.zero_grads(with_scratch=True, deferred=True)
         rt.scratch_prezeroed = True
         try:
             with _Nvtx("forward"):
@@ -456,6 +456,7 @@ class FusedCondTrainer(_FusedBase):
         self._early_segs = None
         if self.world > 1 and getattr(self, "_ar_overlap", False) and not self.sync_bn:
             rt.after_phase1 = self._early_allreduce      # only while the fused step's backward runs
+        rt.join_zero_grads()
         try:
             with _Nvtx("backward"):
                 eng.backward(ctx, d_xhat, d_yhat, d_enc_z, d_enc_u, d_mu3, d_lv3, fused_io=True)
@@ -485,7 +486,7 @@ class FusedVaeTrainer(_FusedBase):
         Wd = eng.Wd
         lib.step_increment(_p(self.step_ptr), st)
         rt.fused_grads = self.fused_tail
-        rt.zero_grads(with_scratch=True)
+        rt.zero_grads(with_scratch=True, deferred=True)
         rt.scratch_prezeroed = True
         try:
             with _Nvtx("forward"):
@@ -507,6 +508,7 @@ class FusedVaeTrainer(_FusedBase):
                      B, _p(acc), _p(self.gam), _p(self.gout), _p(self.dgam), ACT_SIGMOID, st)
         rt.launches += 3
         rt.scratch_prezeroed = True
+        rt.join_zero_grads()
         try:
             with _Nvtx("backward"):
                 eng.backward(ctx, d_xhat, d_enc, fused_io=True)
