@@ -20,6 +20,8 @@ import torch.nn as nn
 from .lib import ACT_HARDTANH7, ACT_NONE, ACT_SIGMOID, BF16, F32, SvrsError, SvrsUnsupported, lib
 
 BN_EPS_DEFAULT = 1e-5
+FUSE_BN = os.environ.get("SVRS_FUSE_BN", "1") != "0"            # BatchNorm statistics in the producing conv's epilogue
+FUSE_BN_MAX_MB = float(os.environ.get("SVRS_FUSE_BN_MAX_MB", "5"))   # fuse only for conv outputs up to this size (0 = no limit): on the big maps the extra epilogue costs what the streaming bn_stats pass does (measured 2.856 -> 2.827 ms/step)
 
 
 @dataclass
@@ -583,7 +585,9 @@ class Runtime:
                 bias = op.mod.bias
                 is_last = i == last_conv
                 nxt = net.ops[i + 1] if i + 1 < len(net.ops) else None
-                want_bn = fuse and training and isinstance(nxt, BNOp) and op.fuse_bn is not False
+                want_bn = fuse and FUSE_BN and training and isinstance(nxt, BNOp) and op.fuse_bn is not False
+                if want_bn and FUSE_BN_MAX_MB and n * oh * ow * op.cout * 2 > FUSE_BN_MAX_MB * 1e6:
+                    want_bn = False
                 want_head = is_last and head is not None and fuse and op.fuse_head is not False and op.kind != "ct"
                 want_f32 = is_last and f32_out and self.dtype != torch.float32 and op.fuse_f32 is not False and op.kind != "ct"
                 out_dtype = torch.float32 if want_f32 else self.dtype
