@@ -274,3 +274,49 @@ def test_sample_stats_batched_patches_match_single(golden_dir):
         st = model.sample_stats(y, samples=S)
         assert st["std"].shape == (B, 64, 64) and float(st["std"].min()) >= 0 and float(st["std"].mean()) > 0
         assert "mae" not in st
+
+
+# ------------------------------------------------------------------------------------------------ narrow layers: guard bands
+# (compute-sanitizer is closed on the GPU pool: out-of-bounds WRITES are caught with sentinel guard bands around every output,
+# partial 16-pixel steps and non-power-of-two maps exercise the tail / division paths of the mma.sync narrow kernels)
+class _Guarded:
+    def __init__(self, shape, dtype, fill=float("nan"), pad=4096):
+        n = int(np.prod(shape))
+        self.pad, self.n = pad, n
+        self.buf = torch.full((n + 2 * pad,), 12345.0, device=DEV, dtype=dtype)
+        self.t = self.buf[pad:pad + n].view(shape)
+        self.t.fill_(fill)
+
+    def intact(self):
+        return bool((self.buf[:self.pad] == 12345.0).all() and (self.buf[self.pad + self.n:] == 12345.0).all())
+
+
+@pytest.mark.parametrize("case", [(3, 12, 20, 4, 4, 3), (3, 12, 20, 16, 4, 3), (2, 20, 12, 4, 16, 3), (5, 6, 6, 4, 16, 4), (1, 64, 64, 16, 4, 3),
+                                  (2, 10, 6, 4, 4, 4), (7, 4, 4, 16, 4, 4)])
+def test_narrow_mma_kernels_odd_shapes_and_guard_bands(case):
+    N, H, W, Cin, Cout, ks = case
+    g = torch.Generator().manual_seed(sum(case) + 5)
+    s = 1 if ks == 3 else 2
+    x = _rand((N, Cin, H, W), g)
+    w = (_rand((Cout, Cin, ks, ks), g) * 0.2).to(torch.bfloat16).float()
+    b = torch.randn(Cout, generator=g)
+    xr, wr, br = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, stride=s, padding=1)
+    gy = _rand(tuple(yr.shape), g)
+    yr.backward(gy.double())
+    OH, OW = yr.shape[2:]
+    xd, wd, bd, gyd = nhwc(x.to(DEV), torch.bfloat16), w.to(DEV), b.to(DEV), nhwc(gy.to(DEV), torch.bfloat16)
+    pf, pb = pack(wd, torch.bfloat16)
+    y = _Guarded((N, OH, OW, Cout), torch.bfloat16)
+    dx = _Guarded((N, H, W, Cin), torch.bfloat16)
+    dw = _Guarded((Cout, Cin, ks, ks), torch.float32, fill=0.0)
+    db = _Guarded((Cout,), torch.float32, fill=0.0)
+    lib.conv2d_fprop(xd.data_ptr(), pf.data_ptr(), pb.data_ptr(), bd.data_ptr(), y.t.data_ptr(), BF16, N, H, W, Cin, Cout, ks, 0, st())
+    lib.conv2d_dgrad(gyd.data_ptr(), pb.data_ptr(), pf.data_ptr(), dx.t.data_ptr(), BF16, N, H, W, Cin, Cout, ks, st())
+    lib.conv2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.t.data_ptr(), None, db.t.data_ptr(), BF16, N, H, W, Cin, Cout, ks, 0, st())
+    torch.cuda.synchronize()
+    report(f"narrow {case} fprop", nchw(y.t), yr, 1e-2)
+    report(f"narrow {case} dgrad", nchw(dx.t), xr.grad, 1e-2)
+    report(f"narrow {case} wgrad", dw.t, wr.grad, 2e-5)
+    report(f"narrow {case} bgrad", db.t, br.grad, 2e-5)
+    assert y.intact() and dx.intact() and dw.intact() and db.intact(), "write outside an output buffer"
