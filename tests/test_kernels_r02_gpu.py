@@ -292,7 +292,10 @@ class _Guarded:
 
 
 @pytest.mark.parametrize("case", [(3, 12, 20, 4, 4, 3), (3, 12, 20, 16, 4, 3), (2, 20, 12, 4, 16, 3), (5, 6, 6, 4, 16, 4), (1, 64, 64, 16, 4, 3),
-                                  (2, 10, 6, 4, 4, 4), (7, 4, 4, 16, 4, 4)])
+                                  (2, 10, 6, 4, 4, 4), (7, 4, 4, 16, 4, 4),
+                                  # 16 / 64 -> 16 channels: wgrad16 (mma.sync + ldmatrix.trans from staged rows)
+                                  (2, 16, 16, 16, 16, 3), (1, 64, 64, 64, 16, 3), (3, 32, 32, 16, 16, 3), (2, 16, 48, 64, 16, 3),
+                                  (5, 8, 16, 16, 16, 3)])
 def test_narrow_mma_kernels_odd_shapes_and_guard_bands(case):
     N, H, W, Cin, Cout, ks = case
     g = torch.Generator().manual_seed(sum(case) + 5)
