@@ -328,6 +328,10 @@ static int wg_plan(const TapGeom& g, int KK, WgParams& p) {
     // grid that takes every SM only queues behind (or in front of) the kernel it is supposed to overlap with.
     static const int target = getenv("SVRS_WG_TARGET_CTAS") ? atoi(getenv("SVRS_WG_TARGET_CTAS")) : num_sms() / 2;
     int ksplit = (target + base / 2) / base;
+    // every split pays the fixed costs again (first load ~4 k cycles, TMA-reduce epilogue of group x 64 KB ~10 k cycles): a CTA
+    // should own at least a few 128-pixel steps of MMA work
+    static const int min_ksteps = getenv("SVRS_WG_MIN_KSTEPS") ? atoi(getenv("SVRS_WG_MIN_KSTEPS")) : 4;     // measured on the bench step: 1 -> 4 = -0.9 %, 16 = +4 %
+    if (ksplit > p.ksteps_total / min_ksteps) ksplit = p.ksteps_total / min_ksteps;
     if (ksplit > p.ksteps_total) ksplit = p.ksteps_total;
     if (ksplit < 1) ksplit = 1;
     const int steps_per = (p.ksteps_total + ksplit - 1) / ksplit;
