@@ -35,7 +35,7 @@ for r in data:
 n = len(out)
 print(json.dumps({
     "kernel": kern, "launches": n,
-    "command": "ncu --set full --import-source on --clock-control none -k regex:%s -s 70 -c 40 python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline" % kern,
+    "command": "ncu --set full --clock-control none --profile-from-start off -k regex:%s -c 54 python tools/ncu_step.py" % kern,
     "dram_bytes_per_launch": sum(o["dram_read_bytes"] + o["dram_write_bytes"] for o in out) / max(n, 1),
     "mean_us": sum(o["us"] for o in out) / max(n, 1),
     "per_launch": out}, indent=1))
