@@ -80,22 +80,33 @@ __global__ void __launch_bounds__(WG16_THREADS) wgrad16_mma_kernel(const __grid_
     for (int u = u0; u < u1; ++u) {
         const int n = u / blocks_per_img, y0 = (u % blocks_per_img) * R;
         __syncthreads();                                     // previous step's ldmatrix reads are done
-        // ---- stage X rows y0-1 .. y0+R and G rows y0 .. y0+R-1 (16-byte chunks, zero rows outside the image)
-        const int xchunks = W * (CB / 8);                    // 16-byte chunks per X row
-        for (int i = threadIdx.x; i < (R + 2) * xchunks; i += WG16_THREADS) {
-            const int row = i / xchunks, rem = i - row * xchunks;
-            const int px = rem / (CB / 8), c16 = rem - px * (CB / 8);
-            const int yy = y0 - 1 + row;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (yy >= 0 && yy < a.H)
-                v = __ldg(reinterpret_cast<const uint4*>(a.x + (((long long)n * a.H + yy) * W + px) * CB + c16 * 8));
-            *reinterpret_cast<uint4*>(xs + (size_t)row * xrow_bytes + (size_t)(px + 1) * XP + c16 * 16) = v;
-        }
-        for (int i = threadIdx.x; i < R * W * 2; i += WG16_THREADS) {
-            const int row = i / (W * 2), rem = i - row * (W * 2);
-            const int px = rem >> 1, c16 = rem & 1;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.g + (((long long)n * a.H + y0 + row) * W + px) * 16 + c16 * 8));
-            *reinterpret_cast<uint4*>(gs + ((size_t)row * W + px) * GP + c16 * 16) = v;
+        // ---- stage X rows y0-1 .. y0+R and G rows y0 .. y0+R-1 (16-byte chunks, zero rows outside the image).  A thread keeps
+        //      its 16-byte column of the pixel (c16) and walks pixels with a fixed stride: no index arithmetic per chunk (the
+        //      first version spent 3x more instructions computing chunk indices than on ldmatrix + MMA)
+        {
+            constexpr int CPP = CB / 8;                      // 16-byte chunks per pixel
+            constexpr int PPP = WG16_THREADS / CPP;          // pixels per pass of the CTA
+            const int c16 = threadIdx.x % CPP, pxl = threadIdx.x / CPP;
+            for (int row = 0; row < R + 2; ++row) {
+                const int yy = y0 - 1 + row;
+                const bool ok = yy >= 0 && yy < a.H;
+                const __nv_bfloat16* src = a.x + (((long long)n * a.H + (ok ? yy : 0)) * W) * CB + c16 * 8;
+                uint8_t* dst = xs + (size_t)row * xrow_bytes + XP + c16 * 16;
+#pragma unroll 4
+                for (int px = pxl; px < W; px += PPP) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)px * CB));
+                    *reinterpret_cast<uint4*>(dst + (size_t)px * XP) = v;
+                }
+            }
+            const int gc = threadIdx.x & 1, gpx = threadIdx.x >> 1;
+            for (int row = 0; row < R; ++row) {
+                const __nv_bfloat16* src = a.g + (((long long)n * a.H + y0 + row) * W) * 16 + gc * 8;
+                uint8_t* dst = gs + (size_t)row * W * GP + gc * 16;
+#pragma unroll 2
+                for (int px = gpx; px < W; px += WG16_THREADS / 2)
+                    *reinterpret_cast<uint4*>(dst + (size_t)px * GP) = __ldg(reinterpret_cast<const uint4*>(src + (long long)px * 16));
+            }
         }
         __syncthreads();
         // ---- MMAs: CB = 16 -> warps split the 16-pixel steps; CB = 64 -> warps split the channel chunks
@@ -179,7 +190,11 @@ static int launch_wgrad16(const void* x, const void* g, float* dw, float* db, in
     a.x = reinterpret_cast<const __nv_bfloat16*>(x); a.g = reinterpret_cast<const __nv_bfloat16*>(g);
     a.dw = dw; a.db = db; a.N = N; a.H = H; a.W = W; a.R = W >= 32 ? 2 : 4;
     a.units = N * (H / a.R);
-    long long ctas = 2LL * num_sms();
+    // 2 CTAs per SM.  MEASURED (SVRS_WG16_CTAS_PER_SM, tools/narrow_bench.py): 4 and 8 per SM are SLOWER (16->16 at 64x64:
+    // 45 / 63 / 63 us; whole step 2.79 / 2.87 / 2.98 ms) although the kernel stalls on its staging loads at 13 % warp
+    // occupancy - every extra CTA pays the fold + cluster reduction + atomics of 9 * CB * 16 outputs again
+    static const int per_sm = getenv("SVRS_WG16_CTAS_PER_SM") ? atoi(getenv("SVRS_WG16_CTAS_PER_SM")) : 2;
+    long long ctas = (long long)per_sm * num_sms();
     if (ctas > a.units) ctas = a.units;
     a.units_per_cta = (int)((a.units + ctas - 1) / ctas);
     ctas = (a.units + a.units_per_cta - 1) / a.units_per_cta;

@@ -16,7 +16,11 @@ CASES = [  # name, H, Cin, Cout, ksize, form
     ("enc_x.0.conv   c3 4->4   @64", 64, 4, 4, 3), ("enc_x.0.down   c4 4->16  @64", 64, 4, 16, 4),
     ("enc_y.0.conv   c3 4->4   @32", 32, 4, 4, 3), ("enc_y.0.down   c4 4->16  @32", 32, 4, 16, 4),
     ("dec_x.7        c3 16->4  @64", 64, 16, 4, 3), ("dec_y.6        c3 16->4  @32", 32, 16, 4, 3),
+    ("dec_x.6        c3 16->16 @64", 64, 16, 16, 3), ("dec_x.5        c3 64->16 @64", 64, 64, 16, 3),
+    ("dec_y.5        c3 16->16 @32", 32, 16, 16, 3), ("enc_y.1.conv   c3 16->16 @16", 16, 16, 16, 3),
 ]
+if os.environ.get("ONLY16"):
+    CASES = CASES[-4:]
 
 
 def timeit(fn, reps=20):
