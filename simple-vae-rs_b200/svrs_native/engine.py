@@ -249,6 +249,7 @@ class Runtime:
         self._unpack_cache: Dict = {}
         self._unpacked_early: set = set()
         self.after_phase1 = None   # optional hook(list of Nets whose backward is complete), see CondEngine.backward
+        self.after_heads = None    # same, called as soon as the prior heads + u_to_z are complete (inside their branch)
         self.scratch_prezeroed = False   # the fused step zeroes all BatchNorm scratch once per step
         self.packs_dirty = True
         self._replayed = 0         # kernels re-issued by CUDA-graph replays (not seen by the library's own counter)
@@ -1000,6 +1001,10 @@ class CondEngine:
                 lib.copy2d(d_joint.data_ptr() + es * c16, rt.dt, 2 * c16, _p(d_uz), rt.dt, c16, rows, c16, 0, _st())
                 rt.launches += 1
                 du16 = rt.net_backward(N["u_to_z"], ctx["t_uz"], d_uz, True)
+            if rt.after_heads is not None:
+                # prior heads + u_to_z are done long before the decoder_x chain: their 15 M parameters (60 MB of gradients) can
+                # travel while the rest of the backward pass runs
+                rt.after_heads([N[k] for k in ("u_to_z", "mu_u_y_to_z", "logvar_u_y_to_z")])
         if d_xhat is not None:
             g_x = d_xhat if fused_io else self._image_grad(d_xhat, ctx["x_hat_nhwc"], B, P)
             ds8 = rt.net_backward(N["decoder_x"], ctx["t_dx"], g_x, True, act_done=True)
@@ -1007,8 +1012,9 @@ class CondEngine:
             rt.to_nchw(ds8, d_stack, 2 * Wz)
         rt.join(0, 1)
         if rt.after_phase1 is not None:
-            # decoders, prior heads and u_to_z are done (their wgrads are queued on the wgrad stream)
-            rt.after_phase1([N[k] for k in ("decoder_x", "decoder_y", "mu_u_y_to_z", "logvar_u_y_to_z", "u_to_z")])
+            # decoders (and, unless after_heads took them, prior heads and u_to_z) are done; their wgrads are queued on the wgrad streams
+            rest = ("decoder_x", "decoder_y") if rt.after_heads is not None else ("decoder_x", "decoder_y", "mu_u_y_to_z", "logvar_u_y_to_z", "u_to_z")
+            rt.after_phase1([N[k] for k in rest])
         if du16 is not None:
             if d_u is None:
                 d_u = zeros(B, Wu)

@@ -131,6 +131,7 @@ class _FusedBase:
         are scheduled ahead of queued compute CTAs as soon as any SM frees up.  SVRS_AR_OVERLAP=0 restores the single
         all-reduce after the backward pass."""
         self._ar_overlap = os.environ.get("SVRS_AR_OVERLAP", "1") == "1"
+        self._ar_two_buckets = os.environ.get("SVRS_AR_BUCKETS", "2") != "1"
         self._comm_stream = torch.cuda.Stream(device=dev, priority=-1)
         self._ar_pg = self.pg
         max_ctas = int(os.environ.get("SVRS_NCCL_MAX_CTAS", "8"))
@@ -262,23 +263,25 @@ class _FusedBase:
         return [(lo, min(hi, store.total)) for lo, hi in merged]
 
     def _early_allreduce(self, nets):
-        """Called by CondEngine.backward when phase 1 (decoders, prior heads, u_to_z) is complete: their gradients are the
-        contiguous range [0, early_end) of the flat buffer (ParamStore lays the encoders out last) - ONE all-reduce on the
-        communication stream, overlapped with the encoders' backward pass."""
+        """Called by CondEngine.backward when a group of sub-networks is complete - first the prior heads + u_to_z (15 M
+        parameters, done a few hundred microseconds into the backward pass), then the decoders: each group is ONE contiguous
+        range of the flat gradient buffer (ParamStore lays the encoders out last, the heads right before them) and ONE
+        all-reduce on the communication stream, overlapped with whatever backward work is still running."""
         rt = self.rt
         store = rt.store
         segs = self._net_segments(nets)
-        assert segs == [(0, store.early_end)], (segs, store.early_end)
+        assert len(segs) == 1 and segs[0][1] <= store.early_end, (segs, store.early_end)
+        lo, hi = segs[0]
         comm = self._comm_stream
         comm.wait_stream(torch.cuda.current_stream())
         if rt._side_busy:
-            for side in rt.wgrad_streams():            # the wgrads queued so far are exactly those of `nets`
+            for side in rt.wgrad_streams():            # weight gradients queued so far (a superset of those of `nets`)
                 comm.wait_stream(side)
         with torch.cuda.stream(comm):
             if not rt.fused_grads:
                 rt.unpack_nets(nets)
-            torch.distributed.all_reduce(store.grad_full[:store.early_end], group=self._ar_pg)
-        self._early_segs = segs
+            torch.distributed.all_reduce(store.grad_full[lo:hi], group=self._ar_pg)
+        self._early_segs = (self._early_segs or []) + segs
 
     def _allreduce_all(self):
         """The rest of the exchange after the backward pass: the encoders' range plus the gamma gradients in the tail of the
@@ -456,6 +459,7 @@ class FusedCondTrainer(_FusedBase):
         self._early_segs = None
         if self.world > 1 and getattr(self, "_ar_overlap", False) and not self.sync_bn:
             rt.after_phase1 = self._early_allreduce      # only while the fused step's backward runs
+            rt.after_heads = self._early_allreduce if self._ar_two_buckets else None
         rt.join_zero_grads()
         try:
             with _Nvtx("backward"):
@@ -463,6 +467,7 @@ class FusedCondTrainer(_FusedBase):
         finally:
             rt.scratch_prezeroed = False
             rt.after_phase1 = None
+            rt.after_heads = None
         with _Nvtx("allreduce"):
             self._allreduce_all()
         with _Nvtx("optimizer"):
