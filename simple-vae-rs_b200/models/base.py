@@ -71,6 +71,9 @@ class BaseVAE(nn.Module, metaclass=abc.ABCMeta):
         self._trainer = None
         self._anchor = None
         self.use_cuda_graph = os.environ.get("SVRS_CUDA_GRAPH", "1") == "1"
+        # data parallel only: BatchNorm statistics of the GLOBAL batch (per-layer all-reduce of the 2C sums) - exact parity with
+        # a single process on the global batch; default = per-rank statistics (standard DDP)
+        self.sync_bn = os.environ.get("SVRS_SYNC_BN", "0") == "1"
 
     # ------------------------------------------------------------------ kernel engine plumbing
     def set_compute_dtype(self, dtype: torch.dtype):

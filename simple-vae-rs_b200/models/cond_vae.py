@@ -68,7 +68,7 @@ class Cond_SRVAE(BaseVAE):
     def _fused_trainer(self, optimizer):
         from svrs_native.trainer import FusedCondTrainer
         if self._trainer is None or self._trainer.optimizer is not optimizer:
-            self._trainer = FusedCondTrainer(self, optimizer)
+            self._trainer = FusedCondTrainer(self, optimizer, sync_bn=getattr(self, "sync_bn", False))
         return self._trainer
 
     def _run(self, x, y, eps_u=None, eps_z=None):

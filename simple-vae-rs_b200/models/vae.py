@@ -36,7 +36,7 @@ class VAE(BaseVAE):
     def _fused_trainer(self, optimizer):
         from svrs_native.trainer import FusedVaeTrainer
         if self._trainer is None or self._trainer.optimizer is not optimizer:
-            self._trainer = FusedVaeTrainer(self, optimizer)
+            self._trainer = FusedVaeTrainer(self, optimizer, sync_bn=getattr(self, "sync_bn", False))
         return self._trainer
 
     # ------------------------------------------------------------------ reference API
