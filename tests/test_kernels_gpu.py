@@ -2,8 +2,8 @@
 reference calls at that site (and against oracle/np_primitives for first-principles definitions).
 
 Tolerances: fp32 kernels 1e-5 relative to the tensor's max magnitude (north star: 1e-5 in fp32);
-bf16 kernels 1e-2 relative-to-max per element (bf16 has 8 mantissa bits; inputs are pre-rounded to bf16 so the
-only error is the bf16 rounding of the OUTPUT plus fp32 accumulation order)."""
+bf16 kernels 7e-3 relative-to-max per element (<= 2x the measured 3.6e-3: bf16 has 8 mantissa bits; inputs are pre-rounded to
+bf16 so the only error is the bf16 rounding of the OUTPUT plus fp32 accumulation order)."""
 import numpy as np
 import pytest
 import torch
@@ -14,7 +14,7 @@ from helpers import BF16, F32, dt, lib, nchw, nhwc, pack, report, st
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-TOL = {torch.float32: 1e-5, torch.bfloat16: 1e-2}
+TOL = {torch.float32: 1e-5, torch.bfloat16: 7e-3}      # bf16: <= 2x the measured 3.6e-3 (output rounding to bf16 = 2^-9 relative)
 
 CONV_CASES = [
     # N, H, W, Cin, Cout
@@ -492,8 +492,8 @@ def test_conv_tc_all_forms(case):
         lib.set_tc_enabled(1)
         ran_f = lib.tc_would_run(BF16, Cin, Cout, OH if form != "ct" else H, OW if form != "ct" else W)
         print(f"[parity] {form} {case}: conv_tc taken for fprop: {bool(ran_f)}")
-        report(f"conv_tc {form} fprop {case} vs fp64", nchw(res[1][0]), yr, 1e-2)
-        report(f"conv_tc {form} dgrad {case} vs fp64", nchw(res[1][1]), xr.grad, 1e-2)
+        report(f"conv_tc {form} fprop {case} vs fp64", nchw(res[1][0]), yr, 7e-3)
+        report(f"conv_tc {form} dgrad {case} vs fp64", nchw(res[1][1]), xr.grad, 7e-3)
         report(f"conv_tc {form} fprop {case} vs simt", res[1][0].float(), res[0][0].float(), 8e-3)
         report(f"conv_tc {form} dgrad {case} vs simt", res[1][1].float(), res[0][1].float(), 8e-3)
 
@@ -597,8 +597,8 @@ def test_conv3_halo_kernel(case):
             print(f"[parity] conv3 halo mode {mode} {case}: fprop rel err {ef:.3e}, dgrad rel err {ed:.3e}")
     finally:
         lib.set_halo_mode(1)
-    assert max(errs[0]) < 1e-2, "per-tap kernel"
-    assert max(errs[1]) < 1e-2, f"halo kernel: {errs}"
+    assert max(errs[0]) < 7e-3, "per-tap kernel"
+    assert max(errs[1]) < 7e-3, f"halo kernel: {errs}"
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, 64, 64, "c3"), (2, 8, 8, 64, 128, "c4"), (3, 8, 8, 128, 64, "ct"), (2, 16, 16, 16, 32, "c3")])

@@ -118,7 +118,7 @@ def test_conv_fprop_ex_head_and_bn_sums(case):
                             sums.data_ptr(), N, H, W, Cin, Cout, ks, 0, st())
         torch.cuda.synchronize()
         s = sums.view(R, 2, Cout).sum(0).cpu()
-        report(f"fprop_ex {case} y", nchw(y), yr, 1e-2)
+        report(f"fprop_ex {case} y", nchw(y), yr, 7e-3)
         report(f"fprop_ex {case} bn sum", s[0], yr.sum(dim=(0, 2, 3)), 1e-5, atol=1e-3)
         report(f"fprop_ex {case} bn sumsq", s[1], (yr * yr).sum(dim=(0, 2, 3)), 1e-5)
     except SvrsUnsupported as ex:
@@ -158,7 +158,7 @@ def test_convT_fprop_ex_bn_sums(case):
                          N, H, W, Cin, Cout, 0, st())
     torch.cuda.synchronize()
     s = sums.view(R, 2, Cout).sum(0).cpu()
-    report(f"convT fprop_ex {case} y", nchw(y), yr, 1e-2)
+    report(f"convT fprop_ex {case} y", nchw(y), yr, 7e-3)
     report(f"convT fprop_ex {case} bn sum", s[0], yr.sum(dim=(0, 2, 3)), 1e-5, atol=1e-3)
     report(f"convT fprop_ex {case} bn sumsq", s[1], (yr * yr).sum(dim=(0, 2, 3)), 1e-5)
 
@@ -318,8 +318,8 @@ def test_narrow_mma_kernels_odd_shapes_and_guard_bands(case):
     lib.conv2d_dgrad(gyd.data_ptr(), pb.data_ptr(), pf.data_ptr(), dx.t.data_ptr(), BF16, N, H, W, Cin, Cout, ks, st())
     lib.conv2d_wgrad(xd.data_ptr(), gyd.data_ptr(), dw.t.data_ptr(), None, db.t.data_ptr(), BF16, N, H, W, Cin, Cout, ks, 0, st())
     torch.cuda.synchronize()
-    report(f"narrow {case} fprop", nchw(y.t), yr, 1e-2)
-    report(f"narrow {case} dgrad", nchw(dx.t), xr.grad, 1e-2)
+    report(f"narrow {case} fprop", nchw(y.t), yr, 7e-3)
+    report(f"narrow {case} dgrad", nchw(dx.t), xr.grad, 7e-3)
     report(f"narrow {case} wgrad", dw.t, wr.grad, 2e-5)
     report(f"narrow {case} bgrad", db.t, br.grad, 2e-5)
     assert y.intact() and dx.intact() and dw.intact() and db.intact(), "write outside an output buffer"

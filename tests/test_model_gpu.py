@@ -5,8 +5,8 @@
 Tolerances (stated here, as the north star asks; "rel" = max |err| / max |reference| of the tensor):
   fp32 mode : forward activations and ELBO terms 1e-5 rel; raw parameter gradients 2e-4 rel (fp32 atomics reorder
               the wgrad reduction); global gradient norm 1e-4; BN running stats 1e-5.
-  bf16 mode : ELBO terms 1e-3 rel (kld terms, which are differences of O(1) numbers, 5e-3); activations 3e-2 rel
-              (bf16 keeps 8 mantissa bits and every layer rounds).
+  bf16 mode : ELBO terms 2e-4 rel (NLL terms, loss) / 1e-3 (KL terms) - inside the north star's 1e-3; decoder images 4e-3
+              rel-to-max, encoder / prior heads 3e-2 (<= 2x measured; the bf16 operand format, tests/test_parity_configs_gpu.py).
   100 steps : ELBO curve within 2e-3 rel of the reference's curve; parameters whose gradient is mathematically
               zero (conv bias feeding a BatchNorm) are excluded - Adam turns their rounding noise into +-lr steps.
 """
@@ -200,18 +200,21 @@ def test_cond_bf16_mode(golden_dir):
     model.train()
     outs = model(x.to(DEV), y.to(DEV), eu.to(DEV), ez.to(DEV))
     for n, got in zip(NAMES8, outs):
-        report(f"bf16 fwd {n} vs golden", got, fx["outputs"][n], 3e-2)
+        # decoder images: fp32 sigmoid tail, measured 1.6e-3; encoder / prior heads: measured <= 1.4e-2 (the bf16 operand
+        # format itself, see tests/test_parity_configs_gpu.py) - bounds <= 2x measured
+        report(f"bf16 fwd {n} vs golden", got, fx["outputs"][n], 4e-3 if n in ("x_hat", "y_hat") else 3e-2)
     model2, _ = FX.build(fx, device=DEV, dtype=torch.bfloat16)
     model2.train()
     tr = FusedCondTrainer(model2)
     t = tr.step(x.to(DEV), y.to(DEV), eu.to(DEV), ez.to(DEV)).cpu()
     ref = fx["curve"][0]       # [loss, mse_x, kld_u, mse_y, kld_z, norm]
-    report("bf16 ELBO term mse_x", t[0].reshape(1), ref[1].reshape(1), 1e-3)
-    report("bf16 ELBO term kld_u", t[1].reshape(1), ref[2].reshape(1), 5e-3)
-    report("bf16 ELBO term mse_y", t[2].reshape(1), ref[3].reshape(1), 1e-3)
-    report("bf16 ELBO term kld_z", t[3].reshape(1), ref[4].reshape(1), 5e-3)
-    report("bf16 loss", t[4].reshape(1), ref[0].reshape(1), 1e-3)
-    report("bf16 grad norm", tr.grad_norm().reshape(1), ref[5].reshape(1), 3e-2)
+    # north star: ELBO terms within 1e-3 relative in bf16
+    report("bf16 ELBO term mse_x", t[0].reshape(1), ref[1].reshape(1), 2e-4)
+    report("bf16 ELBO term kld_u", t[1].reshape(1), ref[2].reshape(1), 1e-3)
+    report("bf16 ELBO term mse_y", t[2].reshape(1), ref[3].reshape(1), 2e-4)
+    report("bf16 ELBO term kld_z", t[3].reshape(1), ref[4].reshape(1), 1e-3)
+    report("bf16 loss", t[4].reshape(1), ref[0].reshape(1), 2e-4)
+    report("bf16 grad norm", tr.grad_norm().reshape(1), ref[5].reshape(1), 2e-3)
 
 
 def test_cuda_graph_replay_matches_eager(golden_dir):
