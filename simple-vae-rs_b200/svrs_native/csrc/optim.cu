@@ -1,5 +1,6 @@
 // optim.cu - global-norm clip + Adam on flat fp32 buffers (models/base.py:106-107, train.py:65).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace svrs {
 
@@ -64,12 +65,19 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
 
 // ------------------------------------------------------------------------------------------------------------------
 // adam_multi_kernel: the whole optimiser tail of the fused step in ONE launch over a device job table.
-//   * conv-weight jobs (d1 > 0): a CTA owns a 32 (d0) x 16 (d1) x kk tile of one layer.  The gradient is read in the layout
+//   * conv-weight jobs (d1 > 0): a CTA owns a 16 (d0) x 16 (d1) x kk tile of one layer.  The gradient is read in the layout
 //     the weight-gradient kernel left it in - torch [d0][d1][kk] (SIMT kernels) or the per-tap packed scratch
 //     [kk][d1][d0] (tcgen05 kernels' TMA-reduce epilogue) - transposed through shared memory, Adam runs on the torch-layout
-//     master weight / moments (coalesced runs of 16*kk floats), and the updated weight goes back through shared memory
-//     into BOTH compute-dtype packs [kk][d0][d1] and [kk][d1][d0] that the next step's fprop / dgrad kernels consume.
+//     master weight / moments, and the updated weight goes back through shared memory into BOTH compute-dtype packs
+//     [kk][d0][d1] and [kk][d1][d0] that the next step's fprop / dgrad kernels consume.
 //     This replaces unpack_multi + clip_adam + pack_multi (three passes over 82 MB each) by one.
+//     Full tiles of the 3x3 / 4x4 layers (all but a few hundred parameters) move m / v / p with 1-D BULK copies
+//     (cp.async.bulk + mbarrier): the tile's 16 rows of each array - contiguous runs of 16*kk floats in the torch layout -
+//     land in shared memory, Adam runs in place there, and the rows leave as bulk stores again while the threads write
+//     the packs.  MEASURED (tools/adam_bench.py, 20.6 M parameters): register-file loads (float4 LDG, 8 in flight per
+//     thread, 4 CTAs per SM) cap this kernel at 195 us = 3.4 TB/s whatever the instruction count (a version with half
+//     the instructions and one with approximate div / sqrt ran at the same 195 us; reads alone, all stores removed, took
+//     105-123 us) - the same ceiling bn_reduce hit before it went to bulk copies.
 //   * plain jobs (d1 == 0): biases and BatchNorm affine parameters, d0 contiguous elements from `off`.
 // p / g / m / v are the flat buffers; a job addresses all four at the same element offset.
 // ------------------------------------------------------------------------------------------------------------------
@@ -82,7 +90,23 @@ struct AdamJob {
     int tile0;          // first global tile of this job
     int tiles_b;        // tiles along d1 (conv jobs)
 };
-constexpr int AD_TA = 32, AD_TB = 16, AD_PLAIN = 2048, AD_MAX_JOBS = 512;
+constexpr int AD_TA = 16, AD_TB = 16, AD_PLAIN = 2048, AD_MAX_JOBS = 512;
+// shared memory of a CTA: the padded transpose tile [AD_TA][AD_TB * (kk + 1) + 1] (rounded up to 128 bytes), then the dense
+// m / v / p rows of the bulk path
+__host__ __device__ constexpr int ad_pad_floats(int kk) { return (AD_TA * (AD_TB * (kk + 1) + 1) + 31) / 32 * 32; }
+
+__device__ __forceinline__ void bulk_ld_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_st_1d(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ unsigned pack_bf16x2_(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<unsigned*>(&t);
+}
 
 __device__ __forceinline__ void split_kk_(int i, int kk, int& b, int& t) {
     if (kk == 16) { b = i >> 4; t = i & 15; }
@@ -90,19 +114,176 @@ __device__ __forceinline__ void split_kk_(int i, int kk, int& b, int& t) {
     else { b = i / kk; t = i - kk * b; }
 }
 
+// Full 16 x 16 x KK tile, bf16 packs.  On entry the bulk loads of the tile's m / v / p rows (dense: row a at a * 16 * KK
+// floats) are in flight on `bar`.
+template <int KK>
+__device__ __forceinline__ void adam_tile_bulk(const AdamJob& jb, const int a0, const int b0, float* __restrict__ tile,
+                                               float* __restrict__ dm, float* __restrict__ dv, float* __restrict__ dp,
+                                               const uint32_t bar, float* __restrict__ p, const float* __restrict__ g,
+                                               float* __restrict__ m, float* __restrict__ v, const long long row0,
+                                               const long long rstride, const float coef, const float step_size,
+                                               const float bc2s, const float b1, const float b2, const float eps) {
+    constexpr int ROW = AD_TB * (KK + 1) + 1;
+    constexpr int RUN = AD_TB * KK, RUN4 = RUN / 4;      // floats / float4 per tile row (torch layout): 144 | 256, 36 | 64
+    constexpr int Q = AD_TA * RUN4;                      // float4 per array and tile: 576 | 1024
+    constexpr int TRIPS = (Q + 255) / 256;               // 3 | 4
+    const int d0 = jb.d0, d1 = jb.d1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool packed = jb.layout == 1;
+    if (packed) {        // [kk][d1][d0] -> tile[a][b][t]: a half-warp reads the 16 consecutive d0 of one (t, b)
+        const int a = lane & 15, b = 2 * warp + (lane >> 4);
+        const float* gj = g + jb.off + (long long)(b0 + b) * d0 + a0 + a;
+        float r[KK];
+#pragma unroll
+        for (int t = 0; t < KK; ++t) r[t] = __ldcs(gj + (long long)t * d1 * d0);
+#pragma unroll
+        for (int t = 0; t < KK; ++t) tile[a * ROW + b * (KK + 1) + t] = r[t];
+    }
+    float4 gi[TRIPS];
+    if (!packed) {
+#pragma unroll
+        for (int j = 0; j < TRIPS; ++j) {
+            const int q = threadIdx.x + 256 * j;
+            if (q < Q) {
+                const int a = q / RUN4, i4 = q - a * RUN4;
+                gi[j] = __ldcs(reinterpret_cast<const float4*>(g + row0 + (long long)a * rstride + 4 * i4));
+            }
+        }
+    }
+    __syncthreads();                                     // transposed gradient tile complete
+    mbar_wait(bar, 0);                                   // m / v / p rows have landed
+#pragma unroll
+    for (int j = 0; j < TRIPS; ++j) {
+        const int q = threadIdx.x + 256 * j;
+        if (q < Q) {
+            const int a = q / RUN4, i4 = q - a * RUN4;
+            int sl[4];
+            {
+                int b = (4 * i4) / KK, t = 4 * i4 - b * KK;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sl[e] = a * ROW + b * (KK + 1) + t;
+                    if (++t == KK) { t = 0; ++b; }
+                }
+            }
+            const float4 m4 = reinterpret_cast<const float4*>(dm)[q], v4 = reinterpret_cast<const float4*>(dv)[q];
+            const float4 p4 = reinterpret_cast<const float4*>(dp)[q];
+            float ga[4];
+            if (packed) { ga[0] = tile[sl[0]]; ga[1] = tile[sl[1]]; ga[2] = tile[sl[2]]; ga[3] = tile[sl[3]]; }
+            else { ga[0] = gi[j].x; ga[1] = gi[j].y; ga[2] = gi[j].z; ga[3] = gi[j].w; }
+            float ma[4] = {m4.x, m4.y, m4.z, m4.w}, va[4] = {v4.x, v4.y, v4.z, v4.w}, pa[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float gg = ga[e] * coef;
+                ma[e] = b1 * ma[e] + (1.f - b1) * gg;
+                va[e] = b2 * va[e] + (1.f - b2) * gg * gg;
+                pa[e] = pa[e] - step_size * (ma[e] / (sqrtf(va[e]) / bc2s + eps));
+                tile[sl[e]] = pa[e];
+            }
+            reinterpret_cast<float4*>(dm)[q] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+            reinterpret_cast<float4*>(dv)[q] = make_float4(va[0], va[1], va[2], va[3]);
+            reinterpret_cast<float4*>(dp)[q] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+        }
+    }
+    fence_proxy_async_smem();                            // generic-proxy writes of the dense rows -> visible to the bulk stores
+    __syncthreads();
+    if (warp == 0) {
+        if (lane < AD_TA) {
+            const long long r = row0 + (long long)lane * rstride;
+            bulk_st_1d(m + r, smem_u32(dm + lane * RUN), RUN * 4);
+            bulk_st_1d(v + r, smem_u32(dv + lane * RUN), RUN * 4);
+            bulk_st_1d(p + r, smem_u32(dp + lane * RUN), RUN * 4);
+        }
+        bulk_commit();
+    }
+    // bf16 packs from the transpose tile, 8 elements (16 bytes) per store
+    const int h = threadIdx.x & 1;
+    if (jb.p01) {                                        // [t][a][b]: a (t, a) row is 16 b = two 16-byte halves
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(jb.p01);
+#pragma unroll
+        for (int r = threadIdx.x >> 1; r < KK * AD_TA; r += 128) {
+            const int t = r >> 4, a = r & 15;
+            const float* src = tile + a * ROW + 8 * h * (KK + 1) + t;
+            uint4 o;
+            o.x = pack_bf16x2_(src[0], src[KK + 1]);
+            o.y = pack_bf16x2_(src[2 * (KK + 1)], src[3 * (KK + 1)]);
+            o.z = pack_bf16x2_(src[4 * (KK + 1)], src[5 * (KK + 1)]);
+            o.w = pack_bf16x2_(src[6 * (KK + 1)], src[7 * (KK + 1)]);
+            *reinterpret_cast<uint4*>(dst + ((long long)t * d0 + a0 + a) * d1 + b0 + 8 * h) = o;
+        }
+    }
+    if (jb.p10) {                                        // [t][b][a]: a (t, b) row is 16 a = two 16-byte halves
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(jb.p10);
+#pragma unroll
+        for (int r = threadIdx.x >> 1; r < KK * AD_TB; r += 128) {
+            const int t = r >> 4, b = r & 15;
+            const float* src = tile + 8 * h * ROW + b * (KK + 1) + t;
+            uint4 o;
+            o.x = pack_bf16x2_(src[0], src[ROW]);
+            o.y = pack_bf16x2_(src[2 * ROW], src[3 * ROW]);
+            o.z = pack_bf16x2_(src[4 * ROW], src[5 * ROW]);
+            o.w = pack_bf16x2_(src[6 * ROW], src[7 * ROW]);
+            *reinterpret_cast<uint4*>(dst + ((long long)t * d1 + b0 + b) * d0 + a0 + 8 * h) = o;
+        }
+    }
+    if (warp == 0) bulk_wait_read_0();                   // shared memory must outlive the bulk stores' reads
+}
+
 template <typename TD>
-__global__ void __launch_bounds__(256, 4) adam_multi_kernel(const AdamJob* __restrict__ jobs, int njobs,
+__global__ void __launch_bounds__(256, 3) adam_multi_kernel(const AdamJob* __restrict__ jobs, int njobs,
                                                           float* __restrict__ p, const float* __restrict__ g,
                                                           float* __restrict__ m, float* __restrict__ v,
                                                           const double* __restrict__ sumsq, float max_norm, float grad_scale,
                                                           float lr, float b1, float b2, float eps,
-                                                          const long long* __restrict__ step_ptr) {
+                                                          const long long* __restrict__ step_ptr, const int pad_floats,
+                                                          const int bulk_ok) {
     pdl_entry();
-    extern __shared__ float tile[];
+    extern __shared__ __align__(128) float tile[];
     __shared__ int s_tile0[AD_MAX_JOBS];
     __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+    __shared__ __align__(8) unsigned long long s_bar;
+    const uint32_t bar = smem_u32(&s_bar);
     for (int i = threadIdx.x; i < njobs; i += blockDim.x) s_tile0[i] = jobs[i].tile0;
     if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_tile0[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const AdamJob jb = jobs[lo];
+    const int lt = blockIdx.x - jb.tile0;
+    // tile geometry (conv jobs) and the bulk loads of a full tile: issued before anything else so that the clip
+    // coefficient below (double-precision pow / sqrt on one thread) is computed while they fly
+    int a0 = 0, b0 = 0, na = 0, nb = 0;
+    long long row0 = 0, rstride = 0;
+    bool fast = false;
+    if (jb.d1 != 0) {
+        a0 = (lt / jb.tiles_b) * AD_TA; b0 = (lt % jb.tiles_b) * AD_TB;
+        na = jb.d0 - a0 < AD_TA ? jb.d0 - a0 : AD_TA; nb = jb.d1 - b0 < AD_TB ? jb.d1 - b0 : AD_TB;
+        row0 = jb.off + ((long long)a0 * jb.d1 + b0) * jb.kk;       // first element of tile row a = 0 (torch layout)
+        rstride = (long long)jb.d1 * jb.kk;                         // distance between tile rows
+        fast = bulk_ok && sizeof(TD) == 2 && na == AD_TA && nb == AD_TB && (jb.kk == 9 || jb.kk == 16) && ((jb.d0 | jb.d1) & 7) == 0 &&
+               (jb.off & 3) == 0 && (((uintptr_t)jb.p01 | (uintptr_t)jb.p10) & 15) == 0;          // CTA-uniform
+    }
+    const int runf = AD_TB * jb.kk;                                 // floats per row of a full tile
+    float* dm = tile + pad_floats;
+    float* dv = dm + AD_TA * runf;
+    float* dp = dv + AD_TA * runf;
+    if (fast && threadIdx.x < 32) {
+        if (threadIdx.x == 0) mbar_expect_tx(bar, 3u * AD_TA * runf * 4u);
+        __syncwarp();
+        if (threadIdx.x < AD_TA) {
+            const long long r = row0 + (long long)threadIdx.x * rstride;
+            bulk_ld_1d(smem_u32(dm + threadIdx.x * runf), m + r, runf * 4u, bar);
+            bulk_ld_1d(smem_u32(dv + threadIdx.x * runf), v + r, runf * 4u, bar);
+            bulk_ld_1d(smem_u32(dp + threadIdx.x * runf), p + r, runf * 4u, bar);
+        }
+    }
+    if (threadIdx.x == 32) {
         float coef = grad_scale;
         if (sumsq) {
             float total = (float)sqrt(*sumsq) * grad_scale;
@@ -117,14 +298,12 @@ __global__ void __launch_bounds__(256, 4) adam_multi_kernel(const AdamJob* __res
         s_bc2_sqrt = (float)sqrt(bc2);
     }
     __syncthreads();
-    int lo = 0, hi = njobs - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_tile0[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    const AdamJob jb = jobs[lo];
-    const int lt = blockIdx.x - jb.tile0;
     const float coef = s_coef, step_size = s_step_size, bc2s = s_bc2_sqrt;
+    if (fast) {
+        if (jb.kk == 9) adam_tile_bulk<9>(jb, a0, b0, tile, dm, dv, dp, bar, p, g, m, v, row0, rstride, coef, step_size, bc2s, b1, b2, eps);
+        else adam_tile_bulk<16>(jb, a0, b0, tile, dm, dv, dp, bar, p, g, m, v, row0, rstride, coef, step_size, bc2s, b1, b2, eps);
+        return;
+    }
     auto adam = [&](long long i, float gi) -> float {
         gi *= coef;
         const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -141,9 +320,7 @@ __global__ void __launch_bounds__(256, 4) adam_multi_kernel(const AdamJob* __res
         for (long long i = i0 + threadIdx.x; i < i1; i += 256) adam(i, g[i]);
         return;
     }
-    const int a0 = (lt / jb.tiles_b) * AD_TA, b0 = (lt % jb.tiles_b) * AD_TB;
     const int kk = jb.kk, d0 = jb.d0, d1 = jb.d1;
-    const int na = d0 - a0 < AD_TA ? d0 - a0 : AD_TA, nb = d1 - b0 < AD_TB ? d1 - b0 : AD_TB;
     const int ROW = AD_TB * (kk + 1) + 1;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const float* gj = g + jb.off;
@@ -156,8 +333,6 @@ __global__ void __launch_bounds__(256, 4) adam_multi_kernel(const AdamJob* __res
     }
     const int run = nb * kk;
     const int E = na * run;
-    const long long row0 = jb.off + ((long long)a0 * d1 + b0) * kk;     // first element of tile row a = 0 (torch layout)
-    const long long rstride = (long long)d1 * kk;                        // distance between tile rows
     // torch layout: row a of the tile is a contiguous run of nb*kk floats.  When the runs are 16-byte aligned (every conv
     // layer of the models: kk = 9 | 16 with d1 % 4 == 0) p / g / m / v move as float4 - this phase is 28 of the kernel's 32
     // bytes per parameter - two independent vectors per thread and trip (8 x 16-byte loads in flight).
@@ -325,24 +500,33 @@ extern "C" int svrs_step_increment(int64_t* step_ptr, void* stream) {
 }
 
 extern "C" int svrs_adam_job_bytes(void) { return (int)sizeof(svrs::AdamJob); }
+extern "C" int svrs_adam_tile_rows(void) { return svrs::AD_TA; }
+extern "C" int svrs_adam_tile_cols(void) { return svrs::AD_TB; }
 
 extern "C" int svrs_adam_multi(const void* jobs, int njobs, int total_tiles, int max_kk, float* p, const float* g, float* m, float* v,
                                int pack_dtype, const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
                                float beta2, float eps, const int64_t* step_ptr, void* stream) {
     SVRS_CHECK_ARG(jobs && njobs > 0 && njobs <= svrs::AD_MAX_JOBS && total_tiles > 0 && max_kk > 0 && max_kk <= 16 && p && g && m && v && step_ptr,
                    "adam_multi: bad args (at most %d jobs)", svrs::AD_MAX_JOBS);
-    size_t smem = (size_t)svrs::AD_TA * (svrs::AD_TB * (max_kk + 1) + 1) * sizeof(float);
+    // padded transpose tile + dense m / v / p rows of the bulk path (66.7 KB at kk = 16: three CTAs per SM)
+    const int pad_floats = svrs::ad_pad_floats(max_kk);
+    size_t smem = ((size_t)pad_floats + 3u * svrs::AD_TA * svrs::AD_TB * max_kk) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    // bulk copies need 16-byte aligned rows: the flat buffers' bases (a job's offset and row pitch are checked per tile)
+    static const bool no_bulk = getenv("SVRS_ADAM_BULK") && atoi(getenv("SVRS_ADAM_BULK")) == 0;
+    const int bulk_ok = !no_bulk && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
     static bool attr_set = false;
-    if (!attr_set) {          // 4-6 CTAs of ~35 KB per SM: ask for the large shared-memory carve-out (the default gave 3)
+    if (!attr_set) {
+        cudaFuncSetAttribute(adam_multi_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(adam_multi_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(adam_multi_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(adam_multi_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     if (pack_dtype == SVRS_F32)
-        SVRS_LAUNCH((adam_multi_kernel<float>), total_tiles, 256, smem, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr);
+        SVRS_LAUNCH((adam_multi_kernel<float>), total_tiles, 256, smem, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr, pad_floats, bulk_ok);
     else if (pack_dtype == SVRS_BF16)
-        SVRS_LAUNCH((adam_multi_kernel<__nv_bfloat16>), total_tiles, 256, smem, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr);
+        SVRS_LAUNCH((adam_multi_kernel<__nv_bfloat16>), total_tiles, 256, smem, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr, pad_floats, bulk_ok);
     else { set_error("adam_multi: bad pack dtype"); return SVRS_E_ARG; }
     return check_launch("adam_multi");
 }

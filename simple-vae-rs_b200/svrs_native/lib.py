@@ -94,7 +94,7 @@ class _Lib:
         if full not in self.protos:
             raise AttributeError(name)
         fn = getattr(self.load(), full)
-        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run", "svrs_pack_job_bytes", "svrs_launch_count", "svrs_adam_job_bytes",
+        if self.protos[full][0] != "int" or full in ("svrs_abi_version", "svrs_device_cc", "svrs_debug_tap_geometry", "svrs_tc_would_run", "svrs_pack_job_bytes", "svrs_launch_count", "svrs_adam_job_bytes", "svrs_adam_tile_rows", "svrs_adam_tile_cols",
                                                   "svrs_conv2d_wgrad_layout", "svrs_convT2d_wgrad_layout", "svrs_sample_tail_splits"):
             setattr(self, name, fn)
             return fn

@@ -213,6 +213,67 @@ def test_fused_tail_equals_separate_kernels(golden_dir):
     assert float(d.max()) <= 2 * 1e-4 * 1.01 and frac < 2e-3
 
 
+def _adam_ref(p, g, m, v, t, coef, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
+    """torch.optim.Adam's single-tensor update (models/base.py:106-107 of the reference: clip_grad_norm_ then Adam.step),
+    float64 on the CPU."""
+    g = g.double() * coef
+    m = b1 * m.double() + (1 - b1) * g
+    v = b2 * v.double() + (1 - b2) * g * g
+    bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+    return p.double() - (lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps), m, v
+
+
+@pytest.mark.parametrize("grad_layout", [0, 1])
+def test_adam_multi_direct(grad_layout):
+    """svrs_adam_multi through the C ABI on a hand-built job table: full tiles of 3x3 / 4x4 layers (the bulk-copy
+    path), ragged d0 / d1 (the generic path), a 1x1-like kk, plain ranges between them; gradients in torch layout or in
+    the tcgen05 weight-gradient kernels' packed [kk][d1][d0] layout.  p / m / v against float64 Adam; both bf16 packs must
+    be EXACTLY the bf16 rounding of the updated fp32 master weight, permuted."""
+    gen = torch.Generator().manual_seed(77 + grad_layout)
+    shapes = [(64, 32, 9), (96, 48, 16), (40, 20, 9), (32, 16, 16), (4, 16, 9), (128, 64, 9), (16, 4, 16), (64, 16, 1)]
+    rec = np.dtype([("off", "<i8"), ("p01", "<u8"), ("p10", "<u8"), ("d0", "<i4"), ("d1", "<i4"), ("kk", "<i4"),
+                    ("layout", "<i4"), ("tile0", "<i4"), ("tiles_b", "<i4")])
+    assert rec.itemsize == lib.adam_job_bytes()
+    rows, off, tile0, keep = [], 0, 0, []
+    tr, tc = lib.adam_tile_rows(), lib.adam_tile_cols()
+    for i, (d0, d1, kk) in enumerate(shapes):
+        gap = 24 + 4 * i                                   # a plain range (bias-like) before every weight; keeps off % 4 == 0
+        rows.append((off, 0, 0, gap, 0, 1, 0, tile0, 0)); tile0 += (gap + 2047) // 2048; off += gap
+        p01 = torch.zeros(kk * d0 * d1, dtype=torch.bfloat16, device=DEV)
+        p10 = torch.zeros(kk * d0 * d1, dtype=torch.bfloat16, device=DEV)
+        tiles_b = (d1 + tc - 1) // tc
+        rows.append((off, p01.data_ptr(), p10.data_ptr(), d0, d1, kk, grad_layout, tile0, tiles_b))
+        keep.append((off, d0, d1, kk, p01, p10))
+        tile0 += ((d0 + tr - 1) // tr) * tiles_b; off += d0 * d1 * kk
+    rows.append((off, 0, 0, 3000, 0, 1, 0, tile0, 0)); tile0 += 2; off += 3000      # a plain range spanning two tiles
+    n = off
+    p0, m0 = torch.randn(n, generator=gen), 0.1 * torch.randn(n, generator=gen)
+    v0, g_t = 0.01 * torch.rand(n, generator=gen), torch.randn(n, generator=gen)
+    g_buf = g_t.clone()
+    if grad_layout == 1:                                   # the weights' gradients sit packed [kk][d1][d0] at the same offset
+        for o, d0, d1, kk, _, _ in keep:
+            g_buf[o:o + d0 * d1 * kk] = g_t[o:o + d0 * d1 * kk].view(d0, d1, kk).permute(2, 1, 0).reshape(-1)
+    t_step, max_norm = 3, 1.0
+    coef = min(1.0, max_norm / (float(g_t.double().pow(2).sum().sqrt()) + 1e-6))
+    pr, mr, vr = _adam_ref(p0, g_t, m0, v0, t_step, coef)
+    pd, md, vd, gd = p0.to(DEV), m0.to(DEV), v0.to(DEV), g_buf.to(DEV)
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    lib.sumsq(gd.data_ptr(), n, acc.data_ptr(), st())
+    step = torch.tensor([t_step], dtype=torch.int64, device=DEV)
+    jobs = torch.from_numpy(np.array(rows, dtype=rec).view(np.uint8).copy()).to(DEV)
+    lib.adam_multi(jobs.data_ptr(), len(rows), tile0, 16, pd.data_ptr(), gd.data_ptr(), md.data_ptr(), vd.data_ptr(), BF16,
+                   acc.data_ptr(), max_norm, 1.0, 1e-4, 0.9, 0.999, 1e-8, step.data_ptr(), st())
+    torch.cuda.synchronize()
+    assert torch.equal(gd.cpu(), g_buf), "gradient buffer must not be modified"
+    report(f"adam_multi[layout {grad_layout}] p", pd, pr, 1e-6)
+    report(f"adam_multi[layout {grad_layout}] m", md, mr, 1e-6)
+    report(f"adam_multi[layout {grad_layout}] v", vd, vr, 1e-6)
+    for o, d0, d1, kk, p01, p10 in keep:
+        w = pd[o:o + d0 * d1 * kk].view(d0, d1, kk)
+        assert torch.equal(p01.view(kk, d0, d1), w.permute(2, 0, 1).to(torch.bfloat16)), (d0, d1, kk, "p01")
+        assert torch.equal(p10.view(kk, d1, d0), w.permute(2, 1, 0).to(torch.bfloat16)), (d0, d1, kk, "p10")
+
+
 # ------------------------------------------------------------------------------------------------ f4: fused uncertainty maps
 def _task_stats(draws, target):
     """models/base.py:305-313, 341 of the reference, verbatim arithmetic on a [S,4,P,P] sample stack."""
