@@ -251,15 +251,16 @@ int svrs_step_increment(int64_t* step_ptr, void* stream);
  * ([kk][d0][d1] and [kk][d1][d0], see svrs_pack_weights) - replacing svrs_unpack_grads_multi + svrs_clip_adam +
  * svrs_pack_weights_multi.  `jobs`: DEVICE array of njobs records (svrs_adam_job_bytes() each)
  *   { int64 off; void* p01; void* p10; int d0, d1, kk; int layout; int tile0; int tiles_b; }
- * off = element offset of the parameter in the flat buffers p / g / m / v.  Conv jobs (d1 > 0) are cut into
- * svrs_adam_tile_rows() x svrs_adam_tile_cols() (16 x 16) tiles of the (d0, d1) plane (tiles_b = ceil(d1 / cols), a job has
- * ceil(d0 / rows) * tiles_b tiles); plain jobs (d1 == 0: biases, BatchNorm affine) into runs of 2048 of their d0 elements.
- * tile0 = running sum of tile counts, total_tiles their total, max_kk <= 16, njobs <= 512.
- * sumsq / max_norm / grad_scale / step_ptr as in svrs_clip_adam.  Full tiles of kk = 9 / 16 layers with d0, d1 % 8 == 0 and
- * 16-byte aligned buffers take the bulk-copy path (cp.async.bulk rows through shared memory); everything else a generic one. */
+ * off = element offset of the parameter in the flat buffers p / g / m / v.  Conv jobs (d1 > 0) are cut into tiles of
+ * svrs_adam_tile_rows() x svrs_adam_tile_cols(kk) (16 x 16; 16 x 8 for kk > 9) of the (d0, d1) plane: tiles_b =
+ * ceil(d1 / cols), a job has ceil(d0 / rows) * tiles_b tiles; plain jobs (d1 == 0: biases, BatchNorm affine) are cut into
+ * runs of 2048 of their d0 elements.  tile0 = running sum of tile counts, total_tiles their total, max_kk <= 16, njobs <= 512.
+ * sumsq / max_norm / grad_scale / step_ptr as in svrs_clip_adam.  Persistent CTAs walk the tile list; full tiles of kk = 9 / 16
+ * layers with d0, d1 % 8 == 0 and 16-byte aligned buffers run through a bulk-copy pipeline (cp.async.bulk rows through shared
+ * memory, SVRS_ADAM_BULK=0 disables it), everything else through a register-file path. */
 int svrs_adam_job_bytes(void);
 int svrs_adam_tile_rows(void);
-int svrs_adam_tile_cols(void);
+int svrs_adam_tile_cols(int kk);
 int svrs_adam_multi(const void* jobs, int njobs, int total_tiles, int max_kk, float* p, const float* g, float* m, float* v,
                     int pack_dtype, const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
                     float beta2, float eps, const int64_t* step_ptr, void* stream);

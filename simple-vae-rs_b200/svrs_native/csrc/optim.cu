@@ -90,10 +90,14 @@ struct AdamJob {
     int tile0;          // first global tile of this job
     int tiles_b;        // tiles along d1 (conv jobs)
 };
-constexpr int AD_TA = 16, AD_TB = 16, AD_PLAIN = 2048, AD_MAX_JOBS = 512;
-// shared memory of a CTA: the padded transpose tile [AD_TA][AD_TB * (kk + 1) + 1] (rounded up to 128 bytes), then the dense
-// m / v / p rows of the bulk path
-__host__ __device__ constexpr int ad_pad_floats(int kk) { return (AD_TA * (AD_TB * (kk + 1) + 1) + 31) / 32 * 32; }
+constexpr int AD_TA = 16, AD_PLAIN = 2048, AD_MAX_JOBS = 512;
+// tile width along d1: 16 columns, 8 for the 4x4 kernels (kk > 9) - a tile row (cols * kk floats, contiguous in the torch
+// layout) is 576 / 512 bytes and a tile's dense m / v / p rows take 27 KB of shared memory either way
+__host__ __device__ constexpr int ad_cols(int kk) { return kk > 9 ? 8 : 16; }
+constexpr int AD_PAD_FLOATS = (AD_TA * (16 * 10 + 1) + 31) / 32 * 32;       // transpose tile [16][cols * (kk + 1) + 1], largest form
+constexpr int AD_STAGE_FLOATS = 3 * AD_TA * 16 * 9;                          // dense m | v | p rows of one tile, largest form
+static_assert(AD_TA * (8 * 17 + 1) <= AD_PAD_FLOATS && 3 * AD_TA * 8 * 16 <= AD_STAGE_FLOATS, "kk = 16 tiles must fit");
+constexpr size_t AD_SMEM_BYTES = (size_t)(AD_PAD_FLOATS + AD_STAGE_FLOATS) * sizeof(float);      // 38 KB: five CTAs per SM fit
 
 __device__ __forceinline__ void bulk_ld_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -114,44 +118,112 @@ __device__ __forceinline__ void split_kk_(int i, int kk, int& b, int& t) {
     else { b = i / kk; t = i - kk * b; }
 }
 
-// Full 16 x 16 x KK tile, bf16 packs.  On entry the bulk loads of the tile's m / v / p rows (dense: row a at a * 16 * KK
-// floats) are in flight on `bar`.
-template <int KK>
-__device__ __forceinline__ void adam_tile_bulk(const AdamJob& jb, const int a0, const int b0, float* __restrict__ tile,
-                                               float* __restrict__ dm, float* __restrict__ dv, float* __restrict__ dp,
-                                               const uint32_t bar, float* __restrict__ p, const float* __restrict__ g,
-                                               float* __restrict__ m, float* __restrict__ v, const long long row0,
-                                               const long long rstride, const float coef, const float step_size,
-                                               const float bc2s, const float b1, const float b2, const float eps) {
-    constexpr int ROW = AD_TB * (KK + 1) + 1;
-    constexpr int RUN = AD_TB * KK, RUN4 = RUN / 4;      // floats / float4 per tile row (torch layout): 144 | 256, 36 | 64
-    constexpr int Q = AD_TA * RUN4;                      // float4 per array and tile: 576 | 1024
-    constexpr int TRIPS = (Q + 255) / 256;               // 3 | 4
-    const int d0 = jb.d0, d1 = jb.d1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool packed = jb.layout == 1;
-    if (packed) {        // [kk][d1][d0] -> tile[a][b][t]: a half-warp reads the 16 consecutive d0 of one (t, b)
-        const int a = lane & 15, b = 2 * warp + (lane >> 4);
-        const float* gj = g + jb.off + (long long)(b0 + b) * d0 + a0 + a;
-        float r[KK];
-#pragma unroll
-        for (int t = 0; t < KK; ++t) r[t] = __ldcs(gj + (long long)t * d1 * d0);
-#pragma unroll
-        for (int t = 0; t < KK; ++t) tile[a * ROW + b * (KK + 1) + t] = r[t];
+struct AdamConsts { float coef, step_size, bc2s, b1, b2, eps; };
+
+// geometry of one tile of the global tile list (CTA-uniform)
+struct AdamTile {
+    AdamJob jb;
+    int a0, b0, na, nb, lt;
+    long long row0, rstride;     // first element of tile row a = 0 in the flat buffers (torch layout), distance between tile rows
+    bool fast;                   // full tile of a kk = 9 | 16 layer, 16-byte aligned rows, bf16 packs: bulk-copy pipeline
+};
+
+template <typename TD>
+__device__ __forceinline__ AdamTile adam_tile_of(const AdamJob* __restrict__ jobs, const int* s_tile0, int njobs, int tile, int bulk_ok) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_tile0[mid] <= tile) lo = mid; else hi = mid - 1;
     }
+    AdamTile T;
+    T.jb = jobs[lo];
+    T.lt = tile - T.jb.tile0;
+    T.a0 = T.b0 = T.na = T.nb = 0; T.row0 = T.rstride = 0; T.fast = false;
+    if (T.jb.d1 != 0) {
+        const int cols = ad_cols(T.jb.kk);
+        T.a0 = (T.lt / T.jb.tiles_b) * AD_TA; T.b0 = (T.lt % T.jb.tiles_b) * cols;
+        T.na = T.jb.d0 - T.a0 < AD_TA ? T.jb.d0 - T.a0 : AD_TA; T.nb = T.jb.d1 - T.b0 < cols ? T.jb.d1 - T.b0 : cols;
+        T.row0 = T.jb.off + ((long long)T.a0 * T.jb.d1 + T.b0) * T.jb.kk;
+        T.rstride = (long long)T.jb.d1 * T.jb.kk;
+        T.fast = bulk_ok && sizeof(TD) == 2 && T.na == AD_TA && T.nb == cols && (T.jb.kk == 9 || T.jb.kk == 16) &&
+                 ((T.jb.d0 | T.jb.d1) & 7) == 0 && (T.jb.off & 3) == 0 && (((uintptr_t)T.jb.p01 | (uintptr_t)T.jb.p10) & 15) == 0;
+    }
+    return T;
+}
+
+// warp 0: bulk loads of a fast tile's m / v / p rows into a pipeline stage
+__device__ __forceinline__ void adam_issue_loads(const AdamTile& T, float* stage, uint32_t bar, const float* __restrict__ p,
+                                                 const float* __restrict__ m, const float* __restrict__ v) {
+    const int lane = threadIdx.x & 31;
+    const int runf = ad_cols(T.jb.kk) * T.jb.kk;                      // floats per tile row: 144 | 128
+    if (lane == 0) mbar_expect_tx(bar, 3u * AD_TA * runf * 4u);
+    __syncwarp();
+    if (lane < AD_TA) {
+        const long long r = T.row0 + (long long)lane * T.rstride;
+        bulk_ld_1d(smem_u32(stage + lane * runf), m + r, runf * 4u, bar);
+        bulk_ld_1d(smem_u32(stage + (AD_TA + lane) * runf), v + r, runf * 4u, bar);
+        bulk_ld_1d(smem_u32(stage + (2 * AD_TA + lane) * runf), p + r, runf * 4u, bar);
+    }
+}
+
+// Packed-layout gradient [kk][d1][d0] of a fast tile into registers (issued before the clip coefficient is computed, used
+// after it): a half-warp reads the 16
+// consecutive d0 of one (t, b) row, 16 rows per pass of the CTA.  (Torch-layout gradients - the few narrow layers whose
+// weight gradients come from the mma.sync / CUDA-core kernels - are read inside the tile's own iteration.)
+constexpr int AD_GREGS = 9;
+template <int KK>
+__device__ __forceinline__ void adam_prefetch_g(const AdamTile& T, const float* __restrict__ g, float (&gr)[AD_GREGS]) {
+    constexpr int COLS = ad_cols(KK);
+    constexpr int PASSES = KK * COLS / 16;                              // 9 | 8
+    static_assert(PASSES <= AD_GREGS, "gradient prefetch registers");
+    const int a = threadIdx.x & 15, slot = threadIdx.x >> 4;
+    const float* gj = g + T.jb.off + (long long)T.b0 * T.jb.d0 + T.a0 + a;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+        const int rr = ps * 16 + slot, t = rr / COLS, b = rr % COLS;
+        gr[ps] = __ldcs(gj + ((long long)t * T.jb.d1 + b) * T.jb.d0);
+    }
+}
+// One fast tile: `stage` holds (or is receiving, tracked by `bar` / `parity`) the tile's dense m | v | p rows, `gr` its gradient
+// when that is packed.  Adam runs in place in shared memory, the rows leave as bulk stores, the packs are written from the
+// transpose tile.
+template <int KK>
+__device__ __forceinline__ void adam_tile_fast(const AdamTile& T, float* __restrict__ tile, float* __restrict__ stage,
+                                               const uint32_t bar, const uint32_t parity, float (&gr)[AD_GREGS],
+                                               float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                               float* __restrict__ v, const AdamConsts& c) {
+    constexpr int COLS = ad_cols(KK);
+    constexpr int ROW = COLS * (KK + 1) + 1;
+    constexpr int RUN = COLS * KK, RUN4 = RUN / 4;       // floats / float4 per tile row: 144 | 128, 36 | 32
+    constexpr int Q = AD_TA * RUN4;                      // float4 per array and tile: 576 | 512
+    constexpr int TRIPS = (Q + 255) / 256;               // 3 | 2
+    constexpr int PASSES = KK * COLS / 16;
+    const int d0 = T.jb.d0, d1 = T.jb.d1, a0 = T.a0, b0 = T.b0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool packed = T.jb.layout == 1;
+    float* dm = stage;
+    float* dv = stage + AD_TA * RUN;
+    float* dp = stage + 2 * AD_TA * RUN;
     float4 gi[TRIPS];
-    if (!packed) {
+    if (packed) {        // [kk][d1][d0] -> tile[a][b][t]
+        const int a = threadIdx.x & 15, slot = threadIdx.x >> 4;
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) {
+            const int rr = ps * 16 + slot, t = rr / COLS, b = rr % COLS;
+            tile[a * ROW + b * (KK + 1) + t] = gr[ps];
+        }
+        __syncthreads();                                 // transposed gradient tile complete
+    } else {
 #pragma unroll
         for (int j = 0; j < TRIPS; ++j) {
             const int q = threadIdx.x + 256 * j;
             if (q < Q) {
                 const int a = q / RUN4, i4 = q - a * RUN4;
-                gi[j] = __ldcs(reinterpret_cast<const float4*>(g + row0 + (long long)a * rstride + 4 * i4));
+                gi[j] = __ldcs(reinterpret_cast<const float4*>(g + T.row0 + (long long)a * T.rstride + 4 * i4));
             }
         }
     }
-    __syncthreads();                                     // transposed gradient tile complete
-    mbar_wait(bar, 0);                                   // m / v / p rows have landed
+    mbar_wait(bar, parity);                              // m / v / p rows have landed
 #pragma unroll
     for (int j = 0; j < TRIPS; ++j) {
         const int q = threadIdx.x + 256 * j;
@@ -174,10 +246,10 @@ __device__ __forceinline__ void adam_tile_bulk(const AdamJob& jb, const int a0, 
             float ma[4] = {m4.x, m4.y, m4.z, m4.w}, va[4] = {v4.x, v4.y, v4.z, v4.w}, pa[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float gg = ga[e] * coef;
-                ma[e] = b1 * ma[e] + (1.f - b1) * gg;
-                va[e] = b2 * va[e] + (1.f - b2) * gg * gg;
-                pa[e] = pa[e] - step_size * (ma[e] / (sqrtf(va[e]) / bc2s + eps));
+                const float gg = ga[e] * c.coef;
+                ma[e] = c.b1 * ma[e] + (1.f - c.b1) * gg;
+                va[e] = c.b2 * va[e] + (1.f - c.b2) * gg * gg;
+                pa[e] = pa[e] - c.step_size * (ma[e] / (sqrtf(va[e]) / c.bc2s + c.eps));
                 tile[sl[e]] = pa[e];
             }
             reinterpret_cast<float4*>(dm)[q] = make_float4(ma[0], ma[1], ma[2], ma[3]);
@@ -189,7 +261,7 @@ __device__ __forceinline__ void adam_tile_bulk(const AdamJob& jb, const int a0, 
     __syncthreads();
     if (warp == 0) {
         if (lane < AD_TA) {
-            const long long r = row0 + (long long)lane * rstride;
+            const long long r = T.row0 + (long long)lane * T.rstride;
             bulk_st_1d(m + r, smem_u32(dm + lane * RUN), RUN * 4);
             bulk_st_1d(v + r, smem_u32(dv + lane * RUN), RUN * 4);
             bulk_st_1d(p + r, smem_u32(dp + lane * RUN), RUN * 4);
@@ -197,11 +269,12 @@ __device__ __forceinline__ void adam_tile_bulk(const AdamJob& jb, const int a0, 
         bulk_commit();
     }
     // bf16 packs from the transpose tile, 8 elements (16 bytes) per store
-    const int h = threadIdx.x & 1;
-    if (jb.p01) {                                        // [t][a][b]: a (t, a) row is 16 b = two 16-byte halves
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(jb.p01);
+    if (T.jb.p01) {                                      // [t][a][b]: a (t, a) row is COLS b = COLS / 8 16-byte pieces
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(T.jb.p01);
+        constexpr int PC = COLS / 8;
+        const int h = threadIdx.x % PC;
 #pragma unroll
-        for (int r = threadIdx.x >> 1; r < KK * AD_TA; r += 128) {
+        for (int r = threadIdx.x / PC; r < KK * AD_TA; r += 256 / PC) {
             const int t = r >> 4, a = r & 15;
             const float* src = tile + a * ROW + 8 * h * (KK + 1) + t;
             uint4 o;
@@ -212,11 +285,12 @@ __device__ __forceinline__ void adam_tile_bulk(const AdamJob& jb, const int a0, 
             *reinterpret_cast<uint4*>(dst + ((long long)t * d0 + a0 + a) * d1 + b0 + 8 * h) = o;
         }
     }
-    if (jb.p10) {                                        // [t][b][a]: a (t, b) row is 16 a = two 16-byte halves
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(jb.p10);
+    if (T.jb.p10) {                                      // [t][b][a]: a (t, b) row is 16 a = two 16-byte halves
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(T.jb.p10);
+        const int h = threadIdx.x & 1;
 #pragma unroll
-        for (int r = threadIdx.x >> 1; r < KK * AD_TB; r += 128) {
-            const int t = r >> 4, b = r & 15;
+        for (int r = threadIdx.x >> 1; r < KK * COLS; r += 128) {
+            const int t = r / COLS, b = r % COLS;
             const float* src = tile + 8 * h * ROW + b * (KK + 1) + t;
             uint4 o;
             o.x = pack_bf16x2_(src[0], src[ROW]);
@@ -229,102 +303,33 @@ __device__ __forceinline__ void adam_tile_bulk(const AdamJob& jb, const int a0, 
     if (warp == 0) bulk_wait_read_0();                   // shared memory must outlive the bulk stores' reads
 }
 
+// Every other tile (ragged edges, the 4-channel layers, kk other than 9 / 16, fp32 packs, plain ranges): register-file path.
 template <typename TD>
-__global__ void __launch_bounds__(256, 3) adam_multi_kernel(const AdamJob* __restrict__ jobs, int njobs,
-                                                          float* __restrict__ p, const float* __restrict__ g,
-                                                          float* __restrict__ m, float* __restrict__ v,
-                                                          const double* __restrict__ sumsq, float max_norm, float grad_scale,
-                                                          float lr, float b1, float b2, float eps,
-                                                          const long long* __restrict__ step_ptr, const int pad_floats,
-                                                          const int bulk_ok) {
-    pdl_entry();
-    extern __shared__ __align__(128) float tile[];
-    __shared__ int s_tile0[AD_MAX_JOBS];
-    __shared__ float s_coef, s_step_size, s_bc2_sqrt;
-    __shared__ __align__(8) unsigned long long s_bar;
-    const uint32_t bar = smem_u32(&s_bar);
-    for (int i = threadIdx.x; i < njobs; i += blockDim.x) s_tile0[i] = jobs[i].tile0;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    int lo = 0, hi = njobs - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_tile0[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    const AdamJob jb = jobs[lo];
-    const int lt = blockIdx.x - jb.tile0;
-    // tile geometry (conv jobs) and the bulk loads of a full tile: issued before anything else so that the clip
-    // coefficient below (double-precision pow / sqrt on one thread) is computed while they fly
-    int a0 = 0, b0 = 0, na = 0, nb = 0;
-    long long row0 = 0, rstride = 0;
-    bool fast = false;
-    if (jb.d1 != 0) {
-        a0 = (lt / jb.tiles_b) * AD_TA; b0 = (lt % jb.tiles_b) * AD_TB;
-        na = jb.d0 - a0 < AD_TA ? jb.d0 - a0 : AD_TA; nb = jb.d1 - b0 < AD_TB ? jb.d1 - b0 : AD_TB;
-        row0 = jb.off + ((long long)a0 * jb.d1 + b0) * jb.kk;       // first element of tile row a = 0 (torch layout)
-        rstride = (long long)jb.d1 * jb.kk;                         // distance between tile rows
-        fast = bulk_ok && sizeof(TD) == 2 && na == AD_TA && nb == AD_TB && (jb.kk == 9 || jb.kk == 16) && ((jb.d0 | jb.d1) & 7) == 0 &&
-               (jb.off & 3) == 0 && (((uintptr_t)jb.p01 | (uintptr_t)jb.p10) & 15) == 0;          // CTA-uniform
-    }
-    const int runf = AD_TB * jb.kk;                                 // floats per row of a full tile
-    float* dm = tile + pad_floats;
-    float* dv = dm + AD_TA * runf;
-    float* dp = dv + AD_TA * runf;
-    if (fast && threadIdx.x < 32) {
-        if (threadIdx.x == 0) mbar_expect_tx(bar, 3u * AD_TA * runf * 4u);
-        __syncwarp();
-        if (threadIdx.x < AD_TA) {
-            const long long r = row0 + (long long)threadIdx.x * rstride;
-            bulk_ld_1d(smem_u32(dm + threadIdx.x * runf), m + r, runf * 4u, bar);
-            bulk_ld_1d(smem_u32(dv + threadIdx.x * runf), v + r, runf * 4u, bar);
-            bulk_ld_1d(smem_u32(dp + threadIdx.x * runf), p + r, runf * 4u, bar);
-        }
-    }
-    if (threadIdx.x == 32) {
-        float coef = grad_scale;
-        if (sumsq) {
-            float total = (float)sqrt(*sumsq) * grad_scale;
-            float c = max_norm / (total + 1e-6f);
-            coef = grad_scale * fminf(c, 1.0f);
-        }
-        double t = (double)(*step_ptr);
-        double bc1 = 1.0 - pow((double)b1, t);
-        double bc2 = 1.0 - pow((double)b2, t);
-        s_coef = coef;
-        s_step_size = (float)((double)lr / bc1);
-        s_bc2_sqrt = (float)sqrt(bc2);
-    }
-    __syncthreads();
-    const float coef = s_coef, step_size = s_step_size, bc2s = s_bc2_sqrt;
-    if (fast) {
-        if (jb.kk == 9) adam_tile_bulk<9>(jb, a0, b0, tile, dm, dv, dp, bar, p, g, m, v, row0, rstride, coef, step_size, bc2s, b1, b2, eps);
-        else adam_tile_bulk<16>(jb, a0, b0, tile, dm, dv, dp, bar, p, g, m, v, row0, rstride, coef, step_size, bc2s, b1, b2, eps);
-        return;
-    }
-    auto adam = [&](long long i, float gi) -> float {
-        gi *= coef;
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        const float pn = p[i] - step_size * (mi / (sqrtf(vi) / bc2s + eps));
-        p[i] = pn;
-        return pn;
-    };
+__device__ __noinline__ void adam_tile_generic(const AdamTile T, float* __restrict__ tile, float* __restrict__ p,
+                                                  const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                  const AdamConsts c) {
+    const AdamJob& jb = T.jb;
+    const float coef = c.coef, step_size = c.step_size, bc2s = c.bc2s, b1 = c.b1, b2 = c.b2, eps = c.eps;
     if (jb.d1 == 0) {                                   // plain range
-        const long long i0 = jb.off + (long long)lt * AD_PLAIN;
+        const long long i0 = jb.off + (long long)T.lt * AD_PLAIN;
         const long long i1 = jb.off + jb.d0 < i0 + AD_PLAIN ? jb.off + jb.d0 : i0 + AD_PLAIN;
-        for (long long i = i0 + threadIdx.x; i < i1; i += 256) adam(i, g[i]);
+        for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+            const float gi = g[i] * coef;
+            const float mi = b1 * m[i] + (1.f - b1) * gi;
+            const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+            m[i] = mi;
+            v[i] = vi;
+            p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2s + eps));
+        }
         return;
     }
-    const int kk = jb.kk, d0 = jb.d0, d1 = jb.d1;
-    const int ROW = AD_TB * (kk + 1) + 1;
+    const int kk = jb.kk, d0 = jb.d0, d1 = jb.d1, a0 = T.a0, b0 = T.b0, na = T.na, nb = T.nb;
+    const int TB = ad_cols(kk);
+    const int ROW = TB * (kk + 1) + 1;
+    const long long row0 = T.row0, rstride = T.rstride;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const float* gj = g + jb.off;
-    if (jb.layout == 1) {                               // packed [kk][d1][d0]: warps read 32 consecutive d0
+    if (jb.layout == 1) {                               // packed [kk][d1][d0]: lanes read consecutive d0
         if (lane < na)
             for (int t = 0; t < kk; ++t)
                 for (int b = warp; b < nb; b += 8)
@@ -333,9 +338,7 @@ __global__ void __launch_bounds__(256, 3) adam_multi_kernel(const AdamJob* __res
     }
     const int run = nb * kk;
     const int E = na * run;
-    // torch layout: row a of the tile is a contiguous run of nb*kk floats.  When the runs are 16-byte aligned (every conv
-    // layer of the models: kk = 9 | 16 with d1 % 4 == 0) p / g / m / v move as float4 - this phase is 28 of the kernel's 32
-    // bytes per parameter - two independent vectors per thread and trip (8 x 16-byte loads in flight).
+    // torch layout: row a of the tile is a contiguous run of nb*kk floats; float4 when the runs are 16-byte aligned
     if ((run & 3) == 0 && (rstride & 3) == 0 && (row0 & 3) == 0) {
         const int run4 = run >> 2;
         const int Q = na * run4;
@@ -365,7 +368,6 @@ __global__ void __launch_bounds__(256, 3) adam_multi_kernel(const AdamJob* __res
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 if (!on[u]) continue;
-                // shared-memory slots of the four consecutive (b, t) elements of this vector
                 int sl[4];
                 int sb = slot[u], st_ = tt[u];
 #pragma unroll
@@ -392,35 +394,18 @@ __global__ void __launch_bounds__(256, 3) adam_multi_kernel(const AdamJob* __res
             }
         }
     } else {
-        for (int e0 = threadIdx.x; e0 < E; e0 += 4 * 256) {
-            float gi[4], mi[4], vi[4], pi[4];
-            long long idx[4];
-            int slot[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * 256;
-                slot[u] = -1;
-                if (e < E) {
-                    const int a = e / run, i = e - a * run;
-                    int b, t;
-                    split_kk_(i, kk, b, t);
-                    slot[u] = a * ROW + b * (kk + 1) + t;
-                    idx[u] = row0 + (long long)a * rstride + i;
-                    gi[u] = jb.layout == 1 ? tile[slot[u]] : g[idx[u]];
-                    mi[u] = m[idx[u]]; vi[u] = v[idx[u]]; pi[u] = p[idx[u]];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (slot[u] >= 0) {
-                    const float gg = gi[u] * coef;
-                    const float mn = b1 * mi[u] + (1.f - b1) * gg;
-                    const float vn = b2 * vi[u] + (1.f - b2) * gg * gg;
-                    const float pn = pi[u] - step_size * (mn / (sqrtf(vn) / bc2s + eps));
-                    m[idx[u]] = mn; v[idx[u]] = vn; p[idx[u]] = pn;
-                    tile[slot[u]] = pn;
-                }
-            }
+        for (int e0 = threadIdx.x; e0 < E; e0 += 256) {
+            const int a = e0 / run, i = e0 - a * run;
+            int b, t;
+            split_kk_(i, kk, b, t);
+            const int slot = a * ROW + b * (kk + 1) + t;
+            const long long idx = row0 + (long long)a * rstride + i;
+            const float gg = (jb.layout == 1 ? tile[slot] : g[idx]) * coef;
+            const float mn = b1 * m[idx] + (1.f - b1) * gg;
+            const float vn = b2 * v[idx] + (1.f - b2) * gg * gg;
+            const float pn = p[idx] - step_size * (mn / (sqrtf(vn) / bc2s + eps));
+            m[idx] = mn; v[idx] = vn; p[idx] = pn;
+            tile[slot] = pn;
         }
     }
     __syncthreads();
@@ -429,25 +414,25 @@ __global__ void __launch_bounds__(256, 3) adam_multi_kernel(const AdamJob* __res
     const bool pair = sizeof(TD) == 2 && (d0 & 1) == 0 && (d1 & 1) == 0;      // bf16 packs: two elements per 4-byte store
     if (p01) {                                          // [t][a][b]: b fastest
         if (pair) {
-            const int tx = threadIdx.x % (AD_TB / 2), ty = threadIdx.x / (AD_TB / 2);      // 8 lanes x 4 B = one 32-byte row
+            const int tx = threadIdx.x % (TB / 2), ty = threadIdx.x / (TB / 2);
             if (2 * tx < nb)
                 for (int t = 0; t < kk; ++t)
-                    for (int a = ty; a < na; a += 256 / (AD_TB / 2)) {
+                    for (int a = ty; a < na; a += 256 / (TB / 2)) {
                         const float* src = tile + a * ROW + 2 * tx * (kk + 1) + t;
                         *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p01) + ((long long)t * d0 + a0 + a) * d1 + b0 + 2 * tx) =
                             __floats2bfloat162_rn(src[0], src[kk + 1]);
                     }
         } else {
-            const int tx = threadIdx.x % AD_TB, ty = threadIdx.x / AD_TB;
+            const int tx = threadIdx.x % TB, ty = threadIdx.x / TB;
             if (tx < nb)
                 for (int t = 0; t < kk; ++t)
-                    for (int a = ty; a < na; a += 256 / AD_TB)
+                    for (int a = ty; a < na; a += 256 / TB)
                         p01[((long long)t * d0 + a0 + a) * d1 + b0 + tx] = Cvt<TD>::from_f(tile[a * ROW + tx * (kk + 1) + t]);
         }
     }
     if (p10) {                                          // [t][b][a]: a fastest
         if (pair) {
-            const int tx = threadIdx.x % (AD_TA / 2), ty = threadIdx.x / (AD_TA / 2);      // 16 lanes x 4 B = one 64-byte row
+            const int tx = threadIdx.x % (AD_TA / 2), ty = threadIdx.x / (AD_TA / 2);
             if (2 * tx < na)
                 for (int t = 0; t < kk; ++t)
                     for (int b = ty; b < nb; b += 256 / (AD_TA / 2)) {
@@ -461,6 +446,68 @@ __global__ void __launch_bounds__(256, 3) adam_multi_kernel(const AdamJob* __res
                     for (int b = warp; b < nb; b += 8)
                         p10[((long long)t * d1 + b0 + b) * d0 + a0 + lane] = Cvt<TD>::from_f(tile[lane * ROW + b * (kk + 1) + t]);
         }
+    }
+    __syncthreads();                                    // the transpose tile is reused by the CTA's next tile
+}
+
+// One CTA per tile, five CTAs per SM (48 registers, 38 KB).  MEASURED (tools/adam_bench.py, 20.6 M parameters; the register-file
+// version with 32 x 16 tiles and 4 CTAs per SM took 195 us = 3.4 TB/s):
+//   * the same tiles through bulk copies at 3 CTAs per SM (67 KB): 195 us - and 195 us again with half the instructions or
+//     with approximate div / sqrt: neither the load path nor the instruction count was the limiter, occupancy was;
+//   * persistent CTAs (two per SM, 93 KB) walking the tile list through a 3-stage bulk-copy pipeline with the next tile's
+//     gradient prefetched into registers: 306 us (544 us with one CTA per SM).  A tile's chain - transpose store, barrier,
+//     ~850 dependent instructions of IEEE div / sqrt per thread, proxy fence, barrier, bulk stores, packs - is ~10 us long
+//     and only thread-level parallelism hides it;
+//   * 16 x 16 / 16 x 8 tiles, one per CTA: 4 CTAs per SM 170 us, 5 per SM 165 us = 4.0 TB/s (approximate div / sqrt would
+//     give 157 us; not taken - the update stays the IEEE arithmetic of svrs_clip_adam).
+template <typename TD, int OCC>
+__global__ void __launch_bounds__(256, OCC) adam_multi_kernel(const AdamJob* __restrict__ jobs, int njobs,
+                                                          float* __restrict__ p, const float* __restrict__ g,
+                                                          float* __restrict__ m, float* __restrict__ v,
+                                                          const double* __restrict__ sumsq, float max_norm, float grad_scale,
+                                                          float lr, float b1, float b2, float eps,
+                                                          const long long* __restrict__ step_ptr, const int bulk_ok) {
+    pdl_entry();
+    extern __shared__ __align__(128) float smem_f[];
+    float* tile = smem_f;
+    float* stage = smem_f + AD_PAD_FLOATS;
+    __shared__ int s_tile0[AD_MAX_JOBS];
+    __shared__ float s_coef, s_step_size, s_bc2_sqrt;
+    __shared__ __align__(8) unsigned long long s_bar;
+    const uint32_t bar = smem_u32(&s_bar);
+    for (int i = threadIdx.x; i < njobs; i += blockDim.x) s_tile0[i] = jobs[i].tile0;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const AdamTile T = adam_tile_of<TD>(jobs, s_tile0, njobs, blockIdx.x, bulk_ok);
+    // the tile's loads first: the clip coefficient (double-precision pow / sqrt on one thread) is computed while they fly
+    if (T.fast && threadIdx.x < 32) adam_issue_loads(T, stage, bar, p, m, v);
+    float gr[AD_GREGS];
+    if (T.fast && T.jb.layout == 1) { if (T.jb.kk == 9) adam_prefetch_g<9>(T, g, gr); else adam_prefetch_g<16>(T, g, gr); }
+    if (threadIdx.x == 32) {
+        float coef = grad_scale;
+        if (sumsq) {
+            float total = (float)sqrt(*sumsq) * grad_scale;
+            float c = max_norm / (total + 1e-6f);
+            coef = grad_scale * fminf(c, 1.0f);
+        }
+        double t = (double)(*step_ptr);
+        double bc1 = 1.0 - pow((double)b1, t);
+        double bc2 = 1.0 - pow((double)b2, t);
+        s_coef = coef;
+        s_step_size = (float)((double)lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    AdamConsts c;
+    c.coef = s_coef; c.step_size = s_step_size; c.bc2s = s_bc2_sqrt; c.b1 = b1; c.b2 = b2; c.eps = eps;
+    if (T.fast) {
+        if (T.jb.kk == 9) adam_tile_fast<9>(T, tile, stage, bar, 0u, gr, p, g, m, v, c);
+        else adam_tile_fast<16>(T, tile, stage, bar, 0u, gr, p, g, m, v, c);
+    } else {
+        adam_tile_generic<TD>(T, tile, p, g, m, v, c);
     }
 }
 
@@ -501,32 +548,31 @@ extern "C" int svrs_step_increment(int64_t* step_ptr, void* stream) {
 
 extern "C" int svrs_adam_job_bytes(void) { return (int)sizeof(svrs::AdamJob); }
 extern "C" int svrs_adam_tile_rows(void) { return svrs::AD_TA; }
-extern "C" int svrs_adam_tile_cols(void) { return svrs::AD_TB; }
+extern "C" int svrs_adam_tile_cols(int kk) { return svrs::ad_cols(kk); }
 
 extern "C" int svrs_adam_multi(const void* jobs, int njobs, int total_tiles, int max_kk, float* p, const float* g, float* m, float* v,
                                int pack_dtype, const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
                                float beta2, float eps, const int64_t* step_ptr, void* stream) {
     SVRS_CHECK_ARG(jobs && njobs > 0 && njobs <= svrs::AD_MAX_JOBS && total_tiles > 0 && max_kk > 0 && max_kk <= 16 && p && g && m && v && step_ptr,
                    "adam_multi: bad args (at most %d jobs)", svrs::AD_MAX_JOBS);
-    // padded transpose tile + dense m / v / p rows of the bulk path (66.7 KB at kk = 16: three CTAs per SM)
-    const int pad_floats = svrs::ad_pad_floats(max_kk);
-    size_t smem = ((size_t)pad_floats + 3u * svrs::AD_TA * svrs::AD_TB * max_kk) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     // bulk copies need 16-byte aligned rows: the flat buffers' bases (a job's offset and row pitch are checked per tile)
     static const bool no_bulk = getenv("SVRS_ADAM_BULK") && atoi(getenv("SVRS_ADAM_BULK")) == 0;
     const int bulk_ok = !no_bulk && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+    static const int occ = getenv("SVRS_ADAM_OCC") ? atoi(getenv("SVRS_ADAM_OCC")) : 5;      // CTAs per SM the bf16 kernel is compiled for
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(adam_multi_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(adam_multi_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(adam_multi_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(adam_multi_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(adam_multi_kernel<float, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(adam_multi_kernel<__nv_bfloat16, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(adam_multi_kernel<__nv_bfloat16, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     if (pack_dtype == SVRS_F32)
-        SVRS_LAUNCH((adam_multi_kernel<float>), total_tiles, 256, smem, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr, pad_floats, bulk_ok);
+        SVRS_LAUNCH((adam_multi_kernel<float, 4>), total_tiles, 256, svrs::AD_SMEM_BYTES, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr, bulk_ok);
+    else if (pack_dtype == SVRS_BF16 && occ == 5)
+        SVRS_LAUNCH((adam_multi_kernel<__nv_bfloat16, 5>), total_tiles, 256, svrs::AD_SMEM_BYTES, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr, bulk_ok);
     else if (pack_dtype == SVRS_BF16)
-        SVRS_LAUNCH((adam_multi_kernel<__nv_bfloat16>), total_tiles, 256, smem, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr, pad_floats, bulk_ok);
+        SVRS_LAUNCH((adam_multi_kernel<__nv_bfloat16, 4>), total_tiles, 256, svrs::AD_SMEM_BYTES, st, (const AdamJob*)jobs, njobs, p, g, m, v, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, (const long long*)step_ptr, bulk_ok);
     else { set_error("adam_multi: bad pack dtype"); return SVRS_E_ARG; }
     return check_launch("adam_multi");
 }

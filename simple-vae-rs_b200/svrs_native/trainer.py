@@ -178,7 +178,7 @@ class _FusedBase:
         convs = sorted(((store.offsets[store._index[id(op.mod.weight)]], op) for net in rt.nets for op in net.ops
                         if isinstance(op, ConvOp)), key=lambda t: t[0])
         rows, tile0, cur = [], 0, 0
-        tr, tc = lib.adam_tile_rows(), lib.adam_tile_cols()
+        tr = lib.adam_tile_rows()
 
         def plain(lo, hi):
             nonlocal tile0
@@ -196,6 +196,7 @@ class _FusedBase:
             else:
                 layout = lib.conv2d_wgrad_layout(rt.dt, n, h, wd, op.cin, op.cout, 3 if op.kind == "c3" else 4)
             p01, p10 = (op.pack_f, op.pack_b) if op.kind == "ct" else (op.pack_b, op.pack_f)
+            tc = lib.adam_tile_cols(op.kk)
             tiles_b = (d1 + tc - 1) // tc
             rows.append((off, p01.data_ptr(), p10.data_ptr(), d0, d1, op.kk, int(layout), tile0, tiles_b))
             tile0 += ((d0 + tr - 1) // tr) * tiles_b

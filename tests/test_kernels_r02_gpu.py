@@ -235,12 +235,13 @@ def test_adam_multi_direct(grad_layout):
                     ("layout", "<i4"), ("tile0", "<i4"), ("tiles_b", "<i4")])
     assert rec.itemsize == lib.adam_job_bytes()
     rows, off, tile0, keep = [], 0, 0, []
-    tr, tc = lib.adam_tile_rows(), lib.adam_tile_cols()
+    tr = lib.adam_tile_rows()
     for i, (d0, d1, kk) in enumerate(shapes):
         gap = 24 + 4 * i                                   # a plain range (bias-like) before every weight; keeps off % 4 == 0
         rows.append((off, 0, 0, gap, 0, 1, 0, tile0, 0)); tile0 += (gap + 2047) // 2048; off += gap
         p01 = torch.zeros(kk * d0 * d1, dtype=torch.bfloat16, device=DEV)
         p10 = torch.zeros(kk * d0 * d1, dtype=torch.bfloat16, device=DEV)
+        tc = lib.adam_tile_cols(kk)
         tiles_b = (d1 + tc - 1) // tc
         rows.append((off, p01.data_ptr(), p10.data_ptr(), d0, d1, kk, grad_layout, tile0, tiles_b))
         keep.append((off, d0, d1, kk, p01, p10))

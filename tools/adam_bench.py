@@ -60,8 +60,4 @@ print(f"clip_adam (plain stream, 28 B/param)  {us:7.1f} us  {28 * n / us / 1e6:5
 us = timeit(lambda: lib.sumsq(_p(store.grad), n, _p(tr.normacc), st()))
 print(f"sumsq                                 {us:7.1f} us  {4 * n / us / 1e6:5.2f} TB/s")
 us = timeit(multi)
-print(f"adam_multi (SVRS_ADAM_BULK={os.environ.get('SVRS_ADAM_BULK', '1')})              {us:7.1f} us  {32 * n / us / 1e6:5.2f} TB/s (32 B/param)")
-for dbg in [int(a) for a in sys.argv[1:]]:
-    os.environ["SVRS_ADAM_DBG"] = str(dbg)
-    us = timeit(multi)
-    print(f"adam_multi dbg={dbg:2d}  {us:7.1f} us")
+print(f"adam_multi (SVRS_ADAM_BULK={os.environ.get('SVRS_ADAM_BULK', '1')}, SVRS_ADAM_OCC={os.environ.get('SVRS_ADAM_OCC', '5')})   {us:7.1f} us  {32 * n / us / 1e6:5.2f} TB/s (32 B/param)")
