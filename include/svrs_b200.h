@@ -245,6 +245,9 @@ int svrs_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, cons
                    float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
                    const int64_t* step_ptr, void* stream);
 int svrs_step_increment(int64_t* step_ptr, void* stream);
+/* first launch of a fused step: ++*step_ptr and *norm_acc = 0 (the svrs_sumsq accumulator) in one kernel - a memset node
+ * between kernel nodes of a captured graph costs a ~15 us bubble (CUPTI timeline, profiles/timeline_r02.txt) */
+int svrs_step_begin(int64_t* step_ptr, double* norm_acc, void* stream);
 /* The optimiser tail of the fused step in ONE launch (csrc/optim.cu adam_multi_kernel): for every conv / convT weight the
  * gradient is read in the layout the wgrad kernel left it in (see svrs_conv2d_wgrad_layout), clip + Adam run on the
  * torch-layout fp32 master weight and moments, and the updated weight is written into both compute-dtype packs

@@ -514,6 +514,9 @@ __global__ void __launch_bounds__(256, OCC) adam_multi_kernel(const AdamJob* __r
 __global__ void step_increment_kernel(long long* s) {
     pdl_entry(); *s += 1; }
 
+__global__ void step_begin_kernel(long long* s, double* acc) {
+    pdl_entry(); *s += 1; *acc = 0.0; }
+
 }  // namespace svrs
 
 using namespace svrs;
@@ -544,6 +547,12 @@ extern "C" int svrs_step_increment(int64_t* step_ptr, void* stream) {
     SVRS_CHECK_ARG(step_ptr, "step_increment: null");
     SVRS_LAUNCH((step_increment_kernel), 1, 1, 0, (cudaStream_t)stream, (long long*)step_ptr);
     return check_launch("step_increment");
+}
+
+extern "C" int svrs_step_begin(int64_t* step_ptr, double* norm_acc, void* stream) {
+    SVRS_CHECK_ARG(step_ptr && norm_acc, "step_begin: null");
+    SVRS_LAUNCH((step_begin_kernel), 1, 1, 0, (cudaStream_t)stream, (long long*)step_ptr, norm_acc);
+    return check_launch("step_begin");
 }
 
 extern "C" int svrs_adam_job_bytes(void) { return (int)sizeof(svrs::AdamJob); }

@@ -479,10 +479,8 @@ class FusedCondTrainer(_FusedBase):
     def _step_impl(self, x, y, eps_u=None, eps_z=None):
         eng, rt, st = self.eng, self.rt, _st()
         Wz, Wu = eng.Wz, eng.Wu
-        lib.step_increment(_p(self.step_ptr), st)
-        lib.fill_zero(_p(self.normacc), 8, st)               # off the optimiser tail; _early_sumsq adds into it during backward
+        lib.step_begin(_p(self.step_ptr), _p(self.normacc), st)   # norm accumulator zeroed off the optimiser tail; _early_sumsq adds into it
         self._norm_zeroed, self._norm_segs = True, []
-        rt.launches += 1
         rt.fused_grads = self.fused_tail
         rt.zero_grads(with_scratch=True, deferred=True)
         rt.scratch_prezeroed = True
@@ -548,7 +546,8 @@ class FusedVaeTrainer(_FusedBase):
     def _step_impl(self, x, eps=None):
         eng, rt, st = self.eng, self.rt, _st()
         Wd = eng.Wd
-        lib.step_increment(_p(self.step_ptr), st)
+        lib.step_begin(_p(self.step_ptr), _p(self.normacc), st)
+        self._norm_zeroed, self._norm_segs = True, []
         rt.fused_grads = self.fused_tail
         rt.zero_grads(with_scratch=True, deferred=True)
         rt.scratch_prezeroed = True

@@ -35,7 +35,7 @@ with open(os.path.join(ROOT, "gpurun_out", "timeline.csv"), "w") as f:
     f.write("name,start_us,dur_us\n")
     for n, t0, d in rows:
         f.write(f"\"{n[:90]}\",{t0:.3f},{d:.3f}\n")
-starts = [r[1] for r in rows if "step_increment" in r[0]]
+starts = [r[1] for r in rows if "step_increment" in r[0] or "step_begin" in r[0]]
 print(len(rows), "device activities;", len(starts), "steps")
 if len(starts) >= 3:
     s0, s1 = starts[1], starts[2]
