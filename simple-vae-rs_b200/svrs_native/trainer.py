@@ -236,7 +236,7 @@ class _FusedBase:
         self._norm_zeroed = False
         # the two gammas (unclipped group, Q3) next to the big launch instead of behind it
         side = None
-        if self.world == 1 and self.early_norm:
+        if self.world == 1 and self.early_norm and rt.branch_streams:
             if self._norm_stream is None:
                 self._norm_stream = torch.cuda.Stream(device=store.grad.device)
             side = self._norm_stream
@@ -514,7 +514,7 @@ class FusedCondTrainer(_FusedBase):
         if self.world > 1 and getattr(self, "_ar_overlap", False) and not self.sync_bn:
             rt.after_phase1 = self._early_allreduce      # only while the fused step's backward runs
             rt.after_heads = self._early_allreduce if self._ar_two_buckets else None
-        elif self.world == 1 and self.early_norm and self.fused_tail:
+        elif self.world == 1 and self.early_norm and self.fused_tail and rt.branch_streams:     # (off in single-stream profiling passes)
             rt.after_phase1 = self._early_sumsq
             rt.after_heads = self._early_sumsq
         rt.join_zero_grads()
