@@ -30,6 +30,21 @@ def test_header_constants_match_host_code():
     assert int(re.search(r"#define\s+SVRS_BN_REPLICAS\s+(\d+)", hdr).group(1)) == engine.BN_REPLICAS
 
 
+def test_adam_tile_geometry_is_host_callable():
+    """The tile geometry svrs_adam_multi's job table is built with (trainer._adam_table): pure host
+    functions, callable without a GPU.  A tile's dense m / v / p rows must fit the kernel's 27 KB shared-memory stage and
+    a tile row must be a whole number of 16-byte pieces (bulk-copy granularity) for the 3x3 and 4x4 kernels."""
+    assert lib.adam_job_bytes() == 48
+    rows = lib.adam_tile_rows()
+    assert rows == 16
+    for kk in (1, 4, 9, 16):
+        cols = lib.adam_tile_cols(kk)
+        assert cols in (8, 16)
+        assert 3 * rows * cols * kk * 4 <= 27648
+    for kk in (9, 16):
+        assert (lib.adam_tile_cols(kk) * kk * 4) % 16 == 0
+
+
 def test_header_cites_reference_call_sites():
     src = open(libmod.HEADER).read()
     for cite in ("layers.py:231-236", "layers.py:275-277", "cond_vae.py:261-265", "loss/cond_vae_loss.py:39-58",
