@@ -236,6 +236,43 @@ def test_cuda_graph_replay_matches_eager(golden_dir):
     assert len(set(round(float(v), 3) for v in res[1][:, 1])) == 4     # KL(u) changes: noise + weights move
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_early_gradient_norm_equals_single_pass(golden_dir, dtype):
+    """clip_grad_norm_ (models/base.py:106) needs the norm of ALL gradients.  The fused step accumulates the squared norm
+    of the groups whose backward pass is complete (prior heads + u_to_z, decoders) on a side stream while the encoders'
+    backward still runs (FusedCondTrainer._early_sumsq) and only the rest in the optimiser tail: the total must equal the
+    single svrs_sumsq pass over the whole flat gradient, eagerly and under CUDA-graph replay, and so must the parameters."""
+    from svrs_native.trainer import FusedCondTrainer
+    fx = FX.load(golden_dir, "cond_cr2_p64_b2")
+    x, y = FX.inputs(fx)
+    x, y = x.to(DEV), y.to(DEV)
+    norms, flats, used = [], [], []
+    for early in (True, False):
+        model, _ = FX.build(fx, device=DEV, dtype=dtype)
+        model.train()
+        tr = FusedCondTrainer(model)
+        tr.early_norm = early
+        tr.eng.rng.seed = 77
+        n = []
+        for i in range(4):
+            tr.step(x, y, use_graph=i >= 1)
+            n.append(tr.normacc.clone())
+        used.append(tr._norm_stream is not None)
+        norms.append(torch.cat(n).cpu())
+        flats.append(tr.rt.store.flat.clone())
+    assert used == [True, False]
+    print("[parity] squared gradient norms, early vs single pass:", norms[0].tolist(), norms[1].tolist())
+    # Step 1 starts from identical weights: same kernels, same gradients up to the order of the fp32 weight-gradient atomics,
+    # double accumulation either way.  Later steps start from parameters that may differ where a noise-level gradient flipped
+    # the sign of Adam's first updates (by at most 2 * lr per step, see test_fused_tail_equals_separate_kernels).
+    f32 = dtype == torch.float32
+    report("squared norm, step 1: early partial sums vs single pass", norms[0][:1], norms[1][:1], 1e-5 if f32 else 2e-4)
+    report("squared norms, steps 2-4 (graph replay)", norms[0][1:], norms[1][1:], 1e-3 if f32 else 2e-2)
+    # measured: fp32 2e-9 / 2e-6 / |dp| 6e-5; bf16 1.5e-5 / 1.3e-3 / |dp| 7e-4 (every Adam step moves a parameter by <= lr = 1e-4
+    # per step in either direction)
+    report("parameters after 4 steps", flats[0], flats[1], 0.0, atol=4 * 2e-4 * 1.05 if f32 else 2e-3)
+
+
 def test_fit_runs_one_epoch_like_reference_tests(monkeypatch, tmp_path):
     """tests/test_training.py of the reference, on the CUDA device."""
     import models.base as base_module
