@@ -72,12 +72,9 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
 //     [kk][d0][d1] and [kk][d1][d0] that the next step's fprop / dgrad kernels consume.
 //     This replaces unpack_multi + clip_adam + pack_multi (three passes over 82 MB each) by one.
 //     Full tiles of the 3x3 / 4x4 layers (all but a few hundred parameters) move m / v / p with 1-D BULK copies
-//     (cp.async.bulk + mbarrier): the tile's 16 rows of each array - contiguous runs of 16*kk floats in the torch layout -
+//     (cp.async.bulk + mbarrier): the tile's 16 rows of each array - contiguous runs of cols*kk floats in the torch layout -
 //     land in shared memory, Adam runs in place there, and the rows leave as bulk stores again while the threads write
-//     the packs.  MEASURED (tools/adam_bench.py, 20.6 M parameters): register-file loads (float4 LDG, 8 in flight per
-//     thread, 4 CTAs per SM) cap this kernel at 195 us = 3.4 TB/s whatever the instruction count (a version with half
-//     the instructions and one with approximate div / sqrt ran at the same 195 us; reads alone, all stores removed, took
-//     105-123 us) - the same ceiling bn_reduce hit before it went to bulk copies.
+//     the packs (measurements in front of the kernel below).
 //   * plain jobs (d1 == 0): biases and BatchNorm affine parameters, d0 contiguous elements from `off`.
 // p / g / m / v are the flat buffers; a job addresses all four at the same element offset.
 // ------------------------------------------------------------------------------------------------------------------
