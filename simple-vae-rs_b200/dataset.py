@@ -6,14 +6,19 @@ twin) becomes 16 patches of 64x64 (32x32), patch index = row*4 + col, each patch
 batches ordered tile-major.  Here that is ONE kernel launch per tensor (svrs_grid_patch_normalize, one CTA per
 patch, bit-exact fp32) instead of CPU slicing in DataLoader workers.
 
-The GeoTIFF / CSV reading of the reference's Sen2VenDataset (:49-218, tifffile + polars) is disk IO outside the
-hot-path scope; `TileDataset` wraps tiles that are already in memory (decoded by any reader) and
-`synthetic_tiles` produces the multispectral test tiles used by the benchmark.
+The GeoTIFF / CSV reading of the reference's Sen2VenDataset / FloodDataset (:49-218, tifffile + polars) is host-side IO
+in front of the hot path: `load_sen2venus_tiles` / `load_flood_patches` decode the files ONCE into an in-memory tile pool
+(tiff_reader.imread: `tifffile` when installed, else a numpy restatement of the baseline TIFF decode; the index is a plain
+tab-separated file), `TileDataset` wraps tiles that are already in memory and `synthetic_tiles` produces the multispectral
+test tiles used by the benchmark.
 """
 from __future__ import annotations
 
+import csv
+import os
 from typing import Iterator, Optional, Tuple
 
+import numpy as np
 import torch
 
 
@@ -133,6 +138,86 @@ class TileDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, i):
         return self.lr[i], self.hr[i]
+
+
+def _as_chw(img: np.ndarray, path: str) -> np.ndarray:
+    """tifffile returns [S, H, W] for band-sequential files and [H, W, S] for pixel-interleaved ones; the reference indexes
+    tiles as [C, H, W] (dataset.py:70, 205)."""
+    if img.ndim == 2:
+        return img[None]
+    if img.ndim != 3:
+        raise ValueError(f"{path}: expected a 2-D or 3-D image, got shape {img.shape}")
+    if img.shape[0] > 16 and img.shape[2] <= 16:          # [H, W, S] -> [S, H, W]
+        return np.ascontiguousarray(img.transpose(2, 0, 1))
+    return img
+
+
+def load_sen2venus_tiles(dataset: str = "ARM", root: Optional[str] = None, limit: Optional[int] = None) -> TileDataset:
+    """The reference's Sen2VenDataset file handling (dataset.py:99-113, 165-174) as a one-off decode into a tile pool:
+    `<root or cwd>/<dataset>/index.csv` (tab-separated, header row) lists one tile pair per row in the columns
+    `b2b3b4b8_10m` (LR, [4, S/2, S/2]) and `b2b3b4b8_05m` (HR, [4, S, S]), paths relative to the dataset directory
+    (bands="visu", the only implemented choice, :107-110).  Row order is kept (the 80 / 20 split of init_dataloader is by
+    index, :31-33).  int16 files stay int16 in the pool (the patch gather converts on the fly); anything else becomes fp32
+    as in the reference (:154-155)."""
+    import tiff_reader
+    base = os.path.join(root if root is not None else os.getcwd(), dataset)
+    index = os.path.join(base, "index.csv")
+    if not os.path.isfile(index):
+        raise FileNotFoundError(f"Sen2Venus index not found: {index} (the reference reads <cwd>/{dataset}/index.csv, dataset.py:99-101)")
+    with open(index, newline="") as f:
+        rows = list(csv.DictReader(f, delimiter="\t"))
+    p0, p1 = "b2b3b4b8_10m", "b2b3b4b8_05m"
+    if rows and (p0 not in rows[0] or p1 not in rows[0]):
+        raise KeyError(f"{index}: columns {p0!r} and {p1!r} are required (bands='visu', dataset.py:107-110)")
+    if limit is not None:
+        rows = rows[:limit]
+    if not rows:
+        raise ValueError(f"{index}: no tile pairs listed")
+    lr, hr = [], []
+    for r in rows:
+        a = _as_chw(tiff_reader.imread(os.path.join(base, r[p0])), r[p0])
+        b = _as_chw(tiff_reader.imread(os.path.join(base, r[p1])), r[p1])
+        if b.shape[0] != a.shape[0] or b.shape[1] != 2 * a.shape[1] or b.shape[2] != 2 * a.shape[2]:
+            raise ValueError(f"{r[p0]} {a.shape} / {r[p1]} {b.shape}: the HR tile must be twice the LR tile (same-origin crops, dataset.py:205-216)")
+        lr.append(a)
+        hr.append(b)
+    keep_i16 = all(t.dtype == np.int16 for t in lr + hr)
+
+    def stack(ts):
+        t = torch.from_numpy(np.stack(ts))
+        return t if keep_i16 else t.to(torch.float32)
+
+    return TileDataset(stack(lr), stack(hr))
+
+
+def load_flood_patches(root: str = "/scratch/disc/e.bardet/Simple-VAE-RS/floods", patch_size: int = 256) -> torch.Tensor:
+    """The reference's FloodDataset.precompute_patches (dataset.py:56-93) on the CPU, once: every `<root>/<event>/S2/*.tif`
+    (all bands) is cut into non-overlapping patch_size^2 patches, each scaled per band to its own [1 %, 99 %] quantile range
+    `(p - q01) / (q99 - q01 + 1e-5)`, clipped to [0, 1]; patches containing NaN are dropped.  -> fp32 [N, C, P, P]."""
+    import tiff_reader
+    if not os.path.isdir(root):
+        raise FileNotFoundError(f"flood tiles not found: {root} (dataset.py:57)")
+    patches = []
+    for event in os.listdir(root):
+        s2 = os.path.join(root, event, "S2")
+        if not os.path.isdir(s2):
+            continue
+        for name in os.listdir(s2):
+            if not name.endswith(".tif"):
+                continue
+            img = _as_chw(tiff_reader.imread(os.path.join(s2, name)), name)
+            height, width = img.shape[1], img.shape[2]
+            for row in range(0, height - patch_size + 1, patch_size):
+                for col in range(0, width - patch_size + 1, patch_size):
+                    patch = img[:, row:row + patch_size, col:col + patch_size]
+                    q = np.quantile(patch, [0.01, 0.99], axis=(1, 2), keepdims=True)
+                    patch = np.clip((patch - q[0]) / (q[1] - q[0] + 1e-5), 0, 1)
+                    patch = torch.tensor(patch, dtype=torch.float32)
+                    if not torch.isnan(patch).any():
+                        patches.append(patch)
+    if not patches:
+        raise ValueError(f"{root}: no <event>/S2/*.tif tiles of at least {patch_size} x {patch_size} pixels")
+    return torch.stack(patches)
 
 
 class TilePrefetcher:
@@ -315,22 +400,59 @@ class RandomCropLoader:
             yield y, x
 
 
+class PatchTensorLoader:
+    """DataLoader(FloodDataset, batch_size, shuffle) of the reference (dataset.py:27-46): batches of the precomputed,
+    already normalised patches [b, C, P, P], as single tensors (the reference's FloodDataset yields no LR / HR pair).  The
+    patch pool lives on `device`; under torchrun every rank keeps its contiguous share of each global batch."""
+
+    def __init__(self, patches: torch.Tensor, batch_size: int, device="cuda", shuffle: bool = False, seed: int = 0,
+                 rank: int = 0, world: int = 1):
+        self.x, self.bs, self.shuffle = patches.to(device), batch_size, shuffle
+        self._gen = torch.Generator().manual_seed(seed)
+        self.rank, self.world = rank, world
+
+    def __len__(self):
+        return -(-self.x.shape[0] // self.bs)
+
+    def __iter__(self):
+        from svrs_native.parallel import shard_bounds
+        n = self.x.shape[0]
+        order = torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
+        for i in range(0, n, self.bs):
+            idx = order[i:i + self.bs]
+            m = len(idx) // self.world * self.world
+            if m == 0:
+                continue
+            lo, hi = shard_bounds(m, self.rank, self.world)
+            yield self.x[idx[lo:hi].to(self.x.device)]
+
+
 def init_dataloader(dataset: str, batch_size: int = 16, patch_size: int = 64, device="cuda", n_tiles: int = 64,
                     crop: str = "random", seed: int = 0):
-    """Same entry point as the reference (dataset.py:13-47): returns (train_loader, val_loader), 80 / 20 split, batches
-    are (y, x) = (LR, HR) patch tensors.  `crop="random"` (the reference's only reachable mode, dataset.py:24): batch_size
-    counts crops, exactly as in the reference; `crop="grid"`: every tile yields its (256/P)^2 grid patches and batch_size
-    (in patches) is rounded DOWN to whole tiles (at least one).  Under torchrun the loaders shard every global batch by
-    rank (see the loader classes).  `synthetic` builds in-memory multispectral tiles; the Sen2Venus / flood datasets need
-    the reference's GeoTIFF readers (tifffile / polars, not installed here and outside the hot-path scope): decode tiles
-    with the reference's reader and wrap them in TileDataset + RandomCropLoader."""
-    if dataset != "synthetic":
-        raise NotImplementedError(
-            f"dataset '{dataset}': GeoTIFF decoding (tifffile/polars) is outside the hot-path scope of svrs_b200; "
-            "decode tiles with the reference's reader and wrap them in TileDataset, or use --dataset synthetic")
+    """Same entry point as the reference (dataset.py:13-47): returns (train_loader, val_loader), 80 / 20 split by index,
+    batches are (y, x) = (LR, HR) patch tensors.  `crop="random"` (the reference's only reachable mode, dataset.py:24):
+    batch_size counts crops, exactly as in the reference; `crop="grid"`: every tile yields its (256/P)^2 grid patches and
+    batch_size (in patches) is rounded DOWN to whole tiles (at least one).  Under torchrun the loaders shard every global
+    batch by rank (see the loader classes).  Datasets, named as in the reference (:23-29): "Sen2Venus" / "sen2venus" / "s2v"
+    = the tile pairs listed in <cwd>/ARM/index.csv, decoded once into a device-resident tile pool (load_sen2venus_tiles);
+    "Floods" / "floods" = the reference's quantile-normalised 256^2 flood patches (load_flood_patches, single tensors);
+    "synthetic" (not in the reference) = in-memory multispectral test tiles."""
     rank, world = _dist_info()
-    lr, hr = synthetic_tiles(n_tiles)
-    split = max(1, int(0.8 * n_tiles))
+    if dataset in ("Floods", "floods"):
+        patches = load_flood_patches(patch_size=256)                  # dataset.py:27: always 256
+        split = int(0.8 * patches.shape[0])
+        return (PatchTensorLoader(patches[:split], batch_size, device, shuffle=True, seed=seed, rank=rank, world=world),
+                PatchTensorLoader(patches[split:], batch_size, device, shuffle=False))
+    if dataset in ("Sen2Venus", "sen2venus", "s2v"):
+        tiles = load_sen2venus_tiles()
+        lr, hr = tiles.lr, tiles.hr
+        n_tiles = lr.shape[0]
+        split = int(0.8 * n_tiles)                                    # dataset.py:31
+    elif dataset == "synthetic":
+        lr, hr = synthetic_tiles(n_tiles)
+        split = max(1, int(0.8 * n_tiles))
+    else:
+        raise ValueError(f"Unknown dataset: {dataset}")               # dataset.py:29-30
     tr_ds, va_ds = TileDataset(lr[:split], hr[:split]), TileDataset(lr[split:], hr[split:])
     if crop == "random":
         train = RandomCropLoader(tr_ds, batch_size, patch_size, device, shuffle=True, seed=seed, rank=rank, world=world)
