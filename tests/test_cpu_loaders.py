@@ -57,3 +57,23 @@ def test_grid_loader_shards_tiles_by_rank():
         raise AssertionError("uneven split must be refused")
     except ValueError:
         pass
+
+
+def test_patch_tensor_loader_shards_and_order():
+    """PatchTensorLoader (the reference's DataLoader over FloodDataset, dataset.py:27-46): unshuffled batches in index order
+    incl. the ragged last one; under `world` ranks the shards of every global batch are equal, contiguous, and their union
+    is the single-process batch trimmed to a multiple of the world size."""
+    x = torch.arange(23, dtype=torch.float32).reshape(23, 1, 1, 1).expand(23, 2, 4, 4).contiguous()
+    plain = list(D.PatchTensorLoader(x, 5, device="cpu"))
+    assert len(plain) == len(D.PatchTensorLoader(x, 5, device="cpu")) == 5
+    assert torch.equal(torch.cat(plain), x) and plain[-1].shape[0] == 3
+    single = list(D.PatchTensorLoader(x, 6, device="cpu", shuffle=True, seed=4))
+    assert sorted(torch.cat(single)[:, 0, 0, 0].tolist()) == list(range(23))          # a permutation: every patch once
+    for world in (2, 3):
+        ranks = [list(D.PatchTensorLoader(x, 6, device="cpu", shuffle=True, seed=4, rank=r, world=world)) for r in range(world)]
+        assert len({len(b) for b in ranks}) == 1
+        for step in range(len(ranks[0])):
+            parts = [ranks[r][step] for r in range(world)]
+            assert len({p.shape[0] for p in parts}) == 1
+            n = sum(p.shape[0] for p in parts)
+            assert torch.equal(torch.cat(parts), single[step][:n])
