@@ -170,7 +170,13 @@ def decode(buf: bytes) -> np.ndarray:
         offsets, counts = t[T_TILE_OFFSETS], t[T_TILE_COUNTS]
     else:
         cw, ch = W, min(int(one(T_ROWS_PER_STRIP, H)), H)
-        offsets, counts = t[T_STRIP_OFFSETS], t[T_STRIP_COUNTS]
+        if T_STRIP_OFFSETS not in t:
+            raise TiffError("neither strips nor tiles")
+        offsets = t[T_STRIP_OFFSETS]
+        counts = t.get(T_STRIP_COUNTS)
+        if counts is None:                              # some writers omit StripByteCounts: every strip runs to the next one
+            ends = sorted(offsets) + [len(buf)]
+            counts = tuple(ends[ends.index(o) + 1] - o for o in offsets)
     across, down = -(-W // cw), -(-H // ch)
     if len(offsets) != across * down * planes or len(counts) != len(offsets):
         raise TiffError(f"expected {across * down * planes} chunks, the file lists {len(offsets)}")

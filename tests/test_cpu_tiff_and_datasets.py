@@ -125,6 +125,15 @@ def test_decode_multiband_int16(planar, layout, big, bo):
         assert np.array_equal(got, want), (planar, layout, big, bo, deflate, predictor)
 
 
+def test_decode_without_strip_byte_counts():
+    """StripByteCounts is omitted by some old writers; uncompressed strips then run up to the next strip (or the end)."""
+    a = np.arange(4 * 20 * 12, dtype=np.int16).reshape(4, 20, 12)
+    f = bytearray(write_tiff(a, True, rows_per_strip=7))
+    i = bytes(f).index(struct.pack("<HH", 279, 4))       # StripByteCounts entry -> an unknown private tag
+    f[i:i + 2] = struct.pack("<H", 65000)
+    assert np.array_equal(tiff_reader.decode(bytes(f)), a)
+
+
 def test_decode_rejects_what_it_does_not_implement():
     a = np.zeros((8, 8), np.uint8)
     f = bytearray(write_tiff(a, False))
